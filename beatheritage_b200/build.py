@@ -1,0 +1,55 @@
+"""In-tree build of libbhmel.so (nvcc, sm_100a only).  `python -m beatheritage_b200.build`.
+
+The library is written next to this file so it travels with the repo snapshot to the GPU box
+(built artefacts are git-ignored, not gpurun-ignored)."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "libbhmel.so")
+GEN = os.path.join(CSRC, "fft32_gen.h")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v",
+]
+
+
+def _newer(target: str, sources: list[str]) -> bool:
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def generate() -> str:
+    gen_py = os.path.join(CSRC, "gen_fft32.py")
+    if not _newer(GEN, [gen_py]):
+        out = subprocess.run([sys.executable, gen_py], check=True, capture_output=True, text=True).stdout
+        with open(GEN, "w") as f:
+            f.write(out)
+    return GEN
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    generate()
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".py"))]
+    srcs.append(os.path.join(os.path.dirname(PKG), "include", "bhmel.h"))
+    if not force and _newer(LIB, srcs):
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, os.path.join(CSRC, "bhmel.cu")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed building libbhmel.so")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,316 @@
+// libbhmel.so -- C ABI implementation (see include/bhmel.h for the contract and the reference
+// file:line each entry point replaces).
+#include "../../include/bhmel.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "bhmel_kernel.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define BH_CUDA(call)                                                                        \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess)                                                                  \
+      return fail(BHMEL_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));         \
+  } while (0)
+
+constexpr int kHostSlots = 3;
+
+}  // namespace
+
+struct bhmel_handle {
+  int device = 0;
+  int num_sms = 0;
+  bhmel_params prm{};
+  std::vector<float> fb;       // host copy [513][n_mels]
+  std::vector<float> window;   // host copy [1024]
+  float* d_win = nullptr;      // 0.5 * window
+  float2* d_tw = nullptr;
+  bhmel::FilterBand* d_bands = nullptr;
+  float* d_weights = nullptr;
+  std::atomic<int64_t> launches{0};
+  // bhmel_forward_host pipeline (lazily created)
+  std::mutex host_mu;
+  cudaStream_t hs[kHostSlots] = {nullptr, nullptr, nullptr};
+  float* d_in[kHostSlots] = {nullptr, nullptr, nullptr};
+  float* d_out[kHostSlots] = {nullptr, nullptr, nullptr};
+  size_t cap_in = 0, cap_out = 0;
+};
+
+namespace {
+
+int upload_filterbank(bhmel_handle* h) {
+  bhmel::BandTables t = bhmel::make_bands(h->fb.data(), h->prm.n_mels);
+  // The tables may be in use by kernels in flight on any stream of this device.
+  BH_CUDA(cudaDeviceSynchronize());
+  if (h->d_bands) cudaFree(h->d_bands);
+  if (h->d_weights) cudaFree(h->d_weights);
+  h->d_bands = nullptr;
+  h->d_weights = nullptr;
+  BH_CUDA(cudaMalloc(&h->d_bands, t.bands.size() * sizeof(bhmel::FilterBand)));
+  BH_CUDA(cudaMalloc(&h->d_weights, t.weights.size() * sizeof(float)));
+  BH_CUDA(cudaMemcpy(h->d_bands, t.bands.data(), t.bands.size() * sizeof(bhmel::FilterBand),
+                     cudaMemcpyHostToDevice));
+  BH_CUDA(cudaMemcpy(h->d_weights, t.weights.data(), t.weights.size() * sizeof(float),
+                     cudaMemcpyHostToDevice));
+  return BHMEL_OK;
+}
+
+int upload_window(bhmel_handle* h) {
+  std::vector<float> half(bhmel::kNfft);
+  for (int i = 0; i < bhmel::kNfft; ++i) half[i] = 0.5f * h->window[i];   // exact scaling
+  BH_CUDA(cudaDeviceSynchronize());
+  if (!h->d_win) BH_CUDA(cudaMalloc(&h->d_win, bhmel::kNfft * sizeof(float)));
+  BH_CUDA(cudaMemcpy(h->d_win, half.data(), bhmel::kNfft * sizeof(float), cudaMemcpyHostToDevice));
+  return BHMEL_OK;
+}
+
+int check_device(const bhmel_handle* h) {
+  int dev = -1;
+  BH_CUDA(cudaGetDevice(&dev));
+  if (dev != h->device)
+    return fail(BHMEL_EDEVICE, "handle was created on device " + std::to_string(h->device) +
+                                   " but the current device is " + std::to_string(dev));
+  return BHMEL_OK;
+}
+
+int launch(bhmel_handle* h, const float* x, long long row_stride, long long row0, long long n_total,
+           long long B, long long N, float* y, cudaStream_t stream) {
+  if (!h) return fail(BHMEL_EINVAL, "null handle");
+  if (!x || !y) return fail(BHMEL_EINVAL, "null data pointer");
+  if (B <= 0 || N <= 0) return fail(BHMEL_ESHAPE, "batch and sample count must be positive");
+  if (B > INT_MAX) return fail(BHMEL_ESHAPE, "batch too large");
+  if (h->prm.pad_mode == BHMEL_PAD_REFLECT && N <= bhmel::kNfft / 2)
+    return fail(BHMEL_ESHAPE,
+                "reflect padding needs more than n_fft/2 = 512 samples per row (got " +
+                    std::to_string(N) + "); torch.nn.functional.pad raises for the reference too");
+  if (int rc = check_device(h)) return rc;
+
+  bhmel::KParams p{};
+  p.x = x;
+  p.row_stride = row_stride;
+  p.row0 = row0;
+  p.n_total = n_total;
+  p.N = N;
+  p.T = N / bhmel::kHop + 1;
+  p.tiles_per_row = static_cast<int>((p.T + bhmel::kTileF - 1) / bhmel::kTileF);
+  p.n_tiles = static_cast<long long>(p.tiles_per_row) * B;
+  p.y = y;
+  p.win_half = h->d_win;
+  p.tw = h->d_tw;
+  p.bands = h->d_bands;
+  p.weights = h->d_weights;
+  p.B = static_cast<int>(B);
+  p.n_mels = h->prm.n_mels;
+  p.pad_reflect = h->prm.pad_mode == BHMEL_PAD_REFLECT;
+  p.log_scale = h->prm.log_scale != 0;
+  static const bool no_bulk = std::getenv("BHMEL_NO_BULK") != nullptr;   // debugging aid
+  p.use_bulk = no_bulk ? 0 : 1;
+
+  const long long grid = p.n_tiles < h->num_sms ? p.n_tiles : h->num_sms;
+  bhmel::bhmel_logmel_kernel<<<static_cast<unsigned>(grid), bhmel::kThreads, sizeof(bhmel::SmemLayout),
+                               stream>>>(p);
+  BH_CUDA(cudaGetLastError());
+  h->launches.fetch_add(1, std::memory_order_relaxed);
+  return BHMEL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bhmel_version(void) { return BHMEL_VERSION; }
+
+const char* bhmel_last_error(void) { return g_err.c_str(); }
+
+void bhmel_kernel_info(int32_t* smem_bytes, int32_t* threads, int32_t* tile_frames) {
+  if (smem_bytes) *smem_bytes = static_cast<int32_t>(sizeof(bhmel::SmemLayout));
+  if (threads) *threads = bhmel::kThreads;
+  if (tile_frames) *tile_frames = bhmel::kTileF;
+}
+
+int bhmel_create(const bhmel_params* prm, bhmel_handle** out) {
+  if (!prm || !out) return fail(BHMEL_EINVAL, "null argument");
+  *out = nullptr;
+  if (prm->n_fft != bhmel::kNfft || prm->hop_length != bhmel::kHop)
+    return fail(BHMEL_EINVAL, "only n_fft=1024 / hop_length=128 are compiled in (constant in every "
+                              "reference config); got n_fft=" + std::to_string(prm->n_fft) +
+                                  " hop_length=" + std::to_string(prm->hop_length));
+  if (prm->n_mels < 1 || prm->n_mels > 1024) return fail(BHMEL_EINVAL, "n_mels must be in [1, 1024]");
+  if (prm->pad_mode != BHMEL_PAD_CONSTANT && prm->pad_mode != BHMEL_PAD_REFLECT)
+    return fail(BHMEL_EINVAL, "pad_mode must be BHMEL_PAD_CONSTANT or BHMEL_PAD_REFLECT");
+  if (prm->sample_rate <= 0) return fail(BHMEL_EINVAL, "sample_rate must be positive");
+  if (!prm->fb && !(prm->f_max > prm->f_min && prm->f_min >= 0))
+    return fail(BHMEL_EINVAL, "need 0 <= f_min < f_max");
+
+  int dev = 0;
+  BH_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop{};
+  BH_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return fail(BHMEL_EDEVICE, std::string("libbhmel is built for sm_100a only; device is ") + prop.name +
+                                   " (sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+  BH_CUDA(cudaFuncSetAttribute(bhmel::bhmel_logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(sizeof(bhmel::SmemLayout))));
+
+  bhmel_handle* h = new bhmel_handle();
+  h->device = dev;
+  h->num_sms = prop.multiProcessorCount;
+  h->prm = *prm;
+  h->prm.fb = nullptr;
+  h->prm.window = nullptr;
+  const size_t fb_elems = static_cast<size_t>(bhmel::kBins) * prm->n_mels;
+  if (prm->fb) h->fb.assign(prm->fb, prm->fb + fb_elems);
+  else h->fb = bhmel::make_mel_fb(prm->n_mels, prm->f_min, prm->f_max, prm->sample_rate);
+  if (prm->window) h->window.assign(prm->window, prm->window + bhmel::kNfft);
+  else h->window = bhmel::make_hann_window();
+
+  auto cleanup = [&](int rc) {
+    bhmel_destroy(h);
+    return rc;
+  };
+  std::vector<float> tw = bhmel::make_twiddles();
+  cudaError_t e = cudaMalloc(&h->d_tw, tw.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_tw, tw.data(), tw.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return cleanup(fail(BHMEL_ECUDA, std::string("twiddle upload: ") + cudaGetErrorString(e)));
+  if (int rc = upload_window(h)) return cleanup(rc);
+  if (int rc = upload_filterbank(h)) return cleanup(rc);
+  *out = h;
+  return BHMEL_OK;
+}
+
+void bhmel_destroy(bhmel_handle* h) {
+  if (!h) return;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(h->device);
+  for (int i = 0; i < kHostSlots; ++i) {
+    if (h->hs[i]) {
+      cudaStreamSynchronize(h->hs[i]);
+      cudaStreamDestroy(h->hs[i]);
+    }
+    if (h->d_in[i]) cudaFree(h->d_in[i]);
+    if (h->d_out[i]) cudaFree(h->d_out[i]);
+  }
+  if (h->d_win) cudaFree(h->d_win);
+  if (h->d_tw) cudaFree(h->d_tw);
+  if (h->d_bands) cudaFree(h->d_bands);
+  if (h->d_weights) cudaFree(h->d_weights);
+  if (prev >= 0) cudaSetDevice(prev);
+  delete h;
+}
+
+int bhmel_set_fb(bhmel_handle* h, const float* fb_host) {
+  if (!h || !fb_host) return fail(BHMEL_EINVAL, "null argument");
+  if (int rc = check_device(h)) return rc;
+  h->fb.assign(fb_host, fb_host + static_cast<size_t>(bhmel::kBins) * h->prm.n_mels);
+  return upload_filterbank(h);
+}
+
+int bhmel_set_window(bhmel_handle* h, const float* window_host) {
+  if (!h || !window_host) return fail(BHMEL_EINVAL, "null argument");
+  if (int rc = check_device(h)) return rc;
+  h->window.assign(window_host, window_host + bhmel::kNfft);
+  return upload_window(h);
+}
+
+int bhmel_get_fb(const bhmel_handle* h, float* fb_host) {
+  if (!h || !fb_host) return fail(BHMEL_EINVAL, "null argument");
+  std::memcpy(fb_host, h->fb.data(), h->fb.size() * sizeof(float));
+  return BHMEL_OK;
+}
+
+int bhmel_get_window(const bhmel_handle* h, float* window_host) {
+  if (!h || !window_host) return fail(BHMEL_EINVAL, "null argument");
+  std::memcpy(window_host, h->window.data(), h->window.size() * sizeof(float));
+  return BHMEL_OK;
+}
+
+int64_t bhmel_num_frames(const bhmel_handle* h, int64_t n_samples) {
+  (void)h;
+  return n_samples < 0 ? 0 : n_samples / bhmel::kHop + 1;
+}
+
+int64_t bhmel_launch_count(const bhmel_handle* h) { return h ? h->launches.load() : 0; }
+
+int bhmel_forward(bhmel_handle* h, const float* x, int64_t B, int64_t N, int64_t x_row_stride, float* y,
+                  void* stream) {
+  if (x_row_stride < N) return fail(BHMEL_EINVAL, "x_row_stride must be >= N");
+  return launch(h, x, x_row_stride, 0, LLONG_MAX, B, N, y, static_cast<cudaStream_t>(stream));
+}
+
+int bhmel_forward_gather(bhmel_handle* h, const float* song, int64_t n_song, int64_t first_offset,
+                         int64_t stride, int64_t W, int64_t window_len, float* y, void* stream) {
+  if (n_song < 0 || first_offset < 0 || stride <= 0)
+    return fail(BHMEL_EINVAL, "need n_song >= 0, first_offset >= 0, stride > 0");
+  return launch(h, song, stride, first_offset, n_song, W, window_len, y, static_cast<cudaStream_t>(stream));
+}
+
+int bhmel_forward_host(bhmel_handle* h, const float* x_host, int64_t B, int64_t N, int64_t x_row_stride,
+                       float* y_host) {
+  if (!h) return fail(BHMEL_EINVAL, "null handle");
+  if (!x_host || !y_host) return fail(BHMEL_EINVAL, "null data pointer");
+  if (B <= 0 || N <= 0) return fail(BHMEL_ESHAPE, "batch and sample count must be positive");
+  if (x_row_stride < N) return fail(BHMEL_EINVAL, "x_row_stride must be >= N");
+  if (int rc = check_device(h)) return rc;
+  std::lock_guard<std::mutex> lock(h->host_mu);
+
+  const int64_t T = N / bhmel::kHop + 1;
+  const size_t row_in = static_cast<size_t>(N) * sizeof(float);
+  const size_t row_out = static_cast<size_t>(T) * h->prm.n_mels * sizeof(float);
+  // ~32 MB of input per chunk keeps three chunks in flight (H2D / kernel / D2H) with small tails.
+  int64_t rows = static_cast<int64_t>((32u << 20) / row_in);
+  if (rows < 1) rows = 1;
+  if (rows > B) rows = B;
+  if (rows * 2 > B && B >= 2 * kHostSlots) rows = (B + 2 * kHostSlots - 1) / (2 * kHostSlots);
+  const size_t need_in = static_cast<size_t>(rows) * row_in, need_out = static_cast<size_t>(rows) * row_out;
+  for (int i = 0; i < kHostSlots; ++i) {
+    if (!h->hs[i]) BH_CUDA(cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking));
+  }
+  if (need_in > h->cap_in || need_out > h->cap_out) {
+    for (int i = 0; i < kHostSlots; ++i) {
+      BH_CUDA(cudaStreamSynchronize(h->hs[i]));
+      if (h->d_in[i]) cudaFree(h->d_in[i]);
+      if (h->d_out[i]) cudaFree(h->d_out[i]);
+      h->d_in[i] = h->d_out[i] = nullptr;
+    }
+    h->cap_in = h->cap_out = 0;
+    for (int i = 0; i < kHostSlots; ++i) {
+      BH_CUDA(cudaMalloc(&h->d_in[i], need_in));
+      BH_CUDA(cudaMalloc(&h->d_out[i], need_out));
+    }
+    h->cap_in = need_in;
+    h->cap_out = need_out;
+  }
+  int slot = 0;
+  for (int64_t b0 = 0; b0 < B; b0 += rows, slot = (slot + 1) % kHostSlots) {
+    const int64_t nb = (B - b0) < rows ? (B - b0) : rows;
+    cudaStream_t s = h->hs[slot];
+    BH_CUDA(cudaMemcpy2DAsync(h->d_in[slot], row_in, x_host + b0 * x_row_stride,
+                              static_cast<size_t>(x_row_stride) * sizeof(float), row_in,
+                              static_cast<size_t>(nb), cudaMemcpyHostToDevice, s));
+    if (int rc = launch(h, h->d_in[slot], N, 0, LLONG_MAX, nb, N, h->d_out[slot], s)) return rc;
+    BH_CUDA(cudaMemcpyAsync(y_host + static_cast<size_t>(b0) * T * h->prm.n_mels, h->d_out[slot],
+                            static_cast<size_t>(nb) * row_out, cudaMemcpyDeviceToHost, s));
+  }
+  for (int i = 0; i < kHostSlots; ++i) BH_CUDA(cudaStreamSynchronize(h->hs[i]));
+  return BHMEL_OK;
+}
+
+}  // extern "C"

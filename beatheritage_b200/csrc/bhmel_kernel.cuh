@@ -1,0 +1,301 @@
+// bhmel_kernel.cuh -- the fused log-mel kernel for sm_100a.
+//
+// Replaces, in ONE launch, what the reference reaches through
+// osuT5/osuT5/model/spectrogram.py:79-82 (transform -> log1p -> permute), i.e.
+// F.pad(reflect|constant) -> torch.stft (frame gather * Hann, 1024-pt rFFT) -> |X|^2 ->
+// matmul(fb) -> log1p -> [B, T, n_mels]   (SURVEY.md 8a rows a2..a9).
+//
+// Work decomposition
+//   tile        = 32 consecutive frames of one input row (window); persistent CTAs (one per SM)
+//                 walk tiles with a static stride.
+//   stage 1     the 4992-sample span a tile needs is staged in shared memory, double buffered:
+//                 interior, 16-byte aligned tiles by ONE cp.async.bulk (TMA bulk copy,
+//                 mbarrier completion); edge / unaligned tiles by per-element cp.async with the
+//                 reflect / zero index mapping (so every window is padded on its own).
+//   stage 2     one warp transforms a PAIR of frames as one 1024-pt complex FFT split 32 x 32:
+//                 lane = fast sample index, in-register 32-pt pass A over the slow index with
+//                 the Hann window fused into the first butterflies, warp transpose through
+//                 padded shared memory, in-register 32-pt pass B with the inter-pass twiddle
+//                 fused, then the two real spectra are separated with one shuffle per value and
+//                 |X|^2 goes to the tile's power buffer P[32][516].
+//   stage 3     banded mel projection with lane = frame (weights are warp-uniform, P rows are
+//                 read with conflict-free 128-bit loads), log1p epilogue, staged through shared
+//                 memory so the [frames, n_mels] tile is written with coalesced stores.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bhmel_tables.h"
+
+#ifndef BHMEL_HD
+#define BHMEL_HD __device__ __forceinline__
+#endif
+#include "fft32_gen.h"
+
+namespace bhmel {
+
+constexpr int kTileF = 32;                                // frames per tile
+constexpr int kSpan = (kTileF - 1) * kHop + kNfft;        // 4992 samples
+constexpr int kSpanBytes = kSpan * 4;                     // 19968 (multiple of 16)
+constexpr int kPPitch = 516;                              // 513 bins + pad; /4 odd -> LDS.128 conflict-free
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kScrPitch = 33;                             // complex elements per transpose row
+constexpr int kMChunk = 96;                               // mel filters per epilogue chunk
+constexpr int kOutPitch = kMChunk + 1;                    // odd -> conflict-free lane=frame writes
+constexpr int kPairs = kTileF / 2;
+
+struct SmemLayout {
+  float P[kTileF * kPPitch];                  // 66 048 B  power spectra of the tile
+  float2 scr[kWarps][32 * kScrPitch];         // 67 584 B  per-warp transpose scratch
+  float span[2][kSpan];                       // 39 936 B  double-buffered sample span
+  float out[kTileF * kOutPitch];              // 12 416 B  epilogue staging
+  float win[kNfft];                           //  4 096 B  0.5 * window
+  float2 tw[32 * 32];                         //  8 192 B  W_1024^(a*b)
+  unsigned long long mbar[2];
+};
+
+struct KParams {
+  const float* x;          // module mode: [B][row_stride]; gather mode: the song
+  long long row_stride;    // elements between consecutive rows (gather: window stride)
+  long long row0;          // offset of row 0 inside x (gather: first_offset)
+  long long n_total;       // samples at absolute index >= n_total read as zero
+  long long N;             // logical row length (samples per window)
+  long long T;             // frames per row = N / hop + 1
+  long long n_tiles;
+  float* y;                // [B][T][n_mels]
+  const float* win_half;   // [1024]
+  const float2* tw;        // [32*32]
+  const FilterBand* bands; // [n_mels]
+  const float* weights;
+  int B;
+  int tiles_per_row;
+  int n_mels;
+  int pad_reflect;
+  int log_scale;
+  int use_bulk;
+};
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void cp_async_4(void* dst, const float* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+
+// ---------------------------------------------------------------- stage 1: span staging
+// Issues the asynchronous fill of span buffer `dst` for `tile`; returns true when the TMA bulk
+// path was used (caller then waits on the mbarrier), false for the cp.async path.
+__device__ __forceinline__ bool stage_span(const KParams& p, long long tile, float* dst,
+                                           unsigned long long* bar, int tid) {
+  const long long r = tile / p.tiles_per_row;
+  const int tb = static_cast<int>(tile - r * p.tiles_per_row);
+  const long long s0 = static_cast<long long>(tb) * (kTileF * kHop) - kNfft / 2;   // first sample of the span
+  const long long row_off = p.row0 + r * p.row_stride;
+  long long valid = p.n_total - row_off;                  // real samples available in this row
+  valid = valid < 0 ? 0 : (valid > p.N ? p.N : valid);
+  const float* row = p.x + row_off;
+  const bool bulk = p.use_bulk && s0 >= 0 && s0 + kSpan <= valid &&
+                    ((reinterpret_cast<uintptr_t>(row + s0) & 15) == 0);
+  if (bulk) {
+    if (tid == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(bar, kSpanBytes);
+      bulk_g2s(dst, row + s0, kSpanBytes, bar);
+    }
+    return true;
+  }
+  const long long N = p.N;
+  for (int e = tid; e < kSpan; e += kThreads) {
+    long long i = s0 + e;
+    if (i < 0) i = p.pad_reflect ? -i : -1;
+    else if (i >= N) i = p.pad_reflect ? 2 * (N - 1) - i : -1;
+    const bool ok = (i >= 0) && (i < valid);
+    cp_async_4(dst + e, row + (ok ? i : 0), ok ? 4 : 0);   // src-size 0 -> zero fill
+  }
+  cp_async_commit();
+  return false;
+}
+
+// ---------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(kThreads, 1) bhmel_logmel_kernel(const __grid_constant__ KParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SmemLayout& S = *reinterpret_cast<SmemLayout*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  // one-time: constant tables -> shared memory, zero the pad columns of P, init mbarriers
+  for (int i = tid; i < kNfft; i += kThreads) {
+    S.win[i] = p.win_half[i];
+    S.tw[i] = p.tw[i];
+  }
+  for (int i = tid; i < kTileF * (kPPitch - kBins); i += kThreads)
+    S.P[(i / (kPPitch - kBins)) * kPPitch + kBins + i % (kPPitch - kBins)] = 0.f;
+  if (tid == 0) {
+    mbar_init(&S.mbar[0], 1);
+    mbar_init(&S.mbar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  uint32_t parity0 = 0, parity1 = 0;
+  long long tile = blockIdx.x;
+  int buf = 0;
+  bool cur_bulk = false;
+  if (tile < p.n_tiles) cur_bulk = stage_span(p, tile, S.span[0], &S.mbar[0], tid);
+
+  for (; tile < p.n_tiles; tile += gridDim.x, buf ^= 1) {
+    // ---- wait for this tile's span ------------------------------------------------------
+    cp_async_wait_all();
+    if (cur_bulk) {
+      if (buf == 0) { mbar_wait(&S.mbar[0], parity0); parity0 ^= 1; }
+      else          { mbar_wait(&S.mbar[1], parity1); parity1 ^= 1; }
+    }
+    __syncthreads();   // span[buf] visible to all; every thread is done with the previous tile
+
+    // ---- prefetch the next tile's span into the other buffer -----------------------------
+    const long long next_tile = tile + gridDim.x;
+    bool next_bulk = false;
+    if (next_tile < p.n_tiles)
+      next_bulk = stage_span(p, next_tile, S.span[buf ^ 1], &S.mbar[buf ^ 1], tid);
+
+    // ---- stage 2: FFT of frame pairs ------------------------------------------------------
+    const float* span = S.span[buf];
+    float2* scr = S.scr[warp];
+#pragma unroll 1
+    for (int j = warp; j < kPairs; j += kWarps) {
+      float ar[32], ai[32];
+      {
+        float v[36], w[32];
+        const float* sp = span + (2 * j) * kHop + lane;
+#pragma unroll
+        for (int m = 0; m < 36; ++m) v[m] = sp[32 * m];
+#pragma unroll
+        for (int m = 0; m < 32; ++m) w[m] = S.win[lane + 32 * m];
+        fft32_pass_a(v, w, ar, ai);
+      }
+      // transpose: thread (lane = n2) holds Y[k1] -> thread (lane = k1) holds Y[n2]
+#pragma unroll
+      for (int k = 0; k < 32; ++k) scr[k * kScrPitch + lane] = make_float2(ar[k], ai[k]);
+      __syncwarp();
+      float br[32], bi[32];
+      {
+        float ur[32], ui[32], tr[32], ti[32];
+#pragma unroll
+        for (int n = 0; n < 32; ++n) {
+          const float2 u = scr[lane * kScrPitch + n];
+          ur[n] = u.x;
+          ui[n] = u.y;
+          const float2 t = S.tw[n * 32 + lane];
+          tr[n] = t.x;
+          ti[n] = t.y;
+        }
+        __syncwarp();   // all lanes have read the scratch before the next pair overwrites it
+        fft32_pass_b(ur, ui, tr, ti, br, bi);
+      }
+      // Z[k], k = lane + 32*k2.  Partner bin 1024-k lives in lane (32-lane)&31, slot 31-k2
+      // (lane 0: its own slot (32-k2)&31).  Xa = (Z[k] + conj Z[N-k])/2, Xb = (Z[k] - conj Z[N-k])/2i;
+      // the window carries the factor 1/2, so the sums below are Xa, Xb themselves.
+      const int src = (32 - lane) & 31;
+      float* Pa = S.P + (2 * j) * kPPitch + lane;
+      float* Pb = Pa + kPPitch;
+#pragma unroll
+      for (int k2 = 0; k2 < 16; ++k2) {
+        const int s = 31 - k2;
+        float pr = __shfl_sync(0xffffffffu, br[s], src);
+        float pi = __shfl_sync(0xffffffffu, bi[s], src);
+        if (lane == 0) {
+          pr = br[(s + 1) & 31];
+          pi = bi[(s + 1) & 31];
+        }
+        const float a1 = br[k2] + pr, a2 = bi[k2] - pi;
+        const float b1 = bi[k2] + pi, b2 = pr - br[k2];
+        Pa[32 * k2] = fmaf(a1, a1, a2 * a2);
+        Pb[32 * k2] = fmaf(b1, b1, b2 * b2);
+      }
+      if (lane == 0) {   // bin 512 = (k1 = 0, k2 = 16) is its own partner
+        const float zr = 2.f * br[16], zi = 2.f * bi[16];
+        Pa[512] = zr * zr;
+        Pb[512] = zi * zi;
+      }
+    }
+    __syncthreads();   // P complete
+
+    // ---- stage 3: banded mel projection + log1p + coalesced store ------------------------
+    const long long r = tile / p.tiles_per_row;
+    const int t0 = static_cast<int>(tile - r * p.tiles_per_row) * kTileF;
+    const long long frames_left = p.T - t0;
+    const int nf = frames_left < kTileF ? static_cast<int>(frames_left) : kTileF;
+    float* ybase = p.y + (r * p.T + t0) * static_cast<long long>(p.n_mels);
+    const float4* prow = reinterpret_cast<const float4*>(S.P + lane * kPPitch);
+    for (int mc = 0; mc < p.n_mels; mc += kMChunk) {
+      const int mcount = (p.n_mels - mc) < kMChunk ? (p.n_mels - mc) : kMChunk;
+      if (mc > 0) __syncthreads();   // previous chunk's staging fully stored
+      for (int m = warp; m < mcount; m += kWarps) {
+        const int4 fb4 = __ldg(reinterpret_cast<const int4*>(p.bands) + mc + m);
+        FilterBand fbnd;
+        fbnd.g0 = fb4.x; fbnd.ng = fb4.y; fbnd.woff = fb4.z; fbnd.pad = 0;
+        const float4* wp = reinterpret_cast<const float4*>(p.weights + fbnd.woff);
+        const float4* pp = prow + fbnd.g0;
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 2
+        for (int g = 0; g < fbnd.ng; ++g) {
+          const float4 w4 = __ldg(wp + g);
+          const float4 p4 = pp[g];
+          acc0 = fmaf(p4.x, w4.x, acc0);
+          acc1 = fmaf(p4.y, w4.y, acc1);
+          acc0 = fmaf(p4.z, w4.z, acc0);
+          acc1 = fmaf(p4.w, w4.w, acc1);
+        }
+        float v = acc0 + acc1;
+        if (p.log_scale) v = __logf(1.0f + v);
+        S.out[lane * kOutPitch + m] = v;
+      }
+      __syncthreads();
+      for (int f = warp; f < nf; f += kWarps) {
+        float* yrow = ybase + static_cast<long long>(f) * p.n_mels + mc;
+        const float* orow = S.out + f * kOutPitch;
+        for (int c = lane; c < mcount; c += 32) yrow[c] = orow[c];
+      }
+    }
+    cur_bulk = next_bulk;
+  }
+}
+
+}  // namespace bhmel

@@ -1,0 +1,104 @@
+// Host-side constant-table builders for libbhmel (plain C++, also used by the CPU lane emulator).
+//
+// What each table restates in the reference stack (ref = BeatHeritage repo root):
+//   window     torch.hann_window(n_fft, periodic=True), the `window` buffer torchaudio's
+//              Spectrogram registers (ref: osuT5/osuT5/model/spectrogram.py:40-49)
+//   filterbank torchaudio.functional.melscale_fbanks(n_freqs, f_min, f_max, n_mels, sr,
+//              norm=None, mel_scale="htk") -> the `fb` buffer of MelScale
+//   twiddles   W_1024^(a*b), a,b in [0,32): the inter-pass factors of the 32x32 split
+//   bands      per-filter contiguous non-zero range of fb, padded to groups of 4 bins so the
+//              kernel can use 128-bit shared-memory loads
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+namespace bhmel {
+
+constexpr int kNfft = 1024;
+constexpr int kHop = 128;
+constexpr int kBins = kNfft / 2 + 1;   // 513
+
+inline std::vector<float> make_hann_window() {
+  std::vector<float> w(kNfft);
+  for (int n = 0; n < kNfft; ++n)
+    w[n] = static_cast<float>(0.5 - 0.5 * std::cos(2.0 * M_PI * n / kNfft));
+  return w;
+}
+
+// [32][32] complex (cos, -sin) of 2*pi*a*b/1024, laid out [a][b] (symmetric).
+inline std::vector<float> make_twiddles() {
+  std::vector<float> t(32 * 32 * 2);
+  for (int a = 0; a < 32; ++a)
+    for (int b = 0; b < 32; ++b) {
+      const double th = 2.0 * M_PI * static_cast<double>(a * b) / kNfft;
+      t[(a * 32 + b) * 2 + 0] = static_cast<float>(std::cos(th));
+      t[(a * 32 + b) * 2 + 1] = static_cast<float>(-std::sin(th));
+    }
+  return t;
+}
+
+// htk mel filterbank, norm=None, evaluated in double and rounded once (torchaudio evaluates in
+// fp32; the two agree to ~1e-5 absolute, far inside the 1e-3 parity bar -- callers that need the
+// reference's exact buffer pass it through bhmel_params.fb / bhmel_set_fb).
+inline std::vector<float> make_mel_fb(int n_mels, double f_min, double f_max, int sample_rate) {
+  auto hz2mel = [](double f) { return 2595.0 * std::log10(1.0 + f / 700.0); };
+  auto mel2hz = [](double m) { return 700.0 * (std::pow(10.0, m / 2595.0) - 1.0); };
+  const double m_min = hz2mel(f_min), m_max = hz2mel(f_max);
+  std::vector<double> f_pts(n_mels + 2);
+  for (int i = 0; i < n_mels + 2; ++i)
+    f_pts[i] = mel2hz(m_min + (m_max - m_min) * i / (n_mels + 1));
+  std::vector<float> fb(static_cast<size_t>(kBins) * n_mels, 0.f);
+  const double nyq = sample_rate / 2;   // integer division like `sample_rate // 2`
+  for (int k = 0; k < kBins; ++k) {
+    const double f = nyq * k / (kBins - 1);
+    for (int m = 0; m < n_mels; ++m) {
+      const double down = (f - f_pts[m]) / (f_pts[m + 1] - f_pts[m]);
+      const double up = (f_pts[m + 2] - f) / (f_pts[m + 2] - f_pts[m + 1]);
+      const double v = std::fmax(0.0, std::fmin(down, up));
+      fb[static_cast<size_t>(k) * n_mels + m] = static_cast<float>(v);
+    }
+  }
+  return fb;
+}
+
+// Per-filter band descriptor consumed by the kernel's mel stage.
+struct FilterBand {
+  int32_t g0;      // first 4-bin group (bin index / 4)
+  int32_t ng;      // number of 4-bin groups (0 for an all-zero filter)
+  int32_t woff;    // offset (in floats, multiple of 4) of this filter's weights
+  int32_t pad;
+};
+
+struct BandTables {
+  std::vector<FilterBand> bands;   // [n_mels]
+  std::vector<float> weights;      // 4-aligned groups, zero padded
+  int max_groups = 0;
+};
+
+// fb: [kBins][n_mels] row-major.  Works for ANY matrix (a dense filter simply gets one long band).
+inline BandTables make_bands(const float* fb, int n_mels) {
+  BandTables t;
+  t.bands.resize(n_mels);
+  for (int m = 0; m < n_mels; ++m) {
+    int first = -1, last = -1;
+    for (int k = 0; k < kBins; ++k)
+      if (fb[static_cast<size_t>(k) * n_mels + m] != 0.f) {
+        if (first < 0) first = k;
+        last = k;
+      }
+    FilterBand b{0, 0, static_cast<int32_t>(t.weights.size()), 0};
+    if (first >= 0) {
+      b.g0 = first / 4;
+      b.ng = last / 4 - b.g0 + 1;
+      for (int k = b.g0 * 4; k < (b.g0 + b.ng) * 4; ++k)
+        t.weights.push_back(k < kBins ? fb[static_cast<size_t>(k) * n_mels + m] : 0.f);
+    }
+    if (b.ng > t.max_groups) t.max_groups = b.ng;
+    t.bands[m] = b;
+  }
+  if (t.weights.empty()) t.weights.assign(4, 0.f);
+  return t;
+}
+
+}  // namespace bhmel

@@ -1,0 +1,116 @@
+/* bhmel.h -- C ABI of libbhmel.so: the B200-native (sm_100a) replacement for the hot path of
+ * BeatHeritage's audio frontend, osuT5/osuT5/model/spectrogram.py::MelSpectrogram
+ * (reference file:line cited per entry point below; "ref:" paths are relative to the
+ * reference repository root).
+ *
+ * All entry points are plain C: pointers, sizes and a CUDA stream handle -- no torch types.
+ * Device pointers are owned by the caller; the handle owns only its constant tables (and, for
+ * bhmel_forward_host, its private staging buffers).  bhmel_forward / bhmel_forward_gather
+ * launch on the caller's stream, never synchronise the device and allocate nothing.
+ * Every function returning int returns 0 on success and a BHMEL_E* code otherwise; the
+ * message is available through bhmel_last_error() (thread-local).
+ * The library is re-entrant: no global mutable state besides the thread-local error string.
+ */
+#ifndef BHMEL_H_
+#define BHMEL_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BHMEL_VERSION 100          /* 0.1.0 */
+
+#define BHMEL_OK 0
+#define BHMEL_EINVAL 1             /* bad argument / unsupported parameter combination */
+#define BHMEL_ECUDA 2              /* CUDA runtime error (message carries cudaGetErrorString) */
+#define BHMEL_ESHAPE 3             /* input too short for reflect padding, empty input, ... */
+#define BHMEL_EDEVICE 4            /* not an sm_100 device / wrong current device */
+
+#define BHMEL_PAD_CONSTANT 0       /* ref: configs/model/default.yaml:27 pad_mode 'constant' */
+#define BHMEL_PAD_REFLECT 1        /* ref: configs/model/whisper_small_v2.yaml:21 pad_mode 'reflect' */
+
+/* Output element type of the forward calls (the reference always returns float32,
+ * ref: osuT5/osuT5/model/spectrogram.py:79-83). */
+#define BHMEL_OUT_F32 0
+
+typedef struct bhmel_handle bhmel_handle;
+
+/* Mirrors the constructor arguments of the reference module
+ * (ref: osuT5/osuT5/model/spectrogram.py:8-19; values from configs/model/default.yaml:18-27 and
+ * configs/model/whisper_small_v2.yaml:16-21).  n_fft must be 1024 and hop_length 128 (constant in
+ * every reference config); 1 <= n_mels <= 1024. */
+typedef struct bhmel_params {
+  int32_t sample_rate;     /* 16000 */
+  int32_t n_fft;           /* 1024 ("n_ftt" in the reference signature) */
+  int32_t hop_length;      /* 128 */
+  int32_t n_mels;          /* 80 / 128 / 388 / 512 */
+  double f_min;            /* Hz */
+  double f_max;            /* Hz */
+  int32_t pad_mode;        /* BHMEL_PAD_* (torch.stft center=True padding) */
+  int32_t log_scale;       /* non-zero: log1p epilogue (ref: spectrogram.py:80-81) */
+  const float* fb;         /* optional HOST [n_fft/2+1][n_mels] row-major filterbank override (the
+                              state-dict buffer transform.mel_scale.fb); NULL -> htk/norm=None
+                              triangular bank as torchaudio.functional.melscale_fbanks builds it */
+  const float* window;     /* optional HOST [n_fft] window override (state-dict buffer
+                              transform.spectrogram.window); NULL -> periodic Hann */
+} bhmel_params;
+
+/* Replaces MelSpectrogram.__init__ (ref: spectrogram.py:8-61): validates the parameters and
+ * builds the device-resident constant tables (window, twiddles, banded filterbank) on the
+ * CURRENT CUDA device.  */
+int bhmel_create(const bhmel_params* params, bhmel_handle** out);
+void bhmel_destroy(bhmel_handle* h);
+
+/* Replaces the persistent buffers of the reference module (state_dict keys
+ * transform.spectrogram.window / transform.mel_scale.fb): set from / copy to HOST arrays.
+ * Setting rebuilds the derived device tables (synchronises the handle's device). */
+int bhmel_set_fb(bhmel_handle* h, const float* fb_host /* [n_fft/2+1][n_mels] */);
+int bhmel_set_window(bhmel_handle* h, const float* window_host /* [n_fft] */);
+int bhmel_get_fb(const bhmel_handle* h, float* fb_host);
+int bhmel_get_window(const bhmel_handle* h, float* window_host);
+
+/* Number of output frames for an input of n_samples: n_samples / hop + 1
+ * (ref: spectrogram.py:71 "n_frames = n_samples // hop_length + 1"). */
+int64_t bhmel_num_frames(const bhmel_handle* h, int64_t n_samples);
+
+/* Replaces MelSpectrogram.forward (ref: spectrogram.py:63-83):
+ *   x  DEVICE float32 [B][N] with row stride x_row_stride (elements, >= N)
+ *   y  DEVICE float32 [B][N/hop+1][n_mels], contiguous -- the encoder's [batch, frames, n_mels]
+ * One fused kernel: centre pad (reflect/constant) + framing + Hann + 1024-pt real FFT +
+ * |X|^2 + mel filterbank + log1p.  Asynchronous on `stream` (a cudaStream_t).
+ * Errors: BHMEL_ESHAPE if N <= n_fft/2 with reflect padding (the reference raises RuntimeError
+ * from F.pad), or B/N <= 0. */
+int bhmel_forward(bhmel_handle* h, const float* x, int64_t B, int64_t N, int64_t x_row_stride,
+                  float* y, void* stream);
+
+/* Fused segmentation + forward.  Replaces Preprocessor.segment/window followed by forward
+ * (ref: osuT5/osuT5/inference/preprocessor.py:58-71, 94-102): window w (0 <= w < W) covers
+ * song[first_offset + w*stride ... + window_len), samples at or beyond n_song read as zero
+ * (the right padding segment() applies); every window is centre-padded on its own exactly as
+ * forward does.   song DEVICE float32 [n_song];  y DEVICE float32 [W][window_len/hop+1][n_mels]. */
+int bhmel_forward_gather(bhmel_handle* h, const float* song, int64_t n_song, int64_t first_offset,
+                         int64_t stride, int64_t W, int64_t window_len, float* y, void* stream);
+
+/* Same contract as bhmel_forward with HOST buffers (pinned memory recommended): chunks the
+ * batch, and overlaps host->device copy, the kernel and device->host copy on private streams.
+ * Synchronous: returns when y_host is complete.  This is the end-to-end entry the plugin uses
+ * when the caller's data lives on the host (ref: osuT5/dataloading.py:128-130 calls the module
+ * with CPU tensors; osuT5/osuT5/inference/server.py:42 does the H2D copy for inference). */
+int bhmel_forward_host(bhmel_handle* h, const float* x_host, int64_t B, int64_t N,
+                       int64_t x_row_stride, float* y_host);
+
+/* Introspection used by tests and bench.py. */
+int bhmel_version(void);
+const char* bhmel_last_error(void);
+/* Number of kernel launches issued through this handle so far (bench.py's gpu_launches). */
+int64_t bhmel_launch_count(const bhmel_handle* h);
+/* Static facts about the compiled kernel: dynamic shared memory bytes, threads per CTA,
+ * frames per tile. Any pointer may be NULL. */
+void bhmel_kernel_info(int32_t* smem_bytes, int32_t* threads, int32_t* tile_frames);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BHMEL_H_ */

@@ -1,0 +1,122 @@
+// CPU lane-emulator of bhmel_logmel_kernel -- TEST INFRASTRUCTURE ONLY (never shipped, never
+// on the product path).  It executes the kernel's algorithm warp by warp on the host with the
+// SAME generated FFT passes (fft32_gen.h), the SAME constant tables (bhmel_tables.h) and the same
+// index arithmetic (span staging with reflect/zero mapping, 32-frame tiles, frame pairs, the
+// lane <-> bin pairing of the two-real-FFTs-in-one-complex trick, banded mel, log epilogue), so
+// the no-GPU test suite can check everything except CUDA-specific mechanics (barriers, TMA).
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#define BHMEL_HD static inline
+#include "../../beatheritage_b200/csrc/fft32_gen.h"
+#include "../../beatheritage_b200/csrc/bhmel_tables.h"
+
+namespace {
+constexpr int kTileF = 32, kSpan = (kTileF - 1) * bhmel::kHop + bhmel::kNfft, kPPitch = 516, kScrPitch = 33;
+}
+
+extern "C" int bhmel_emu_forward(const float* x, long long B, long long N, long long row_stride,
+                                 long long row0, long long n_total, int n_mels, const float* fb_in,
+                                 const float* window_in, double f_min, double f_max, int sample_rate,
+                                 int pad_reflect, int log_scale, int exact_log1p, float* y) {
+  using namespace bhmel;
+  std::vector<float> fb = fb_in ? std::vector<float>(fb_in, fb_in + (size_t)kBins * n_mels)
+                                : make_mel_fb(n_mels, f_min, f_max, sample_rate);
+  std::vector<float> win = window_in ? std::vector<float>(window_in, window_in + kNfft) : make_hann_window();
+  std::vector<float> win_half(kNfft);
+  for (int i = 0; i < kNfft; ++i) win_half[i] = 0.5f * win[i];
+  std::vector<float> tw = make_twiddles();
+  BandTables bt = make_bands(fb.data(), n_mels);
+
+  const long long T = N / kHop + 1;
+  const int tiles_per_row = (int)((T + kTileF - 1) / kTileF);
+  std::vector<float> span(kSpan), P((size_t)kTileF * kPPitch, 0.f);
+  std::vector<float> scr_r(32 * kScrPitch), scr_i(32 * kScrPitch);
+
+  for (long long r = 0; r < B; ++r) {
+    for (int tb = 0; tb < tiles_per_row; ++tb) {
+      // ---- stage 1 (same mapping as stage_span's cp.async path)
+      const long long s0 = (long long)tb * (kTileF * kHop) - kNfft / 2;
+      const long long row_off = row0 + r * row_stride;
+      long long valid = n_total - row_off;
+      valid = valid < 0 ? 0 : (valid > N ? N : valid);
+      const float* row = x + row_off;
+      for (int e = 0; e < kSpan; ++e) {
+        long long i = s0 + e;
+        if (i < 0) i = pad_reflect ? -i : -1;
+        else if (i >= N) i = pad_reflect ? 2 * (N - 1) - i : -1;
+        const bool ok = (i >= 0) && (i < valid);
+        span[e] = ok ? row[i] : 0.f;
+      }
+      // ---- stage 2
+      for (int j = 0; j < kTileF / 2; ++j) {
+        float ar[32][32], ai[32][32];     // [lane][slot]
+        for (int lane = 0; lane < 32; ++lane) {
+          float v[36], w[32];
+          for (int m = 0; m < 36; ++m) v[m] = span[(2 * j) * kHop + lane + 32 * m];
+          for (int m = 0; m < 32; ++m) w[m] = win_half[lane + 32 * m];
+          fft32_pass_a(v, w, ar[lane], ai[lane]);
+          for (int k = 0; k < 32; ++k) {
+            scr_r[k * kScrPitch + lane] = ar[lane][k];
+            scr_i[k * kScrPitch + lane] = ai[lane][k];
+          }
+        }
+        float br[32][32], bi[32][32];
+        for (int lane = 0; lane < 32; ++lane) {
+          float ur[32], ui[32], tr[32], ti[32];
+          for (int n = 0; n < 32; ++n) {
+            ur[n] = scr_r[lane * kScrPitch + n];
+            ui[n] = scr_i[lane * kScrPitch + n];
+            tr[n] = tw[(n * 32 + lane) * 2 + 0];
+            ti[n] = tw[(n * 32 + lane) * 2 + 1];
+          }
+          fft32_pass_b(ur, ui, tr, ti, br[lane], bi[lane]);
+        }
+        for (int lane = 0; lane < 32; ++lane) {
+          const int src = (32 - lane) & 31;
+          float* Pa = P.data() + (size_t)(2 * j) * kPPitch + lane;
+          float* Pb = Pa + kPPitch;
+          for (int k2 = 0; k2 < 16; ++k2) {
+            const int s = 31 - k2;
+            float pr = br[src][s], pi = bi[src][s];      // __shfl_sync(.., src)
+            if (lane == 0) { pr = br[0][(s + 1) & 31]; pi = bi[0][(s + 1) & 31]; }
+            const float a1 = br[lane][k2] + pr, a2 = bi[lane][k2] - pi;
+            const float b1 = bi[lane][k2] + pi, b2 = pr - br[lane][k2];
+            Pa[32 * k2] = fmaf(a1, a1, a2 * a2);
+            Pb[32 * k2] = fmaf(b1, b1, b2 * b2);
+          }
+          if (lane == 0) {
+            const float zr = 2.f * br[0][16], zi = 2.f * bi[0][16];
+            Pa[512] = zr * zr;
+            Pb[512] = zi * zi;
+          }
+        }
+      }
+      // ---- stage 3
+      const int t0 = tb * kTileF;
+      const int nf = (int)((T - t0) < kTileF ? (T - t0) : kTileF);
+      for (int f = 0; f < nf; ++f) {
+        const float* prow = P.data() + (size_t)f * kPPitch;
+        float* yrow = y + ((r * T + t0 + f) * (long long)n_mels);
+        for (int m = 0; m < n_mels; ++m) {
+          const FilterBand b = bt.bands[m];
+          float acc0 = 0.f, acc1 = 0.f;
+          for (int g = 0; g < b.ng; ++g) {
+            const float* w4 = bt.weights.data() + b.woff + 4 * g;
+            const float* p4 = prow + 4 * (b.g0 + g);
+            acc0 = fmaf(p4[0], w4[0], acc0);
+            acc1 = fmaf(p4[1], w4[1], acc1);
+            acc0 = fmaf(p4[2], w4[2], acc0);
+            acc1 = fmaf(p4[3], w4[3], acc1);
+          }
+          float v = acc0 + acc1;
+          if (log_scale) v = exact_log1p ? log1pf(v) : logf(1.0f + v);
+          yrow[m] = v;
+        }
+      }
+    }
+  }
+  return 0;
+}
