@@ -45,6 +45,7 @@ struct bhmel_handle {
   bhmel::FilterBand* d_bands = nullptr;
   float* d_weights = nullptr;
   std::atomic<int64_t> launches{0};
+  int use_bulk = 1;
   // bhmel_forward_host pipeline (lazily created)
   std::mutex host_mu;
   cudaStream_t hs[kHostSlots] = {nullptr, nullptr, nullptr};
@@ -120,8 +121,7 @@ int launch(bhmel_handle* h, const float* x, long long row_stride, long long row0
   p.n_mels = h->prm.n_mels;
   p.pad_reflect = h->prm.pad_mode == BHMEL_PAD_REFLECT;
   p.log_scale = h->prm.log_scale != 0;
-  static const bool no_bulk = std::getenv("BHMEL_NO_BULK") != nullptr;   // debugging aid
-  p.use_bulk = no_bulk ? 0 : 1;
+  p.use_bulk = h->use_bulk;
 
   const long long grid = p.n_tiles < h->num_sms ? p.n_tiles : h->num_sms;
   bhmel::bhmel_logmel_kernel<<<static_cast<unsigned>(grid), bhmel::kThreads, sizeof(bhmel::SmemLayout),
@@ -245,6 +245,17 @@ int bhmel_get_window(const bhmel_handle* h, float* window_host) {
 int64_t bhmel_num_frames(const bhmel_handle* h, int64_t n_samples) {
   (void)h;
   return n_samples < 0 ? 0 : n_samples / bhmel::kHop + 1;
+}
+
+int bhmel_set_option(bhmel_handle* h, int32_t option, int64_t value) {
+  if (!h) return fail(BHMEL_EINVAL, "null handle");
+  switch (option) {
+    case BHMEL_OPT_BULK_COPY:
+      h->use_bulk = value != 0;
+      return BHMEL_OK;
+    default:
+      return fail(BHMEL_EINVAL, "unknown option " + std::to_string(option));
+  }
 }
 
 int64_t bhmel_launch_count(const bhmel_handle* h) { return h ? h->launches.load() : 0; }

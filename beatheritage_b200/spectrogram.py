@@ -1,0 +1,311 @@
+"""Host-side mirror of the reference audio frontend.
+
+`MelSpectrogram` keeps the interface of reference osuT5/osuT5/model/spectrogram.py:7-83 --
+same constructor signature (including the misspelt `n_ftt` and the positional order the call
+sites rely on, reference osuT5/osuT5/model/modeling_mapperatorinator.py:56-66 and
+osuT5/dataloading.py:81-90), same `forward(samples[B, N]) -> [B, N // hop + 1, n_mels]`
+float32 contract, same state-dict keys (`transform.spectrogram.window`,
+`transform.mel_scale.fb`) -- but the work is one fused CUDA kernel behind the C ABI in
+include/bhmel.h.  PyTorch is only plumbing here: device memory, the current stream, and the
+`torch.library` custom op that keeps `torch.compile(model)` (reference osuT5/train.py:101-102)
+from graph-breaking.  There is no CPU fallback: a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import threading
+import weakref
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+N_FFT = 1024
+HOP = 128
+
+
+# ----------------------------------------------------------------------------------------
+# Buffers, computed with the same torch ops torchaudio uses so the state dict is identical
+# ----------------------------------------------------------------------------------------
+def melscale_fbanks_htk(n_freqs: int, f_min: float, f_max: float, n_mels: int, sample_rate: int) -> torch.Tensor:
+    """htk mel scale, norm=None triangular filterbank [n_freqs, n_mels] float32.
+
+    Restates torchaudio.functional.melscale_fbanks (functional.py @518 with `_hz_to_mel` @425,
+    `_mel_to_hz` @459, `_create_triangular_filterbank` @492) operation by operation in fp32 torch
+    arithmetic, which makes the buffer bit-identical to the one the reference module registers."""
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_min = 2595.0 * math.log10(1.0 + (f_min / 700.0))
+    m_max = 2595.0 * math.log10(1.0 + (f_max / 700.0))
+    m_pts = torch.linspace(m_min, m_max, n_mels + 2)
+    f_pts = 700.0 * (10.0 ** (m_pts / 2595.0) - 1.0)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    rising = (-1.0 * slopes[:, :-2]) / f_diff[:-1]
+    falling = slopes[:, 2:] / f_diff[1:]
+    return torch.max(torch.zeros(1), torch.min(rising, falling))
+
+
+class _WindowHolder(nn.Module):
+    """Carries the `window` buffer under the name torchaudio's Spectrogram uses."""
+
+    def __init__(self, n_fft: int):
+        super().__init__()
+        self.register_buffer("window", torch.hann_window(n_fft), persistent=True)
+
+
+class _FbHolder(nn.Module):
+    """Carries the `fb` buffer under the name torchaudio's MelScale uses."""
+
+    def __init__(self, fb: torch.Tensor):
+        super().__init__()
+        self.register_buffer("fb", fb, persistent=True)
+
+
+class _Transform(nn.Module):
+    """Namespace module so the state-dict keys read `transform.spectrogram.window` and
+    `transform.mel_scale.fb` exactly like torchaudio.transforms.MelSpectrogram's."""
+
+    def __init__(self, n_fft: int, fb: torch.Tensor):
+        super().__init__()
+        self.spectrogram = _WindowHolder(n_fft)
+        self.mel_scale = _FbHolder(fb)
+
+
+# ----------------------------------------------------------------------------------------
+# torch.library custom op (opaque to dynamo/inductor, shape-inferable)
+# ----------------------------------------------------------------------------------------
+_registry: "weakref.WeakValueDictionary[int, MelSpectrogram]" = weakref.WeakValueDictionary()
+_registry_lock = threading.Lock()
+_handle_lock = threading.Lock()
+_next_key = [1]
+
+
+@torch.library.custom_op("beatheritage_b200::mel_forward", mutates_args=(), device_types="cuda")
+def _mel_forward_op(samples: torch.Tensor, module_key: int, n_mels: int) -> torch.Tensor:
+    mod = _registry.get(module_key)
+    if mod is None:
+        raise RuntimeError("beatheritage_b200::mel_forward: the owning MelSpectrogram module is gone")
+    return mod._launch(samples)
+
+
+@_mel_forward_op.register_fake
+def _(samples, module_key, n_mels):
+    return samples.new_empty((samples.shape[0], samples.shape[1] // HOP + 1, n_mels), dtype=torch.float32)
+
+
+# ----------------------------------------------------------------------------------------
+class MelSpectrogram(nn.Module):
+    #: nnAudio arithmetic cannot be pinned (the package is neither vendored in the reference nor
+    #: installed here); set True to map implementation="nnAudio" onto the
+    #: torchaudio arithmetic instead of raising.
+    allow_nnaudio_as_torchaudio = False
+
+    def __init__(
+        self,
+        implementation: str = "nnAudio",
+        log_scale: bool = False,
+        sample_rate: int = 16000,
+        n_ftt: int = 2048,
+        n_mels: int = 512,
+        hop_length: int = 128,
+        f_min: int = 0,
+        f_max: int = 8000,
+        pad_mode: str = "constant",
+    ):
+        """Melspectrogram transformation layer on B200 (see module docstring).
+
+        Arguments mirror the reference (spectrogram.py:8-33): implementation, log_scale,
+        sample_rate, n_ftt (STFT size), n_mels, hop_length, f_min, f_max, pad_mode."""
+        super().__init__()
+        assert implementation in ["torchaudio", "nnAudio"], f"Unsupported implementation: {implementation}"
+        if implementation == "nnAudio" and not self.allow_nnaudio_as_torchaudio:
+            raise NotImplementedError(
+                "implementation='nnAudio': nnAudio's arithmetic is unpinned (not vendored by the reference, "
+                "not installable offline); set MelSpectrogram.allow_nnaudio_as_torchaudio = True to use the "
+                "torchaudio arithmetic with these parameters instead")
+        if n_ftt != N_FFT or hop_length != HOP:
+            raise ValueError(
+                f"the sm_100a kernel is compiled for n_ftt={N_FFT}, hop_length={HOP} (constant in every reference "
+                f"config); got n_ftt={n_ftt}, hop_length={hop_length}")
+        if pad_mode not in ("reflect", "constant"):
+            raise ValueError(f"unsupported pad_mode {pad_mode!r} (reference configs use 'reflect' or 'constant')")
+        self.implementation = implementation
+        self.log_scale = log_scale
+        self.sample_rate = sample_rate
+        self.n_fft = n_ftt
+        self.n_mels = n_mels
+        self.hop_length = hop_length
+        self.f_min = f_min
+        self.f_max = f_max
+        self.pad_mode = pad_mode
+        fb = melscale_fbanks_htk(n_ftt // 2 + 1, float(f_min), float(f_max), n_mels, sample_rate)
+        self.transform = _Transform(n_ftt, fb)
+        self._handles: dict[int, int] = {}        # device index -> bhmel_handle*
+        self._stamp: dict[int, tuple] = {}        # device index -> buffer versions the handle was built from
+        self._bulk = True
+        self._register()
+
+    def _register(self) -> None:
+        with _registry_lock:
+            self._key = _next_key[0]
+            _next_key[0] += 1
+            _registry[self._key] = self
+
+    # handles are process-local device resources: never copied or pickled with the module
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_handles"], state["_stamp"] = {}, {}
+        state.pop("_key", None)
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._register()
+
+    # -- handle management -------------------------------------------------------------
+    def _buffer_stamp(self) -> tuple:
+        w, fb = self.transform.spectrogram.window, self.transform.mel_scale.fb
+        return (w.data_ptr(), w._version, fb.data_ptr(), fb._version)
+
+    def _handle_for(self, device: torch.device) -> int:
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        stamp = self._buffer_stamp()
+        with _handle_lock:
+            h = self._handles.get(idx)
+            if h is not None and self._stamp.get(idx) == stamp:
+                return h
+            lib = _lib.lib()
+            fb = self.transform.mel_scale.fb.detach().to("cpu", torch.float32).contiguous()
+            win = self.transform.spectrogram.window.detach().to("cpu", torch.float32).contiguous()
+            if tuple(fb.shape) != (self.n_fft // 2 + 1, self.n_mels) or tuple(win.shape) != (self.n_fft,):
+                raise RuntimeError(f"unexpected buffer shapes fb{tuple(fb.shape)} window{tuple(win.shape)}")
+            fp = ctypes.POINTER(ctypes.c_float)
+            with torch.cuda.device(idx):
+                if h is None:
+                    prm = _lib.BhmelParams(
+                        self.sample_rate, self.n_fft, self.hop_length, self.n_mels, float(self.f_min),
+                        float(self.f_max), _lib.PAD_REFLECT if self.pad_mode == "reflect" else _lib.PAD_CONSTANT,
+                        int(bool(self.log_scale)), ctypes.cast(fb.data_ptr(), fp), ctypes.cast(win.data_ptr(), fp))
+                    out = ctypes.c_void_p()
+                    _lib.check(lib.bhmel_create(ctypes.byref(prm), ctypes.byref(out)))
+                    h = out.value
+                    self._handles[idx] = h
+                    if not self._bulk:
+                        _lib.check(lib.bhmel_set_option(h, _lib.OPT_BULK_COPY, 0))
+                else:   # buffers were reloaded / edited: refresh the device tables
+                    _lib.check(lib.bhmel_set_fb(h, ctypes.cast(fb.data_ptr(), fp)))
+                    _lib.check(lib.bhmel_set_window(h, ctypes.cast(win.data_ptr(), fp)))
+            self._stamp[idx] = stamp
+            return h
+
+    def __del__(self):
+        try:
+            lib = _lib.lib()
+            for h in self._handles.values():
+                lib.bhmel_destroy(h)
+        except Exception:
+            pass
+
+    def launch_count(self) -> int:
+        """Total kernel launches issued by this module (all devices)."""
+        lib = _lib.lib()
+        return sum(int(lib.bhmel_launch_count(h)) for h in self._handles.values())
+
+    def set_bulk_copy(self, enabled: bool) -> None:
+        """Debug/tuning switch: stage interior tiles with the TMA bulk copy (default) or not."""
+        self._bulk = bool(enabled)
+        for h in self._handles.values():
+            _lib.check(_lib.lib().bhmel_set_option(h, _lib.OPT_BULK_COPY, int(enabled)))
+
+    # -- forward -----------------------------------------------------------------------
+    def _check_input(self, samples: torch.Tensor) -> torch.Tensor:
+        if samples.dim() != 2:
+            # the reference fails in permute(0, 2, 1) for anything but [batch, samples]
+            raise RuntimeError(f"expected samples of shape [batch, n_samples], got {tuple(samples.shape)}")
+        if samples.shape[0] == 0 or samples.shape[1] == 0:
+            raise RuntimeError("empty input")
+        if self.pad_mode == "reflect" and samples.shape[1] <= self.n_fft // 2:
+            # torch.stft's F.pad(..., "reflect") raises for the reference
+            raise RuntimeError(
+                f"Padding size should be less than the corresponding input dimension, but got: padding "
+                f"({self.n_fft // 2}, {self.n_fft // 2}) at dimension 1 of input {list(samples.shape)}")
+        return samples
+
+    def _launch(self, samples: torch.Tensor) -> torch.Tensor:
+        B, N = samples.shape
+        x = samples
+        if x.dtype != torch.float32:
+            x = x.to(torch.float32)
+        if x.stride(1) != 1 or (B > 1 and x.stride(0) < N):
+            x = x.contiguous()
+        stride = x.stride(0) if B > 1 else N
+        T = N // self.hop_length + 1
+        y = torch.empty((B, T, self.n_mels), dtype=torch.float32, device=x.device)
+        h = self._handle_for(x.device)
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            _lib.check(_lib.lib().bhmel_forward(h, x.data_ptr(), B, N, stride, y.data_ptr(), stream))
+        return y
+
+    def forward(self, samples: torch.Tensor) -> torch.Tensor:
+        """Convert a batch of audio windows [batch, n_samples] into log-mel frames
+        [batch, n_samples // hop_length + 1, n_mels] (reference spectrogram.py:63-83)."""
+        self._check_input(samples)
+        if not samples.is_cuda:
+            raise RuntimeError(
+                "beatheritage_b200.MelSpectrogram has no CPU path: move the batch to a CUDA (sm_100) device, "
+                "or use forward_host() for host-resident batches")
+        return _mel_forward_op(samples, self._key, self.n_mels)
+
+    @torch.no_grad()
+    def forward_host(self, samples: torch.Tensor, out: torch.Tensor | None = None,
+                     device: int | None = None) -> torch.Tensor:
+        """End-to-end call for HOST batches (reference osuT5/dataloading.py:128-130 calls the module
+        with CPU tensors): chunked H2D copy, kernel and D2H copy overlapped inside the library.
+        `samples` float32 CPU [B, N] (pinned memory recommended); returns a CPU tensor."""
+        self._check_input(samples)
+        if samples.is_cuda:
+            raise RuntimeError("forward_host expects a CPU tensor")
+        x = samples if samples.dtype == torch.float32 else samples.to(torch.float32)
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        B, N = x.shape
+        T = N // self.hop_length + 1
+        if out is None:
+            out = torch.empty((B, T, self.n_mels), dtype=torch.float32, pin_memory=True)
+        assert out.is_contiguous() and tuple(out.shape) == (B, T, self.n_mels) and out.dtype == torch.float32
+        idx = torch.cuda.current_device() if device is None else device
+        h = self._handle_for(torch.device("cuda", idx))
+        with torch.cuda.device(idx):
+            _lib.check(_lib.lib().bhmel_forward_host(h, x.data_ptr(), B, N, x.stride(0) if B > 1 else N,
+                                                     out.data_ptr()))
+        return out
+
+    @torch.no_grad()
+    def forward_gather(self, song: torch.Tensor, first_offset: int, stride: int, n_windows: int,
+                       window_len: int) -> torch.Tensor:
+        """Fused segmentation + forward: window w covers song[first_offset + w*stride : ... + window_len]
+        with zeros past the end of `song` -- what Preprocessor.segment materialises on the host
+        (reference osuT5/osuT5/inference/preprocessor.py:58-71, 94-102) -- without ever building
+        the [W, window_len] batch.  `song` float32 CUDA [n_song]."""
+        if song.dim() != 1 or not song.is_cuda:
+            raise RuntimeError("forward_gather expects a 1-D CUDA tensor")
+        if self.pad_mode == "reflect" and window_len <= self.n_fft // 2:
+            raise RuntimeError("window_len too short for reflect padding")
+        x = song if song.dtype == torch.float32 else song.to(torch.float32)
+        x = x.contiguous()
+        T = window_len // self.hop_length + 1
+        y = torch.empty((n_windows, T, self.n_mels), dtype=torch.float32, device=x.device)
+        h = self._handle_for(x.device)
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            _lib.check(_lib.lib().bhmel_forward_gather(h, x.data_ptr(), x.numel(), first_offset, stride,
+                                                       n_windows, window_len, y.data_ptr(), stream))
+        return y
+
+    def extra_repr(self) -> str:
+        return (f"implementation={self.implementation!r}, log_scale={self.log_scale}, sample_rate={self.sample_rate}, "
+                f"n_ftt={self.n_fft}, n_mels={self.n_mels}, hop_length={self.hop_length}, f_min={self.f_min}, "
+                f"f_max={self.f_max}, pad_mode={self.pad_mode!r}")

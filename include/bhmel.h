@@ -101,6 +101,11 @@ int bhmel_forward_gather(bhmel_handle* h, const float* song, int64_t n_song, int
 int bhmel_forward_host(bhmel_handle* h, const float* x_host, int64_t B, int64_t N,
                        int64_t x_row_stride, float* y_host);
 
+/* Tuning / debugging switches (per handle).  BHMEL_OPT_BULK_COPY: 1 (default) stages aligned
+ * interior tiles with the TMA bulk copy, 0 forces the per-element cp.async path everywhere. */
+#define BHMEL_OPT_BULK_COPY 1
+int bhmel_set_option(bhmel_handle* h, int32_t option, int64_t value);
+
 /* Introspection used by tests and bench.py. */
 int bhmel_version(void);
 const char* bhmel_last_error(void);

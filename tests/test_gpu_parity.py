@@ -1,0 +1,277 @@
+"""GPU (-m gpu): parity of the CUDA path against the oracle and the reference fixtures, called
+through the reference-facing module and the C ABI.  Tolerance: max abs error in the log1p
+domain <= 1e-3 (north star), and we additionally hold the kernel to 2e-5 (fp32 FFT noise)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mel_oracle, torch_port
+from tests.conftest import PSET_ARGS, golden_case_names, load_case, load_params, parity_error, regenerate_input
+from tests.golden import signals
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+TARGET = 2e-5
+WINDOW = 524160
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda", 0)
+
+
+@pytest.fixture(scope="module")
+def mods(dev):
+    from beatheritage_b200 import MelSpectrogram
+    out = {}
+    for pset, (log, n_mels, f_min, f_max, pad) in PSET_ARGS.items():
+        m = MelSpectrogram("torchaudio", log, 16000, 1024, n_mels, 128, f_min, f_max, pad).to(dev)
+        out[pset] = m
+    return out
+
+
+def run(mod, x, dev):
+    y = mod(torch.from_numpy(np.ascontiguousarray(x)).to(dev))
+    torch.cuda.synchronize()
+    return y.cpu().numpy()
+
+
+def test_native_library_is_loaded_and_kernel_launches(mods, dev):
+    from beatheritage_b200 import _lib
+    m = mods["P0"]
+    before = m.launch_count()
+    y = m(torch.zeros(1, 2048, device=dev))
+    torch.cuda.synchronize()
+    assert m.launch_count() == before + 1
+    assert y.shape == (1, 17, 80) and y.dtype == torch.float32 and y.is_contiguous()
+    assert torch.all(y == 0)                     # zero input -> exactly 0.0 (log1p(0)), SURVEY.md 0.1
+    maps = open("/proc/self/maps").read()
+    assert "libbhmel.so" in maps
+    assert _lib.lib().bhmel_version() == 100
+
+
+@pytest.mark.parametrize("name", golden_case_names())
+def test_golden_fixtures(mods, dev, name):
+    case, pset, frames = load_case(name)
+    log = PSET_ARGS[pset][0]
+    x = regenerate_input(case)
+    y = run(mods[pset], x, dev)
+    assert y.shape == tuple(case["shape"])
+    if frames is not None:
+        y = y[:, frames]
+    err = parity_error(y, case["y"], log)
+    assert err < TOL
+    assert err < TARGET, f"{name}: {err}"
+
+
+@pytest.mark.parametrize("bulk", [True, False])
+def test_bulk_and_cp_async_staging_agree(mods, dev, bulk):
+    m = mods["P0"]
+    x = signals.noise(3, 40000, 42)
+    m.set_bulk_copy(True)
+    y_bulk = run(m, x, dev)
+    m.set_bulk_copy(bulk)
+    y = run(m, x, dev)
+    m.set_bulk_copy(True)
+    assert np.array_equal(y, y_bulk)
+    window, fb = load_params("P0")
+    ref = mel_oracle.mel_forward(x, fb=fb, window=window, dtype=np.float64)
+    assert parity_error(y, ref, True) < TARGET
+
+
+@pytest.mark.parametrize("N", [513, 640, 1151, 4096, 4097, 12345, 131071])
+@pytest.mark.parametrize("pset", ["P0", "P0C"])
+def test_ragged_lengths(mods, dev, N, pset):
+    log, n_mels, f_min, f_max, pad = PSET_ARGS[pset]
+    window, fb = load_params(pset)
+    x = signals.noise(3, N, 5000 + N)
+    y = run(mods[pset], x, dev)
+    ref = mel_oracle.mel_forward(x, fb=fb, window=window, pad_mode=pad, dtype=np.float64)
+    assert y.shape == ref.shape
+    assert parity_error(y, ref, log) < TARGET
+
+
+def test_short_inputs_constant_pad(mods, dev):
+    window, fb = load_params("P0C")
+    for N in (1, 100, 128, 512):
+        x = signals.noise(2, N, N)
+        y = run(mods["P0C"], x, dev)
+        ref = mel_oracle.mel_forward(x, fb=fb, window=window, pad_mode="constant", dtype=np.float64)
+        assert parity_error(y, ref, True) < TARGET
+
+
+def test_strided_and_unaligned_rows(mods, dev):
+    """Row stride > N, and a base pointer that is not 16-byte aligned (forces the cp.async path)."""
+    m = mods["P0"]
+    window, fb = load_params("P0")
+    big = torch.from_numpy(signals.noise(4, 9001, 3)).to(dev)
+    view = big[:, 1:8193]                       # stride 9001, offset 1 element
+    y = m(view)
+    torch.cuda.synchronize()
+    ref = mel_oracle.mel_forward(view.cpu().numpy(), fb=fb, window=window, dtype=np.float64)
+    assert parity_error(y.cpu().numpy(), ref, True) < TARGET
+    yt = m(big.t().contiguous().t()[:, :4096])  # non-unit inner stride -> made contiguous by the wrapper
+    torch.cuda.synchronize()
+    ref = mel_oracle.mel_forward(big[:, :4096].cpu().numpy(), fb=fb, window=window, dtype=np.float64)
+    assert parity_error(yt.cpu().numpy(), ref, True) < TARGET
+
+
+def test_full_context_batch_c2(mods, dev):
+    """C2: a 3-min music-like song, 46 overlapped windows [46, 524160].  Checked
+    against the torch CPU port on every window, all frames."""
+    m = mods["P0"]
+    window, fb = load_params("P0")
+    song = signals.music(2_880_000, seed=1)
+    w, s = mel_oracle.segment_params()
+    seq = mel_oracle.segment(song, w, s)
+    assert seq.shape == (46, WINDOW)
+    y = run(m, seq, dev)
+    assert y.shape == (46, 4096, 80)
+    port = torch_port.TorchPortMel()
+    port.fb.copy_(torch.from_numpy(fb))
+    port.window.copy_(torch.from_numpy(window))
+    ref = port(torch.from_numpy(seq)).numpy()
+    assert parity_error(y, ref, True) < TARGET
+    # fused segmentation must give bit-identical frames without the [46, 524160] batch
+    yg = m.forward_gather(torch.from_numpy(song).to(dev), 0, s, 46, w)
+    torch.cuda.synchronize()
+    assert np.array_equal(yg.cpu().numpy(), y)
+    # parallel (non-overlapped) segmentation: 6 windows
+    seq6 = mel_oracle.segment(song, w, w)
+    y6 = m.forward_gather(torch.from_numpy(song).to(dev), 0, w, 6, w)
+    torch.cuda.synchronize()
+    assert np.array_equal(y6.cpu().numpy(), run(m, seq6, dev))
+
+
+def test_forward_host_matches_forward(mods, dev):
+    m = mods["P0"]
+    x = torch.from_numpy(signals.noise(37, 65536, 99))
+    y_dev = m(x.to(dev)).cpu()
+    xp = x.pin_memory()
+    y_host = m.forward_host(xp)
+    assert torch.equal(y_host, y_dev)
+    y_pageable = m.forward_host(x)            # pageable memory also works (slower)
+    assert torch.equal(y_pageable, y_dev)
+
+
+def test_properties_at_full_size(mods, dev):
+    """Size-independent properties on a [64, 524160] batch (no oracle needed at this size):
+    batch independence, determinism, power scaling (non-log set), zero rows, time shift."""
+    m = mods["P0"]
+    g = torch.Generator(device=dev).manual_seed(1234)
+    x = torch.rand(64, WINDOW, device=dev, generator=g) * 2 - 1
+    x[5].zero_()
+    y = m(x)
+    y2 = m(x)
+    assert torch.equal(y, y2)                                   # deterministic
+    assert torch.all(y[5] == 0)                                 # silent window -> exact zeros
+    sub = m(x[10:13].clone())
+    assert torch.equal(sub, y[10:13])                           # rows are independent
+    # shifting a row by one hop shifts the interior frames by one
+    xs = torch.roll(x[7:8], shifts=-128, dims=1)
+    ys = m(xs)
+    assert torch.allclose(ys[0, 8:4000], y[7, 9:4001], atol=2e-5)
+    # power scaling on the non-log parameter set: mel(a x) = a^2 mel(x)
+    p1 = mods["P1"]
+    xa = x[:4, :65536].contiguous()
+    ya, yb = p1(xa), p1(xa * 0.5)
+    assert torch.allclose(yb * 4, ya, rtol=1e-5, atol=1e-6)
+    # spot-check 3 windows of the big batch against the CPU port
+    window, fb = load_params("P0")
+    port = torch_port.TorchPortMel()
+    port.fb.copy_(torch.from_numpy(fb))
+    port.window.copy_(torch.from_numpy(window))
+    idx = [0, 31, 63]
+    ref = port(x[idx].cpu()).numpy()
+    assert parity_error(y[idx].cpu().numpy(), ref, True) < TARGET
+
+
+def test_state_dict_reload_rebuilds_device_tables(dev):
+    from beatheritage_b200 import MelSpectrogram
+    m = MelSpectrogram("torchaudio", False, 16000, 1024, 80, 128, 20, 8000, "reflect").to(dev)
+    x = torch.from_numpy(signals.noise(1, 8192, 1)).to(dev)
+    y1 = m(x)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    sd["transform.mel_scale.fb"] *= 3.0
+    m.load_state_dict(sd, strict=True)
+    y2 = m(x)
+    assert torch.allclose(y2, 3.0 * y1, rtol=1e-6)
+
+
+def test_dense_filterbank_from_state_dict(dev):
+    from beatheritage_b200 import MelSpectrogram
+    m = MelSpectrogram("torchaudio", False, 16000, 1024, 80, 128, 20, 8000, "reflect").to(dev)
+    rng = np.random.default_rng(3)
+    fb = rng.random((513, 80), dtype=np.float32)
+    fb[:, 3] = 0.0
+    with torch.no_grad():
+        m.transform.mel_scale.fb.copy_(torch.from_numpy(fb))
+    x = signals.noise(1, 5000, 9)
+    y = run(m, x, dev)
+    window, _ = load_params("P0")
+    ref = mel_oracle.mel_forward(x, fb=fb, window=window, log_scale=False, dtype=np.float64)
+    assert np.all(y[..., 3] == 0)
+    assert np.abs(y - ref).max() / ref.max() < 1e-5
+
+
+def test_runs_on_a_side_stream_and_under_autocast(mods, dev):
+    m = mods["P0"]
+    x = torch.from_numpy(signals.noise(2, 30000, 8)).to(dev)
+    ref = m(x)
+    s = torch.cuda.Stream(device=dev)
+    s.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(s), torch.autocast("cuda", dtype=torch.bfloat16), torch.no_grad():
+        y = m(x)
+        assert y.dtype == torch.float32            # the frontend ignores autocast (always fp32)
+    s.synchronize()
+    assert torch.equal(y, ref)
+    assert torch.equal(m(x.double()), ref)         # non-fp32 input is converted
+
+
+def test_c_abi_errors_on_device(dev):
+    from beatheritage_b200 import _lib
+    lib = _lib.lib()
+    prm = _lib.BhmelParams(16000, 1024, 128, 80, 20.0, 8000.0, _lib.PAD_REFLECT, 1, None, None)
+    h = ctypes.c_void_p()
+    _lib.check(lib.bhmel_create(ctypes.byref(prm), ctypes.byref(h)))
+    x = torch.zeros(2, 512, device=dev)
+    y = torch.zeros(2, 5, 80, device=dev)
+    assert lib.bhmel_forward(h, x.data_ptr(), 2, 512, 512, y.data_ptr(), None) == _lib.ESHAPE
+    assert b"reflect" in lib.bhmel_last_error()
+    assert lib.bhmel_forward(h, x.data_ptr(), 0, 4096, 4096, y.data_ptr(), None) == _lib.ESHAPE
+    assert lib.bhmel_forward(h, None, 2, 4096, 4096, y.data_ptr(), None) == _lib.EINVAL
+    assert lib.bhmel_forward(h, x.data_ptr(), 2, 4096, 100, y.data_ptr(), None) == _lib.EINVAL
+    # the library's own C++ filterbank/window builders (no override) stay inside the bar
+    xs = torch.from_numpy(signals.noise(1, 6000, 5)).to(dev)
+    ys = torch.empty(1, 47, 80, device=dev)
+    _lib.check(lib.bhmel_forward(h, xs.data_ptr(), 1, 6000, 6000, ys.data_ptr(), None))
+    torch.cuda.synchronize()
+    ref = mel_oracle.mel_forward(xs.cpu().numpy(), dtype=np.float64)
+    assert parity_error(ys.cpu().numpy(), ref, True) < 1e-4
+    lib.bhmel_destroy(h)
+
+
+def test_torch_compile_does_not_graph_break(mods, dev):
+    m = mods["P0"]
+
+    class Wrap(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.spectrogram = m
+
+        def forward(self, frames):
+            return self.spectrogram(frames).to(torch.bfloat16).sum(-1)
+
+    w = Wrap()
+    x = torch.from_numpy(signals.noise(2, 16384, 4)).to(dev)
+    try:
+        cw = torch.compile(w, fullgraph=True)
+        out = cw(x)
+    except Exception as e:   # inductor needs a working host compiler/triton; not the subject here
+        pytest.skip(f"torch.compile unavailable in this environment: {type(e).__name__}")
+    assert torch.allclose(out.float(), w(x).float(), atol=1e-1)

@@ -1,0 +1,136 @@
+"""CPU: host-side mirror of the reference interface (no kernel launches)."""
+import copy
+import inspect
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from beatheritage_b200 import MelSpectrogram
+from beatheritage_b200 import segment as seg
+from beatheritage_b200.spectrogram import melscale_fbanks_htk
+from oracle import mel_oracle, ref_loader
+from tests.conftest import PSET_ARGS, load_params
+
+P0 = ("torchaudio", True, 16000, 1024, 80, 128, 20, 8000, "reflect")
+
+
+def test_constructor_signature_matches_reference():
+    sig = inspect.signature(MelSpectrogram.__init__)
+    names = list(sig.parameters)[1:]
+    assert names == ["implementation", "log_scale", "sample_rate", "n_ftt", "n_mels", "hop_length", "f_min",
+                     "f_max", "pad_mode"]                     # reference spectrogram.py:8-19, positional order matters
+    defaults = [sig.parameters[n].default for n in names]
+    assert defaults == ["nnAudio", False, 16000, 2048, 512, 128, 0, 8000, "constant"]
+    if ref_loader.available():
+        ref_sig = inspect.signature(ref_loader.load_reference_class().__init__)
+        assert list(ref_sig.parameters) == list(sig.parameters)
+        assert [p.default for p in ref_sig.parameters.values()] == [p.default for p in sig.parameters.values()]
+
+
+def test_positional_and_keyword_construction_like_the_call_sites():
+    m = MelSpectrogram(*P0)                                   # modeling_mapperatorinator.py:56-66
+    assert (m.n_mels, m.pad_mode, m.log_scale) == (80, "reflect", True)
+    m2 = MelSpectrogram("torchaudio", True, 16000, 1024, 80, 128, f_min=20, f_max=8000)   # dataloading.py:81-90
+    assert m2.pad_mode == "constant"
+
+
+def test_state_dict_keys_and_buffers_match_reference():
+    m = MelSpectrogram(*P0)
+    sd = m.state_dict()
+    assert list(sd) == ["transform.spectrogram.window", "transform.mel_scale.fb"]
+    assert sd["transform.spectrogram.window"].shape == (1024,)
+    assert sd["transform.mel_scale.fb"].shape == (513, 80)
+    assert len(list(m.parameters())) == 0
+    for pset, (log, n_mels, f_min, f_max, pad) in PSET_ARGS.items():
+        window, fb = load_params(pset)            # the reference module's own buffers
+        mm = MelSpectrogram("torchaudio", log, 16000, 1024, n_mels, 128, f_min, f_max, pad)
+        assert np.array_equal(mm.transform.spectrogram.window.numpy(), window)
+        assert np.array_equal(mm.transform.mel_scale.fb.numpy(), fb), pset
+
+
+def test_strict_load_of_a_reference_state_dict():
+    window, fb = load_params("P0")
+    ref_sd = {"transform.spectrogram.window": torch.from_numpy(window), "transform.mel_scale.fb": torch.from_numpy(fb * 2)}
+    m = MelSpectrogram(*P0)
+    stamp = m._buffer_stamp()
+    m.load_state_dict(ref_sd, strict=True)                   # inference.py:478-480 loads strictly
+    assert torch.equal(m.transform.mel_scale.fb, torch.from_numpy(fb * 2))
+    assert m._buffer_stamp() != stamp                         # device tables will be rebuilt
+
+    class Model(torch.nn.Module):                             # attribute name carries "spectrogram" (inference.py:486-489)
+        def __init__(self):
+            super().__init__()
+            self.spectrogram = MelSpectrogram(*P0)
+    keys = list(Model().state_dict())
+    assert keys == ["spectrogram.transform.spectrogram.window", "spectrogram.transform.mel_scale.fb"]
+
+
+def test_errors_mirror_the_reference():
+    with pytest.raises(AssertionError):
+        MelSpectrogram("librosa")                             # spectrogram.py:35
+    with pytest.raises(NotImplementedError):
+        MelSpectrogram()                                      # nnAudio arithmetic is unpinned
+    with pytest.raises(ValueError):
+        MelSpectrogram("torchaudio", True, 16000, 2048)
+    m = MelSpectrogram(*P0)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(4, 3, 2048))                            # not [batch, samples]
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(2, 512))                                # reflect pad needs N > 512 (F.pad raises)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(2, 4096))                               # no CPU fallback by design
+
+
+def test_module_survives_copy_and_pickle_without_carrying_handles():
+    m = MelSpectrogram(*P0)
+    m._handles[0] = 12345
+    c = copy.deepcopy(m)
+    assert c._handles == {} and c._key != m._key
+    p = pickle.loads(pickle.dumps(m))
+    assert p._handles == {} and p.n_mels == 80
+    m._handles.clear()
+
+
+def test_fake_kernel_gives_shapes_for_compile():
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    m = MelSpectrogram(*P0)
+    with FakeTensorMode():
+        x = torch.empty(6, 524160, device="cuda")
+        y = torch.ops.beatheritage_b200.mel_forward(x, m._key, 80)
+        assert tuple(y.shape) == (6, 4096, 80) and y.dtype == torch.float32
+
+
+def test_torch_fb_builder_equals_oracle_restatement_for_p0():
+    fb = melscale_fbanks_htk(513, 20.0, 8000.0, 80, 16000).numpy()
+    assert np.array_equal(fb, mel_oracle.melscale_fbanks(513, 20.0, 8000.0, 80, 16000, np.float32))
+
+
+def test_segment_plan_matches_oracle_segment():
+    for n, kw in [(2_880_000, {}), (2_880_000, dict(parallel=True)), (57_600_000, {}), (1000, {}),
+                  (524160, {}), (524161, {}), (600000, dict(lookback=0.25, lookahead=0.25))]:
+        plan = seg.segment_plan(n, **kw)
+        w, s = mel_oracle.segment_params(lookback=kw.get("lookback", 0.5), lookahead=kw.get("lookahead", 0.4),
+                                         parallel=kw.get("parallel", False))
+        assert (plan.window_len, plan.stride) == (w, s)
+        if n <= 3_000_000:
+            assert plan.n_windows == mel_oracle.segment(np.zeros(n, np.float32), w, s).shape[0]
+    assert seg.segment_plan(2_880_000).n_windows == 46
+    assert seg.segment_plan(57_600_000).n_windows == 1090
+    assert seg.segment_plan(57_600_000, parallel=True).n_windows == 110
+
+
+def test_dataset_window_plan_matches_oracle():
+    for n in (2_880_000, 2_880_001, 1280, 100):
+        plan = seg.dataset_window_plan(n)
+        assert plan.n_windows == mel_oracle.dataset_windows(np.zeros(n, np.float32)).shape[0]
+    assert seg.dataset_window_plan(2_880_000).n_windows == 6
+
+
+def test_shard_range_partitions_everything_once():
+    for n, ws in [(4096, 8), (10, 4), (3, 8), (0, 2)]:
+        seen = sorted(i for r in range(ws) for i in seg.shard_range(n, r, ws))
+        assert seen == list(range(n))
+    with pytest.raises(ValueError):
+        seg.shard_range(10, 4, 4)

@@ -1,0 +1,115 @@
+"""CPU: pins the oracle (oracle/mel_oracle.py, oracle/torch_port.py) to the golden fixtures that
+tests/golden/make_golden.py produced by running the UNMODIFIED reference module, and -- when the
+reference tree is present (build container) -- to the live reference."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mel_oracle, ref_loader, torch_port
+from tests.conftest import PSET_ARGS, golden_case_names, load_case, load_params, parity_error, regenerate_input
+
+SMALL = [n for n in golden_case_names() if n not in ("music_2win", "zero_tail", "noise_N524161")]
+BIG = ["music_2win", "zero_tail", "noise_N524161"]
+
+
+@pytest.mark.parametrize("name", SMALL + BIG)
+def test_fp64_oracle_matches_reference_fixtures(name):
+    case, pset, frames = load_case(name)
+    log, n_mels, f_min, f_max, pad = PSET_ARGS[pset]
+    window, fb = load_params(pset)
+    x = regenerate_input(case)
+    y = mel_oracle.mel_forward(x, n_mels=n_mels, f_min=f_min, f_max=f_max, pad_mode=pad, log_scale=log,
+                               dtype=np.float64, fb=fb, window=window)
+    assert y.shape == tuple(case["shape"])
+    if frames is not None:
+        y = y[:, frames]
+    if "y64" in case.files:   # the same module run in fp64: the oracle restates it to rounding error
+        np.testing.assert_allclose(y, case["y64"], rtol=1e-10, atol=1e-10)
+    # fp32 reference output vs fp64 oracle: the reference's own rounding noise, well under the 1e-3 bar
+    assert parity_error(case["y"], y, log) < 2e-5
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_fp32_oracle_and_torch_port_match_fixtures(name):
+    case, pset, frames = load_case(name)
+    log, n_mels, f_min, f_max, pad = PSET_ARGS[pset]
+    window, fb = load_params(pset)
+    x = regenerate_input(case)
+    y32 = mel_oracle.mel_forward(x, n_mels=n_mels, f_min=f_min, f_max=f_max, pad_mode=pad, log_scale=log,
+                                 dtype=np.float32, fb=fb, window=window)
+    assert parity_error(y32, case["y"], log) < 2e-5
+    port = torch_port.TorchPortMel(log, 16000, 1024, n_mels, 128, f_min, f_max, pad)
+    port.fb.copy_(torch.from_numpy(fb))
+    port.window.copy_(torch.from_numpy(window))
+    yp = port(torch.from_numpy(x)).numpy()
+    assert yp.shape == tuple(case["shape"])
+    assert parity_error(yp, case["y"], log) < 2e-5
+
+
+@pytest.mark.parametrize("pset", sorted(PSET_ARGS))
+def test_filterbank_and_window_restatement(pset):
+    log, n_mels, f_min, f_max, pad = PSET_ARGS[pset]
+    window, fb = load_params(pset)
+    fb32 = mel_oracle.melscale_fbanks(513, float(f_min), float(f_max), n_mels, 16000, np.float32)
+    fb64 = mel_oracle.melscale_fbanks(513, float(f_min), float(f_max), n_mels, 16000, np.float64)
+    assert fb32.shape == fb.shape == (513, n_mels)
+    # fp32 restatement: bit-exact for P0; elsewhere a few ulps of torch's fp32 pow leak through
+    assert np.abs(fb32 - fb).max() < 1e-4
+    assert np.abs(fb64 - fb).max() < 1e-4
+    if pset == "P0":
+        assert np.array_equal(fb32, fb)
+        nz = fb != 0
+        assert nz.sum() == 1003 and nz.sum(0).min() == 3 and nz.sum(0).max() == 33
+    assert np.abs(mel_oracle.hann_window(1024) - window).max() < 2e-7
+
+
+def test_reflect_needs_more_than_half_window():
+    with pytest.raises(RuntimeError):
+        mel_oracle.mel_forward(np.zeros((1, 512), np.float32))
+    assert mel_oracle.mel_forward(np.zeros((1, 513), np.float32)).shape == (1, 5, 80)
+    assert mel_oracle.mel_forward(np.zeros((1, 100), np.float32), pad_mode="constant").shape == (1, 1, 80)
+
+
+def test_zero_input_gives_exact_zero():
+    y = mel_oracle.mel_forward(np.zeros((2, 2048), np.float32))
+    assert np.all(y == 0.0)
+
+
+def test_segment_matches_reference_numbers():
+    # 3-min song -> 46 windows at stride 52 415 (6 when parallel); 1 h -> 1 090 / 110
+    w, s = mel_oracle.segment_params()
+    assert (w, s) == (524160, 52415)
+    assert mel_oracle.segment_params(parallel=True) == (524160, 524160)
+    song = np.arange(2_880_000, dtype=np.float32)
+    seq = mel_oracle.segment(song, w, s)
+    assert seq.shape == (46, 524160)
+    assert seq[3, 0] == 3 * 52415 and seq[-1, -1] == 0.0     # right padding is zeros
+    assert mel_oracle.segment(song, w, w).shape == (6, 524160)
+    assert mel_oracle.segment(np.zeros(1000, np.float32), w, s).shape == (1, 524160)
+
+
+def test_dataset_windows_match_reference_numbers():
+    # 180 s song: 22 501 hop-frames -> 6 windows, the last with 2 026 real hop-frames
+    song = np.ones(2_880_000, np.float32)
+    win = mel_oracle.dataset_windows(song)
+    assert win.shape == (6, 524160)
+    # ... 2 026 hop-frames of which the last one is the extra all-zero hop _get_frames appends
+    real = np.count_nonzero(win[-1].reshape(4095, 128).any(axis=1))
+    assert real == 2025
+    # an already hop-aligned song still gains one zero hop-frame (ors_dataset.py:256)
+    assert mel_oracle.dataset_windows(np.ones(128 * 10, np.float32), src_seq_len=5).shape == (3, 512)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree only exists in the build container")
+def test_live_reference_agrees_with_oracle_and_fixtures():
+    Ref = ref_loader.load_reference_class()
+    ref = Ref("torchaudio", True, 16000, 1024, 80, 128, 20, 8000, "reflect")
+    window, fb = load_params("P0")
+    sd = ref.state_dict()
+    assert list(sd) == ["transform.spectrogram.window", "transform.mel_scale.fb"]
+    assert np.array_equal(sd["transform.mel_scale.fb"].numpy(), fb)
+    rng = np.random.default_rng(11)
+    x = (rng.random((3, 6000), dtype=np.float32) * 2 - 1)
+    y_ref = ref(torch.from_numpy(x)).numpy()
+    y = mel_oracle.mel_forward(x, fb=fb, window=window, dtype=np.float64)
+    assert parity_error(y_ref, y, True) < 2e-5
