@@ -44,6 +44,7 @@ struct bhmel_handle {
   float2* d_tw = nullptr;
   bhmel::FilterBand* d_bands = nullptr;
   float* d_weights = nullptr;
+  int n_weights = 0;
   std::atomic<int64_t> launches{0};
   int use_bulk = 1;
   // bhmel_forward_host pipeline (lazily created)
@@ -70,6 +71,7 @@ int upload_filterbank(bhmel_handle* h) {
                      cudaMemcpyHostToDevice));
   BH_CUDA(cudaMemcpy(h->d_weights, t.weights.data(), t.weights.size() * sizeof(float),
                      cudaMemcpyHostToDevice));
+  h->n_weights = static_cast<int>(t.weights.size());
   return BHMEL_OK;
 }
 
@@ -122,6 +124,7 @@ int launch(bhmel_handle* h, const float* x, long long row_stride, long long row0
   p.pad_reflect = h->prm.pad_mode == BHMEL_PAD_REFLECT;
   p.log_scale = h->prm.log_scale != 0;
   p.use_bulk = h->use_bulk;
+  p.n_weights = h->n_weights;
 
   const long long grid = p.n_tiles < h->num_sms ? p.n_tiles : h->num_sms;
   bhmel::bhmel_logmel_kernel<<<static_cast<unsigned>(grid), bhmel::kThreads, sizeof(bhmel::SmemLayout),

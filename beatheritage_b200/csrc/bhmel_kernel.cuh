@@ -44,14 +44,16 @@ constexpr int kScrPitch = 33;                             // complex elements pe
 constexpr int kMChunk = 96;                               // mel filters per epilogue chunk
 constexpr int kOutPitch = kMChunk + 1;                    // odd -> conflict-free lane=frame writes
 constexpr int kPairs = kTileF / 2;
+constexpr int kFwCap = 4096;                              // floats of filter weights kept in shared memory
+constexpr int kBandCap = 512;                             // filters whose descriptors are kept in shared memory
 
 struct SmemLayout {
   float P[kTileF * kPPitch];                  // 66 048 B  power spectra of the tile
   float2 scr[kWarps][32 * kScrPitch];         // 67 584 B  per-warp transpose scratch
   float span[2][kSpan];                       // 39 936 B  double-buffered sample span
   float out[kTileF * kOutPitch];              // 12 416 B  epilogue staging
-  float win[kNfft];                           //  4 096 B  0.5 * window
-  float2 tw[32 * 32];                         //  8 192 B  W_1024^(a*b)
+  float fw[kFwCap];                           // 16 384 B  banded filter weights (when they fit)
+  int4 bands[kBandCap];                       //  8 192 B  per-filter band descriptors (when they fit)
   unsigned long long mbar[2];
 };
 
@@ -74,6 +76,7 @@ struct KParams {
   int pad_reflect;
   int log_scale;
   int use_bulk;
+  int n_weights;           // floats in `weights` (multiple of 4)
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -152,6 +155,37 @@ __device__ __forceinline__ bool stage_span(const KParams& p, long long tile, flo
   return false;
 }
 
+// ---------------------------------------------------------------- stage 3 helpers
+// Dot product of one filter's band (NG groups of 4 bins) with this lane's frame: P row via
+// conflict-free LDS.128, weights via warp-uniform (broadcast) 128-bit loads.
+template <int NG>
+__device__ __forceinline__ float band_dot(const float4* __restrict__ pp, const float4* __restrict__ wp) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    const float4 w4 = wp[g];
+    const float4 p4 = pp[g];
+    a0 = fmaf(p4.x, w4.x, a0);
+    a1 = fmaf(p4.y, w4.y, a1);
+    a2 = fmaf(p4.z, w4.z, a2);
+    a3 = fmaf(p4.w, w4.w, a3);
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+__device__ __forceinline__ float band_dot_n(const float4* __restrict__ pp, const float4* __restrict__ wp, int ng) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+  for (int g = 0; g < ng; ++g) {
+    const float4 w4 = wp[g];
+    const float4 p4 = pp[g];
+    a0 = fmaf(p4.x, w4.x, a0);
+    a1 = fmaf(p4.y, w4.y, a1);
+    a2 = fmaf(p4.z, w4.z, a2);
+    a3 = fmaf(p4.w, w4.w, a3);
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+
 // ---------------------------------------------------------------- the kernel
 __global__ void __launch_bounds__(kThreads, 1) bhmel_logmel_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -160,11 +194,25 @@ __global__ void __launch_bounds__(kThreads, 1) bhmel_logmel_kernel(const __grid_
   const int warp = tid >> 5;
   const int lane = tid & 31;
 
-  // one-time: constant tables -> shared memory, zero the pad columns of P, init mbarriers
-  for (int i = tid; i < kNfft; i += kThreads) {
-    S.win[i] = p.win_half[i];
-    S.tw[i] = p.tw[i];
+  // one-time: this lane's window samples and inter-pass twiddles live in registers for the whole
+  // kernel (one CTA per SM leaves 255 registers per thread); filter tables -> shared memory when
+  // they fit; zero the pad columns of P; init mbarriers
+  float wreg[32], twr[32], twi[32];
+#pragma unroll
+  for (int m = 0; m < 32; ++m) {
+    wreg[m] = __ldg(p.win_half + lane + 32 * m);
+    const float2 t = __ldg(p.tw + m * 32 + lane);
+    twr[m] = t.x;
+    twi[m] = t.y;
   }
+  const bool fw_in_smem = p.n_weights <= kFwCap;
+  const bool bands_in_smem = p.n_mels <= kBandCap;
+  if (fw_in_smem)
+    for (int i = tid; i < p.n_weights; i += kThreads) S.fw[i] = p.weights[i];
+  if (bands_in_smem)
+    for (int i = tid; i < p.n_mels; i += kThreads) S.bands[i] = reinterpret_cast<const int4*>(p.bands)[i];
+  const float* wbase = fw_in_smem ? S.fw : p.weights;
+  const int4* bbase = bands_in_smem ? S.bands : reinterpret_cast<const int4*>(p.bands);
   for (int i = tid; i < kTileF * (kPPitch - kBins); i += kThreads)
     S.P[(i / (kPPitch - kBins)) * kPPitch + kBins + i % (kPPitch - kBins)] = 0.f;
   if (tid == 0) {
@@ -202,13 +250,11 @@ __global__ void __launch_bounds__(kThreads, 1) bhmel_logmel_kernel(const __grid_
     for (int j = warp; j < kPairs; j += kWarps) {
       float ar[32], ai[32];
       {
-        float v[36], w[32];
+        float v[36];
         const float* sp = span + (2 * j) * kHop + lane;
 #pragma unroll
         for (int m = 0; m < 36; ++m) v[m] = sp[32 * m];
-#pragma unroll
-        for (int m = 0; m < 32; ++m) w[m] = S.win[lane + 32 * m];
-        fft32_pass_a(v, w, ar, ai);
+        fft32_pass_a(v, wreg, ar, ai);
       }
       // transpose: thread (lane = n2) holds Y[k1] -> thread (lane = k1) holds Y[n2]
 #pragma unroll
@@ -216,18 +262,15 @@ __global__ void __launch_bounds__(kThreads, 1) bhmel_logmel_kernel(const __grid_
       __syncwarp();
       float br[32], bi[32];
       {
-        float ur[32], ui[32], tr[32], ti[32];
+        float ur[32], ui[32];
 #pragma unroll
         for (int n = 0; n < 32; ++n) {
           const float2 u = scr[lane * kScrPitch + n];
           ur[n] = u.x;
           ui[n] = u.y;
-          const float2 t = S.tw[n * 32 + lane];
-          tr[n] = t.x;
-          ti[n] = t.y;
         }
         __syncwarp();   // all lanes have read the scratch before the next pair overwrites it
-        fft32_pass_b(ur, ui, tr, ti, br, bi);
+        fft32_pass_b(ur, ui, twr, twi, br, bi);
       }
       // Z[k], k = lane + 32*k2.  Partner bin 1024-k lives in lane (32-lane)&31, slot 31-k2
       // (lane 0: its own slot (32-k2)&31).  Xa = (Z[k] + conj Z[N-k])/2, Xb = (Z[k] - conj Z[N-k])/2i;
@@ -268,22 +311,24 @@ __global__ void __launch_bounds__(kThreads, 1) bhmel_logmel_kernel(const __grid_
       const int mcount = (p.n_mels - mc) < kMChunk ? (p.n_mels - mc) : kMChunk;
       if (mc > 0) __syncthreads();   // previous chunk's staging fully stored
       for (int m = warp; m < mcount; m += kWarps) {
-        const int4 fb4 = __ldg(reinterpret_cast<const int4*>(p.bands) + mc + m);
-        FilterBand fbnd;
-        fbnd.g0 = fb4.x; fbnd.ng = fb4.y; fbnd.woff = fb4.z; fbnd.pad = 0;
-        const float4* wp = reinterpret_cast<const float4*>(p.weights + fbnd.woff);
-        const float4* pp = prow + fbnd.g0;
-        float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 2
-        for (int g = 0; g < fbnd.ng; ++g) {
-          const float4 w4 = __ldg(wp + g);
-          const float4 p4 = pp[g];
-          acc0 = fmaf(p4.x, w4.x, acc0);
-          acc1 = fmaf(p4.y, w4.y, acc1);
-          acc0 = fmaf(p4.z, w4.z, acc0);
-          acc1 = fmaf(p4.w, w4.w, acc1);
+        const int4 bd = bbase[mc + m];                       // {g0, ng, woff, -}: warp-uniform
+        const float4* wp = reinterpret_cast<const float4*>(wbase + bd.z);
+        const float4* pp = prow + bd.x;
+        float v;
+        switch (bd.y) {
+          case 0: v = 0.f; break;
+          case 1: v = band_dot<1>(pp, wp); break;
+          case 2: v = band_dot<2>(pp, wp); break;
+          case 3: v = band_dot<3>(pp, wp); break;
+          case 4: v = band_dot<4>(pp, wp); break;
+          case 5: v = band_dot<5>(pp, wp); break;
+          case 6: v = band_dot<6>(pp, wp); break;
+          case 7: v = band_dot<7>(pp, wp); break;
+          case 8: v = band_dot<8>(pp, wp); break;
+          case 9: v = band_dot<9>(pp, wp); break;
+          case 10: v = band_dot<10>(pp, wp); break;
+          default: v = band_dot_n(pp, wp, bd.y); break;
         }
-        float v = acc0 + acc1;
         if (p.log_scale) v = __logf(1.0f + v);
         S.out[lane * kOutPitch + m] = v;
       }

@@ -265,7 +265,7 @@ def test_torch_compile_does_not_graph_break(mods, dev):
             self.spectrogram = m
 
         def forward(self, frames):
-            return self.spectrogram(frames).to(torch.bfloat16).sum(-1)
+            return self.spectrogram(frames) * 2.0 + 1.0
 
     w = Wrap()
     x = torch.from_numpy(signals.noise(2, 16384, 4)).to(dev)
@@ -274,4 +274,4 @@ def test_torch_compile_does_not_graph_break(mods, dev):
         out = cw(x)
     except Exception as e:   # inductor needs a working host compiler/triton; not the subject here
         pytest.skip(f"torch.compile unavailable in this environment: {type(e).__name__}")
-    assert torch.allclose(out.float(), w(x).float(), atol=1e-1)
+    assert torch.allclose(out, w(x), atol=1e-6)

@@ -1,0 +1,28 @@
+"""Profiling target: a few launches of the bench workload (256 windows per launch, P0)."""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from beatheritage_b200 import MelSpectrogram  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--reps", type=int, default=4)
+ap.add_argument("--samples", type=int, default=524160)
+ap.add_argument("--mels", type=int, default=80)
+a = ap.parse_args()
+dev = torch.device("cuda", 0)
+mel = MelSpectrogram("torchaudio", True, 16000, 1024, a.mels, 128, 20, 8000, "reflect").to(dev)
+g = torch.Generator(device=dev).manual_seed(1234)
+x = torch.rand(a.batch, a.samples, device=dev, generator=g).mul_(2).sub_(1)
+torch.cuda.synchronize()
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.reps + 1)]
+ev[0].record()
+for i in range(a.reps):
+    y = mel(x)
+    ev[i + 1].record()
+torch.cuda.synchronize()
+print("ms per launch:", [round(ev[i].elapsed_time(ev[i + 1]), 4) for i in range(a.reps)], "sum", float(y.sum()))
