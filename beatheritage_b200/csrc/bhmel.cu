@@ -42,9 +42,10 @@ struct bhmel_handle {
   std::vector<float> window;   // host copy [1024]
   float* d_win = nullptr;      // 0.5 * window
   float2* d_tw = nullptr;
-  bhmel::FilterBand* d_bands = nullptr;
+  bhmel::PairDesc* d_pairs = nullptr;
   float* d_weights = nullptr;
   int n_weights = 0;
+  int n_pairs = 0;
   std::atomic<int64_t> launches{0};
   int use_bulk = 1;
   // bhmel_forward_host pipeline (lazily created)
@@ -58,20 +59,23 @@ struct bhmel_handle {
 namespace {
 
 int upload_filterbank(bhmel_handle* h) {
-  bhmel::BandTables t = bhmel::make_bands(h->fb.data(), h->prm.n_mels);
+  bhmel::PairTables t = bhmel::make_pairs(h->fb.data(), h->prm.n_mels);
+  if (t.pairs.size() > static_cast<size_t>(bhmel::kPairCap))
+    return fail(BHMEL_EINVAL, "too many filter pairs for the kernel's descriptor table");
   // The tables may be in use by kernels in flight on any stream of this device.
   BH_CUDA(cudaDeviceSynchronize());
-  if (h->d_bands) cudaFree(h->d_bands);
+  if (h->d_pairs) cudaFree(h->d_pairs);
   if (h->d_weights) cudaFree(h->d_weights);
-  h->d_bands = nullptr;
+  h->d_pairs = nullptr;
   h->d_weights = nullptr;
-  BH_CUDA(cudaMalloc(&h->d_bands, t.bands.size() * sizeof(bhmel::FilterBand)));
+  BH_CUDA(cudaMalloc(&h->d_pairs, t.pairs.size() * sizeof(bhmel::PairDesc)));
   BH_CUDA(cudaMalloc(&h->d_weights, t.weights.size() * sizeof(float)));
-  BH_CUDA(cudaMemcpy(h->d_bands, t.bands.data(), t.bands.size() * sizeof(bhmel::FilterBand),
+  BH_CUDA(cudaMemcpy(h->d_pairs, t.pairs.data(), t.pairs.size() * sizeof(bhmel::PairDesc),
                      cudaMemcpyHostToDevice));
   BH_CUDA(cudaMemcpy(h->d_weights, t.weights.data(), t.weights.size() * sizeof(float),
                      cudaMemcpyHostToDevice));
   h->n_weights = static_cast<int>(t.weights.size());
+  h->n_pairs = static_cast<int>(t.pairs.size());
   return BHMEL_OK;
 }
 
@@ -117,7 +121,7 @@ int launch(bhmel_handle* h, const float* x, long long row_stride, long long row0
   p.y = y;
   p.win_half = h->d_win;
   p.tw = h->d_tw;
-  p.bands = h->d_bands;
+  p.pairs = h->d_pairs;
   p.weights = h->d_weights;
   p.B = static_cast<int>(B);
   p.n_mels = h->prm.n_mels;
@@ -125,6 +129,7 @@ int launch(bhmel_handle* h, const float* x, long long row_stride, long long row0
   p.log_scale = h->prm.log_scale != 0;
   p.use_bulk = h->use_bulk;
   p.n_weights = h->n_weights;
+  p.n_pairs = h->n_pairs;
 
   const long long grid = p.n_tiles < h->num_sms ? p.n_tiles : h->num_sms;
   bhmel::bhmel_logmel_kernel<<<static_cast<unsigned>(grid), bhmel::kThreads, sizeof(bhmel::SmemLayout),
@@ -213,7 +218,7 @@ void bhmel_destroy(bhmel_handle* h) {
   }
   if (h->d_win) cudaFree(h->d_win);
   if (h->d_tw) cudaFree(h->d_tw);
-  if (h->d_bands) cudaFree(h->d_bands);
+  if (h->d_pairs) cudaFree(h->d_pairs);
   if (h->d_weights) cudaFree(h->d_weights);
   if (prev >= 0) cudaSetDevice(prev);
   delete h;

@@ -41,11 +41,11 @@ constexpr int kPPitch = 516;                              // 513 bins + pad; /4 
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kScrPitch = 33;                             // complex elements per transpose row
-constexpr int kMChunk = 96;                               // mel filters per epilogue chunk
+constexpr int kMChunk = kMelChunk;                        // mel filters per epilogue chunk (96)
 constexpr int kOutPitch = kMChunk + 1;                    // odd -> conflict-free lane=frame writes
 constexpr int kPairs = kTileF / 2;
 constexpr int kFwCap = 4096;                              // floats of filter weights kept in shared memory
-constexpr int kBandCap = 512;                             // filters whose descriptors are kept in shared memory
+constexpr int kPairCap = 512;                             // filter-pair descriptors (n_mels <= 1024)
 
 struct SmemLayout {
   float P[kTileF * kPPitch];                  // 66 048 B  power spectra of the tile
@@ -53,7 +53,7 @@ struct SmemLayout {
   float span[2][kSpan];                       // 39 936 B  double-buffered sample span
   float out[kTileF * kOutPitch];              // 12 416 B  epilogue staging
   float fw[kFwCap];                           // 16 384 B  banded filter weights (when they fit)
-  int4 bands[kBandCap];                       //  8 192 B  per-filter band descriptors (when they fit)
+  int4 pairs[kPairCap];                       //  8 192 B  filter-pair descriptors (PairDesc)
   unsigned long long mbar[2];
 };
 
@@ -68,15 +68,16 @@ struct KParams {
   float* y;                // [B][T][n_mels]
   const float* win_half;   // [1024]
   const float2* tw;        // [32*32]
-  const FilterBand* bands; // [n_mels]
-  const float* weights;
+  const PairDesc* pairs;   // [n_pairs]  (bhmel_tables.h make_pairs)
+  const float* weights;    // interleaved pair weights
   int B;
   int tiles_per_row;
   int n_mels;
   int pad_reflect;
   int log_scale;
   int use_bulk;
-  int n_weights;           // floats in `weights` (multiple of 4)
+  int n_weights;           // floats in `weights` (multiple of 8)
+  int n_pairs;
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -97,18 +98,24 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+  return ok != 0;
+}
+// The spin loop is written in C++ (not inside the asm block) so the compiler knows about the
+// branch and reconverges the warp afterwards.
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
 }
 // TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
@@ -156,34 +163,81 @@ __device__ __forceinline__ bool stage_span(const KParams& p, long long tile, flo
 }
 
 // ---------------------------------------------------------------- stage 3 helpers
-// Dot product of one filter's band (NG groups of 4 bins) with this lane's frame: P row via
-// conflict-free LDS.128, weights via warp-uniform (broadcast) 128-bit loads.
-template <int NG>
-__device__ __forceinline__ float band_dot(const float4* __restrict__ pp, const float4* __restrict__ wp) {
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+// Dot products of one filter PAIR (NG groups of 4 bins each, zero padded to equal length) with
+// this lane's frame: P rows via conflict-free LDS.128, weights via warp-uniform 128-bit loads
+// (shared memory when the table fits, else the read-only global path).  Eight independent FMA
+// chains per lane.
+template <bool kSmemW>
+__device__ __forceinline__ float4 ldw(const float4* p) {
+  if constexpr (kSmemW) return *p;
+  else return __ldg(p);
+}
+template <int NG, bool kSmemW>
+__device__ __forceinline__ void band_dot2(const float4* __restrict__ pa, const float4* __restrict__ pb,
+                                          const float4* __restrict__ wp, float& va, float& vb) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
-    const float4 w4 = wp[g];
-    const float4 p4 = pp[g];
-    a0 = fmaf(p4.x, w4.x, a0);
-    a1 = fmaf(p4.y, w4.y, a1);
-    a2 = fmaf(p4.z, w4.z, a2);
-    a3 = fmaf(p4.w, w4.w, a3);
+    const float4 wa = ldw<kSmemW>(wp + 2 * g), wb = ldw<kSmemW>(wp + 2 * g + 1);
+    const float4 xa = pa[g], xb = pb[g];
+    a0 = fmaf(xa.x, wa.x, a0); a1 = fmaf(xa.y, wa.y, a1); a2 = fmaf(xa.z, wa.z, a2); a3 = fmaf(xa.w, wa.w, a3);
+    b0 = fmaf(xb.x, wb.x, b0); b1 = fmaf(xb.y, wb.y, b1); b2 = fmaf(xb.z, wb.z, b2); b3 = fmaf(xb.w, wb.w, b3);
   }
-  return (a0 + a1) + (a2 + a3);
+  va = (a0 + a1) + (a2 + a3);
+  vb = (b0 + b1) + (b2 + b3);
 }
-__device__ __forceinline__ float band_dot_n(const float4* __restrict__ pp, const float4* __restrict__ wp, int ng) {
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
+template <bool kSmemW>
+__device__ __forceinline__ void band_dot2_n(const float4* __restrict__ pa, const float4* __restrict__ pb,
+                                            const float4* __restrict__ wp, int ng, float& va, float& vb) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+#pragma unroll 2
   for (int g = 0; g < ng; ++g) {
-    const float4 w4 = wp[g];
-    const float4 p4 = pp[g];
-    a0 = fmaf(p4.x, w4.x, a0);
-    a1 = fmaf(p4.y, w4.y, a1);
-    a2 = fmaf(p4.z, w4.z, a2);
-    a3 = fmaf(p4.w, w4.w, a3);
+    const float4 wa = ldw<kSmemW>(wp + 2 * g), wb = ldw<kSmemW>(wp + 2 * g + 1);
+    const float4 xa = pa[g], xb = pb[g];
+    a0 = fmaf(xa.x, wa.x, a0); a1 = fmaf(xa.y, wa.y, a1); a2 = fmaf(xa.z, wa.z, a2); a3 = fmaf(xa.w, wa.w, a3);
+    b0 = fmaf(xb.x, wb.x, b0); b1 = fmaf(xb.y, wb.y, b1); b2 = fmaf(xb.z, wb.z, b2); b3 = fmaf(xb.w, wb.w, b3);
   }
-  return (a0 + a1) + (a2 + a3);
+  va = (a0 + a1) + (a2 + a3);
+  vb = (b0 + b1) + (b2 + b3);
+}
+
+// One chunk (<= kMChunk output columns) of the mel projection for the 32 frames of the tile:
+// warp w takes pairs w, w + kWarps, ...; results go to the staging buffer [frame][column].
+template <bool kSmemW>
+__device__ __forceinline__ void mel_chunk(const float4* __restrict__ prow, const int4* __restrict__ pd, int npairs,
+                                          const float* __restrict__ wbase, float* __restrict__ orow, int warp,
+                                          bool log_scale) {
+  for (int q = warp; q < npairs; q += kWarps) {
+    const int4 d = pd[q];                                  // PairDesc, warp-uniform
+    const float4* wp = reinterpret_cast<const float4*>(wbase + d.y);
+    const float4* pa = prow + (d.x & 0xFFFF);
+    const float4* pb = prow + (static_cast<unsigned>(d.x) >> 16);
+    float va, vb;
+    if constexpr (!kSmemW) {   // rare path (huge / dense filterbanks): keep the code small
+      band_dot2_n<kSmemW>(pa, pb, wp, d.z, va, vb);
+    } else
+    switch (d.z) {
+      case 0: va = 0.f; vb = 0.f; break;
+      case 1: band_dot2<1, kSmemW>(pa, pb, wp, va, vb); break;
+      case 2: band_dot2<2, kSmemW>(pa, pb, wp, va, vb); break;
+      case 3: band_dot2<3, kSmemW>(pa, pb, wp, va, vb); break;
+      case 4: band_dot2<4, kSmemW>(pa, pb, wp, va, vb); break;
+      case 5: band_dot2<5, kSmemW>(pa, pb, wp, va, vb); break;
+      case 6: band_dot2<6, kSmemW>(pa, pb, wp, va, vb); break;
+      case 7: band_dot2<7, kSmemW>(pa, pb, wp, va, vb); break;
+      case 8: band_dot2<8, kSmemW>(pa, pb, wp, va, vb); break;
+      case 9: band_dot2<9, kSmemW>(pa, pb, wp, va, vb); break;
+      case 10: band_dot2<10, kSmemW>(pa, pb, wp, va, vb); break;
+      default: band_dot2_n<kSmemW>(pa, pb, wp, d.z, va, vb); break;
+    }
+    if (log_scale) {
+      va = __logf(1.0f + va);
+      vb = __logf(1.0f + vb);
+    }
+    const int ca = d.w & 0xFFFF, cb = static_cast<unsigned>(d.w) >> 16;
+    orow[ca] = va;
+    if (cb != 0xFFFF) orow[cb] = vb;
+  }
 }
 
 // ---------------------------------------------------------------- the kernel
@@ -206,13 +260,9 @@ __global__ void __launch_bounds__(kThreads, 1) bhmel_logmel_kernel(const __grid_
     twi[m] = t.y;
   }
   const bool fw_in_smem = p.n_weights <= kFwCap;
-  const bool bands_in_smem = p.n_mels <= kBandCap;
   if (fw_in_smem)
     for (int i = tid; i < p.n_weights; i += kThreads) S.fw[i] = p.weights[i];
-  if (bands_in_smem)
-    for (int i = tid; i < p.n_mels; i += kThreads) S.bands[i] = reinterpret_cast<const int4*>(p.bands)[i];
-  const float* wbase = fw_in_smem ? S.fw : p.weights;
-  const int4* bbase = bands_in_smem ? S.bands : reinterpret_cast<const int4*>(p.bands);
+  for (int i = tid; i < p.n_pairs; i += kThreads) S.pairs[i] = reinterpret_cast<const int4*>(p.pairs)[i];
   for (int i = tid; i < kTileF * (kPPitch - kBins); i += kThreads)
     S.P[(i / (kPPitch - kBins)) * kPPitch + kBins + i % (kPPitch - kBins)] = 0.f;
   if (tid == 0) {
@@ -231,9 +281,9 @@ __global__ void __launch_bounds__(kThreads, 1) bhmel_logmel_kernel(const __grid_
   for (; tile < p.n_tiles; tile += gridDim.x, buf ^= 1) {
     // ---- wait for this tile's span ------------------------------------------------------
     cp_async_wait_all();
-    if (cur_bulk) {
-      if (buf == 0) { mbar_wait(&S.mbar[0], parity0); parity0 ^= 1; }
-      else          { mbar_wait(&S.mbar[1], parity1); parity1 ^= 1; }
+    if (cur_bulk) {   // warp 0 observes the TMA completion; the barrier below publishes it to the CTA
+      if (buf == 0) { if (warp == 0) mbar_wait(&S.mbar[0], parity0); parity0 ^= 1; }
+      else          { if (warp == 0) mbar_wait(&S.mbar[1], parity1); parity1 ^= 1; }
     }
     __syncthreads();   // span[buf] visible to all; every thread is done with the previous tile
 
@@ -307,36 +357,18 @@ __global__ void __launch_bounds__(kThreads, 1) bhmel_logmel_kernel(const __grid_
     const int nf = frames_left < kTileF ? static_cast<int>(frames_left) : kTileF;
     float* ybase = p.y + (r * p.T + t0) * static_cast<long long>(p.n_mels);
     const float4* prow = reinterpret_cast<const float4*>(S.P + lane * kPPitch);
-    for (int mc = 0; mc < p.n_mels; mc += kMChunk) {
+    for (int mc = 0, c = 0; mc < p.n_mels; mc += kMChunk, ++c) {
       const int mcount = (p.n_mels - mc) < kMChunk ? (p.n_mels - mc) : kMChunk;
       if (mc > 0) __syncthreads();   // previous chunk's staging fully stored
-      for (int m = warp; m < mcount; m += kWarps) {
-        const int4 bd = bbase[mc + m];                       // {g0, ng, woff, -}: warp-uniform
-        const float4* wp = reinterpret_cast<const float4*>(wbase + bd.z);
-        const float4* pp = prow + bd.x;
-        float v;
-        switch (bd.y) {
-          case 0: v = 0.f; break;
-          case 1: v = band_dot<1>(pp, wp); break;
-          case 2: v = band_dot<2>(pp, wp); break;
-          case 3: v = band_dot<3>(pp, wp); break;
-          case 4: v = band_dot<4>(pp, wp); break;
-          case 5: v = band_dot<5>(pp, wp); break;
-          case 6: v = band_dot<6>(pp, wp); break;
-          case 7: v = band_dot<7>(pp, wp); break;
-          case 8: v = band_dot<8>(pp, wp); break;
-          case 9: v = band_dot<9>(pp, wp); break;
-          case 10: v = band_dot<10>(pp, wp); break;
-          default: v = band_dot_n(pp, wp, bd.y); break;
-        }
-        if (p.log_scale) v = __logf(1.0f + v);
-        S.out[lane * kOutPitch + m] = v;
-      }
+      const int4* pd = S.pairs + c * (kMChunk / 2);
+      float* orow = S.out + lane * kOutPitch;
+      if (fw_in_smem) mel_chunk<true>(prow, pd, (mcount + 1) >> 1, S.fw, orow, warp, p.log_scale != 0);
+      else mel_chunk<false>(prow, pd, (mcount + 1) >> 1, p.weights, orow, warp, p.log_scale != 0);
       __syncthreads();
       for (int f = warp; f < nf; f += kWarps) {
         float* yrow = ybase + static_cast<long long>(f) * p.n_mels + mc;
-        const float* orow = S.out + f * kOutPitch;
-        for (int c = lane; c < mcount; c += 32) yrow[c] = orow[c];
+        const float* orow_f = S.out + f * kOutPitch;
+        for (int c2 = lane; c2 < mcount; c2 += 32) yrow[c2] = orow_f[c2];
       }
     }
     cur_bulk = next_bulk;

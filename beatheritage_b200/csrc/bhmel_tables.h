@@ -10,6 +10,7 @@
 //              kernel can use 128-bit shared-memory loads
 #pragma once
 #include <cmath>
+#include <utility>
 #include <cstdint>
 #include <vector>
 
@@ -98,6 +99,73 @@ inline BandTables make_bands(const float* fb, int n_mels) {
     t.bands[m] = b;
   }
   if (t.weights.empty()) t.weights.assign(4, 0.f);
+  return t;
+}
+
+// ---- paired band tables ------------------------------------------------------------------
+// The kernel's mel stage handles two filters per step (two independent FMA chains per lane).
+// Filters are taken chunk by chunk (kMelChunk output columns at a time, the size of the epilogue
+// staging buffer), sorted by band length inside the chunk and paired with their neighbour; both
+// members of a pair are padded with zero weights to the longer band, so one statically unrolled
+// loop serves both.  Weights of a pair are interleaved group by group: A0 B0 A1 B1 ...
+constexpr int kMelChunk = 96;
+
+struct PairDesc {
+  int32_t g0;      // first 4-bin group of A (low 16 bits) and of B (high 16 bits)
+  int32_t woff;    // offset (floats) of the pair's interleaved weights
+  int32_t ng;      // groups per member (after padding to the longer one)
+  int32_t mcol;    // output column inside the chunk: A (low 16 bits), B (high 16 bits; 0xFFFF = none)
+};
+
+struct PairTables {
+  std::vector<PairDesc> pairs;        // all chunks, concatenated
+  std::vector<int32_t> chunk_start;   // [n_chunks + 1] index into pairs
+  std::vector<float> weights;
+  int max_groups = 0;
+};
+
+inline PairTables make_pairs(const float* fb, int n_mels) {
+  const BandTables bt = make_bands(fb, n_mels);
+  constexpr int kGroups = (kBins + 3) / 4;   // 129 groups cover bins 0..515
+  PairTables t;
+  t.chunk_start.push_back(0);
+  for (int mc = 0; mc < n_mels; mc += kMelChunk) {
+    const int cnt = (n_mels - mc) < kMelChunk ? (n_mels - mc) : kMelChunk;
+    std::vector<int> order(cnt);
+    for (int i = 0; i < cnt; ++i) order[i] = mc + i;
+    // longest bands first (stable -> deterministic)
+    for (int i = 1; i < cnt; ++i)
+      for (int j = i; j > 0 && bt.bands[order[j]].ng > bt.bands[order[j - 1]].ng; --j) std::swap(order[j], order[j - 1]);
+    for (int i = 0; i < cnt; i += 2) {
+      const int ma = order[i], mb = (i + 1 < cnt) ? order[i + 1] : -1;
+      const FilterBand a = bt.bands[ma];
+      const FilterBand b = mb >= 0 ? bt.bands[mb] : FilterBand{0, 0, 0, 0};
+      const int ng = a.ng > b.ng ? a.ng : b.ng;
+      auto place = [&](const FilterBand& f) { return (f.g0 + ng > kGroups) ? kGroups - ng : f.g0; };
+      const int ga = place(a), gb = place(b);
+      PairDesc d;
+      d.g0 = ga | (gb << 16);
+      d.woff = static_cast<int32_t>(t.weights.size());
+      d.ng = ng;
+      d.mcol = (ma - mc) | ((mb >= 0 ? (mb - mc) : 0xFFFF) << 16);
+      for (int g = 0; g < ng; ++g) {
+        for (int which = 0; which < 2; ++which) {
+          const FilterBand& f = which == 0 ? a : b;
+          const int gbase = which == 0 ? ga : gb;
+          const int grp = gbase + g;                 // absolute group index of this slot
+          for (int e = 0; e < 4; ++e) {
+            float w = 0.f;
+            if (grp >= f.g0 && grp < f.g0 + f.ng) w = bt.weights[f.woff + (grp - f.g0) * 4 + e];
+            t.weights.push_back(w);
+          }
+        }
+      }
+      if (ng > t.max_groups) t.max_groups = ng;
+      t.pairs.push_back(d);
+    }
+    t.chunk_start.push_back(static_cast<int32_t>(t.pairs.size()));
+  }
+  if (t.weights.empty()) t.weights.assign(8, 0.f);
   return t;
 }
 

@@ -28,7 +28,7 @@ extern "C" int bhmel_emu_forward(const float* x, long long B, long long N, long 
   std::vector<float> win_half(kNfft);
   for (int i = 0; i < kNfft; ++i) win_half[i] = 0.5f * win[i];
   std::vector<float> tw = make_twiddles();
-  BandTables bt = make_bands(fb.data(), n_mels);
+  PairTables pt = make_pairs(fb.data(), n_mels);
 
   const long long T = N / kHop + 1;
   const int tiles_per_row = (int)((T + kTileF - 1) / kTileF);
@@ -100,20 +100,27 @@ extern "C" int bhmel_emu_forward(const float* x, long long B, long long N, long 
       for (int f = 0; f < nf; ++f) {
         const float* prow = P.data() + (size_t)f * kPPitch;
         float* yrow = y + ((r * T + t0 + f) * (long long)n_mels);
-        for (int m = 0; m < n_mels; ++m) {
-          const FilterBand b = bt.bands[m];
-          float acc0 = 0.f, acc1 = 0.f;
-          for (int g = 0; g < b.ng; ++g) {
-            const float* w4 = bt.weights.data() + b.woff + 4 * g;
-            const float* p4 = prow + 4 * (b.g0 + g);
-            acc0 = fmaf(p4[0], w4[0], acc0);
-            acc1 = fmaf(p4[1], w4[1], acc1);
-            acc0 = fmaf(p4[2], w4[2], acc0);
-            acc1 = fmaf(p4[3], w4[3], acc1);
+        for (int mc = 0, c = 0; mc < n_mels; mc += kMelChunk, ++c) {
+          for (int q = pt.chunk_start[c]; q < pt.chunk_start[c + 1]; ++q) {
+            const PairDesc d = pt.pairs[q];
+            const float* pa = prow + 4 * (d.g0 & 0xFFFF);
+            const float* pb = prow + 4 * ((unsigned)d.g0 >> 16);
+            const float* w = pt.weights.data() + d.woff;
+            float a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+            for (int g = 0; g < d.ng; ++g)
+              for (int e = 0; e < 4; ++e) {
+                a[e] = fmaf(pa[4 * g + e], w[8 * g + e], a[e]);
+                b[e] = fmaf(pb[4 * g + e], w[8 * g + 4 + e], b[e]);
+              }
+            float va = (a[0] + a[1]) + (a[2] + a[3]), vb = (b[0] + b[1]) + (b[2] + b[3]);
+            if (log_scale) {
+              va = exact_log1p ? log1pf(va) : logf(1.0f + va);
+              vb = exact_log1p ? log1pf(vb) : logf(1.0f + vb);
+            }
+            const int ca = d.mcol & 0xFFFF, cb = (unsigned)d.mcol >> 16;
+            yrow[mc + ca] = va;
+            if (cb != 0xFFFF) yrow[mc + cb] = vb;
           }
-          float v = acc0 + acc1;
-          if (log_scale) v = exact_log1p ? log1pf(v) : logf(1.0f + v);
-          yrow[m] = v;
         }
       }
     }
