@@ -132,8 +132,12 @@ int launch(bhmel_handle* h, const float* x, long long row_stride, long long row0
   p.n_pairs = h->n_pairs;
 
   const long long grid = p.n_tiles < h->num_sms ? p.n_tiles : h->num_sms;
-  bhmel::bhmel_logmel_kernel<<<static_cast<unsigned>(grid), bhmel::kThreads, sizeof(bhmel::SmemLayout),
-                               stream>>>(p);
+  if (p.log_scale)
+    bhmel::bhmel_logmel_kernel<true><<<static_cast<unsigned>(grid), bhmel::kThreads, sizeof(bhmel::SmemLayout),
+                                       stream>>>(p);
+  else
+    bhmel::bhmel_logmel_kernel<false><<<static_cast<unsigned>(grid), bhmel::kThreads, sizeof(bhmel::SmemLayout),
+                                        stream>>>(p);
   BH_CUDA(cudaGetLastError());
   h->launches.fetch_add(1, std::memory_order_relaxed);
   return BHMEL_OK;
@@ -174,7 +178,9 @@ int bhmel_create(const bhmel_params* prm, bhmel_handle** out) {
   if (prop.major != 10)
     return fail(BHMEL_EDEVICE, std::string("libbhmel is built for sm_100a only; device is ") + prop.name +
                                    " (sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + ")");
-  BH_CUDA(cudaFuncSetAttribute(bhmel::bhmel_logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  BH_CUDA(cudaFuncSetAttribute(bhmel::bhmel_logmel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(sizeof(bhmel::SmemLayout))));
+  BH_CUDA(cudaFuncSetAttribute(bhmel::bhmel_logmel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(sizeof(bhmel::SmemLayout))));
 
   bhmel_handle* h = new bhmel_handle();

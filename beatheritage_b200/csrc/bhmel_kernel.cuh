@@ -203,12 +203,14 @@ __device__ __forceinline__ void band_dot2_n(const float4* __restrict__ pa, const
 
 // One chunk (<= kMChunk output columns) of the mel projection for the 32 frames of the tile:
 // warp w takes pairs w, w + kWarps, ...; results go to the staging buffer [frame][column].
-template <bool kSmemW>
+template <bool kSmemW, bool kLog>
 __device__ __forceinline__ void mel_chunk(const float4* __restrict__ prow, const int4* __restrict__ pd, int npairs,
-                                          const float* __restrict__ wbase, float* __restrict__ orow, int warp,
-                                          bool log_scale) {
+                                          const float* __restrict__ wbase, float* __restrict__ orow, int warp) {
+  int4 dnext = pd[warp < npairs ? warp : 0];              // PairDesc, warp-uniform; prefetched one step ahead
+#pragma unroll 1
   for (int q = warp; q < npairs; q += kWarps) {
-    const int4 d = pd[q];                                  // PairDesc, warp-uniform
+    const int4 d = dnext;
+    if (q + kWarps < npairs) dnext = pd[q + kWarps];
     const float4* wp = reinterpret_cast<const float4*>(wbase + d.y);
     const float4* pa = prow + (d.x & 0xFFFF);
     const float4* pb = prow + (static_cast<unsigned>(d.x) >> 16);
@@ -230,7 +232,7 @@ __device__ __forceinline__ void mel_chunk(const float4* __restrict__ prow, const
       case 10: band_dot2<10, kSmemW>(pa, pb, wp, va, vb); break;
       default: band_dot2_n<kSmemW>(pa, pb, wp, d.z, va, vb); break;
     }
-    if (log_scale) {
+    if constexpr (kLog) {
       va = __logf(1.0f + va);
       vb = __logf(1.0f + vb);
     }
@@ -241,6 +243,7 @@ __device__ __forceinline__ void mel_chunk(const float4* __restrict__ prow, const
 }
 
 // ---------------------------------------------------------------- the kernel
+template <bool kLog>
 __global__ void __launch_bounds__(kThreads, 1) bhmel_logmel_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemLayout& S = *reinterpret_cast<SmemLayout*>(smem_raw);
@@ -362,13 +365,27 @@ __global__ void __launch_bounds__(kThreads, 1) bhmel_logmel_kernel(const __grid_
       if (mc > 0) __syncthreads();   // previous chunk's staging fully stored
       const int4* pd = S.pairs + c * (kMChunk / 2);
       float* orow = S.out + lane * kOutPitch;
-      if (fw_in_smem) mel_chunk<true>(prow, pd, (mcount + 1) >> 1, S.fw, orow, warp, p.log_scale != 0);
-      else mel_chunk<false>(prow, pd, (mcount + 1) >> 1, p.weights, orow, warp, p.log_scale != 0);
+      if (fw_in_smem) mel_chunk<true, kLog>(prow, pd, (mcount + 1) >> 1, S.fw, orow, warp);
+      else mel_chunk<false, kLog>(prow, pd, (mcount + 1) >> 1, p.weights, orow, warp);
       __syncthreads();
-      for (int f = warp; f < nf; f += kWarps) {
-        float* yrow = ybase + static_cast<long long>(f) * p.n_mels + mc;
-        const float* orow_f = S.out + f * kOutPitch;
-        for (int c2 = lane; c2 < mcount; c2 += 32) yrow[c2] = orow_f[c2];
+      // coalesced store of the staged [frames][columns] block: all loads first, then all stores
+      {
+        constexpr int kFr = kTileF / kWarps, kCo = kMChunk / 32;   // 4 frames x 3 column steps per thread
+        float vals[kFr][kCo];
+#pragma unroll
+        for (int a = 0; a < kFr; ++a)
+#pragma unroll
+          for (int b = 0; b < kCo; ++b) vals[a][b] = S.out[(warp + a * kWarps) * kOutPitch + lane + 32 * b];
+#pragma unroll
+        for (int a = 0; a < kFr; ++a) {
+          const int f = warp + a * kWarps;
+          float* yrow = ybase + static_cast<long long>(f) * p.n_mels + mc;
+#pragma unroll
+          for (int b = 0; b < kCo; ++b) {
+            const int c2 = lane + 32 * b;
+            if (f < nf && c2 < mcount) yrow[c2] = vals[a][b];
+          }
+        }
       }
     }
     cur_bulk = next_bulk;
