@@ -13,6 +13,8 @@ LIB_PATH = os.path.join(_PKG, "libbhmel.so")
 
 PAD_CONSTANT, PAD_REFLECT = 0, 1
 OPT_BULK_COPY = 1
+OPT_KERNEL = 2
+KERNEL_BARRIER, KERNEL_WARP_SPECIALIZED = 0, 1
 OK, EINVAL, ECUDA, ESHAPE, EDEVICE = 0, 1, 2, 3, 4
 
 

@@ -12,7 +12,7 @@
 #include <string>
 #include <vector>
 
-#include "bhmel_kernel.cuh"
+#include "bhmel_kernel_ws.cuh"
 
 namespace {
 
@@ -48,6 +48,7 @@ struct bhmel_handle {
   int n_pairs = 0;
   std::atomic<int64_t> launches{0};
   int use_bulk = 1;
+  int kernel_variant = BHMEL_KERNEL_WARP_SPECIALIZED;
   // bhmel_forward_host pipeline (lazily created)
   std::mutex host_mu;
   cudaStream_t hs[kHostSlots] = {nullptr, nullptr, nullptr};
@@ -116,7 +117,9 @@ int launch(bhmel_handle* h, const float* x, long long row_stride, long long row0
   p.n_total = n_total;
   p.N = N;
   p.T = N / bhmel::kHop + 1;
-  p.tiles_per_row = static_cast<int>((p.T + bhmel::kTileF - 1) / bhmel::kTileF);
+  const bool ws = h->kernel_variant == BHMEL_KERNEL_WARP_SPECIALIZED;
+  const int tile_frames = ws ? bhmel::ws::kTile : bhmel::kTileF;
+  p.tiles_per_row = static_cast<int>((p.T + tile_frames - 1) / tile_frames);
   p.n_tiles = static_cast<long long>(p.tiles_per_row) * B;
   p.y = y;
   p.win_half = h->d_win;
@@ -131,13 +134,18 @@ int launch(bhmel_handle* h, const float* x, long long row_stride, long long row0
   p.n_weights = h->n_weights;
   p.n_pairs = h->n_pairs;
 
-  const long long grid = p.n_tiles < h->num_sms ? p.n_tiles : h->num_sms;
-  if (p.log_scale)
-    bhmel::bhmel_logmel_kernel<true><<<static_cast<unsigned>(grid), bhmel::kThreads, sizeof(bhmel::SmemLayout),
-                                       stream>>>(p);
-  else
-    bhmel::bhmel_logmel_kernel<false><<<static_cast<unsigned>(grid), bhmel::kThreads, sizeof(bhmel::SmemLayout),
-                                        stream>>>(p);
+  const unsigned grid = static_cast<unsigned>(p.n_tiles < h->num_sms ? p.n_tiles : h->num_sms);
+  if (ws) {
+    if (p.log_scale)
+      bhmel::ws::bhmel_logmel_ws_kernel<true><<<grid, bhmel::ws::kThreadsW, sizeof(bhmel::ws::SmemWS), stream>>>(p);
+    else
+      bhmel::ws::bhmel_logmel_ws_kernel<false><<<grid, bhmel::ws::kThreadsW, sizeof(bhmel::ws::SmemWS), stream>>>(p);
+  } else {
+    if (p.log_scale)
+      bhmel::bhmel_logmel_kernel<true><<<grid, bhmel::kThreads, sizeof(bhmel::SmemLayout), stream>>>(p);
+    else
+      bhmel::bhmel_logmel_kernel<false><<<grid, bhmel::kThreads, sizeof(bhmel::SmemLayout), stream>>>(p);
+  }
   BH_CUDA(cudaGetLastError());
   h->launches.fetch_add(1, std::memory_order_relaxed);
   return BHMEL_OK;
@@ -152,9 +160,9 @@ int bhmel_version(void) { return BHMEL_VERSION; }
 const char* bhmel_last_error(void) { return g_err.c_str(); }
 
 void bhmel_kernel_info(int32_t* smem_bytes, int32_t* threads, int32_t* tile_frames) {
-  if (smem_bytes) *smem_bytes = static_cast<int32_t>(sizeof(bhmel::SmemLayout));
-  if (threads) *threads = bhmel::kThreads;
-  if (tile_frames) *tile_frames = bhmel::kTileF;
+  if (smem_bytes) *smem_bytes = static_cast<int32_t>(sizeof(bhmel::ws::SmemWS));
+  if (threads) *threads = bhmel::ws::kThreadsW;
+  if (tile_frames) *tile_frames = bhmel::ws::kTile;
 }
 
 int bhmel_create(const bhmel_params* prm, bhmel_handle** out) {
@@ -182,6 +190,10 @@ int bhmel_create(const bhmel_params* prm, bhmel_handle** out) {
                                static_cast<int>(sizeof(bhmel::SmemLayout))));
   BH_CUDA(cudaFuncSetAttribute(bhmel::bhmel_logmel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(sizeof(bhmel::SmemLayout))));
+  BH_CUDA(cudaFuncSetAttribute(bhmel::ws::bhmel_logmel_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(sizeof(bhmel::ws::SmemWS))));
+  BH_CUDA(cudaFuncSetAttribute(bhmel::ws::bhmel_logmel_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(sizeof(bhmel::ws::SmemWS))));
 
   bhmel_handle* h = new bhmel_handle();
   h->device = dev;
@@ -266,6 +278,11 @@ int bhmel_set_option(bhmel_handle* h, int32_t option, int64_t value) {
   switch (option) {
     case BHMEL_OPT_BULK_COPY:
       h->use_bulk = value != 0;
+      return BHMEL_OK;
+    case BHMEL_OPT_KERNEL:
+      if (value != BHMEL_KERNEL_BARRIER && value != BHMEL_KERNEL_WARP_SPECIALIZED)
+        return fail(BHMEL_EINVAL, "unknown kernel variant");
+      h->kernel_variant = static_cast<int>(value);
       return BHMEL_OK;
     default:
       return fail(BHMEL_EINVAL, "unknown option " + std::to_string(option));

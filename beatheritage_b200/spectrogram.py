@@ -145,6 +145,7 @@ class MelSpectrogram(nn.Module):
         self._handles: dict[int, int] = {}        # device index -> bhmel_handle*
         self._stamp: dict[int, tuple] = {}        # device index -> buffer versions the handle was built from
         self._bulk = True
+        self._variant = _lib.KERNEL_WARP_SPECIALIZED
         self._register()
 
     def _register(self) -> None:
@@ -194,6 +195,7 @@ class MelSpectrogram(nn.Module):
                     self._handles[idx] = h
                     if not self._bulk:
                         _lib.check(lib.bhmel_set_option(h, _lib.OPT_BULK_COPY, 0))
+                    _lib.check(lib.bhmel_set_option(h, _lib.OPT_KERNEL, self._variant))
                 else:   # buffers were reloaded / edited: refresh the device tables
                     _lib.check(lib.bhmel_set_fb(h, ctypes.cast(fb.data_ptr(), fp)))
                     _lib.check(lib.bhmel_set_window(h, ctypes.cast(win.data_ptr(), fp)))
@@ -218,6 +220,13 @@ class MelSpectrogram(nn.Module):
         self._bulk = bool(enabled)
         for h in self._handles.values():
             _lib.check(_lib.lib().bhmel_set_option(h, _lib.OPT_BULK_COPY, int(enabled)))
+
+    def set_kernel_variant(self, variant: str) -> None:
+        """'ws' (default, warp-specialised schedule) or 'barrier' (stage-by-stage schedule); the two
+        produce bit-identical results."""
+        self._variant = {"ws": _lib.KERNEL_WARP_SPECIALIZED, "barrier": _lib.KERNEL_BARRIER}[variant]
+        for h in self._handles.values():
+            _lib.check(_lib.lib().bhmel_set_option(h, _lib.OPT_KERNEL, self._variant))
 
     # -- forward -----------------------------------------------------------------------
     def _check_input(self, samples: torch.Tensor) -> torch.Tensor:
