@@ -12,7 +12,7 @@
 #include <string>
 #include <vector>
 
-#include "bhmel_kernel_ws.cuh"
+#include "bhmel_kernel_iw.cuh"
 
 namespace {
 
@@ -46,9 +46,14 @@ struct bhmel_handle {
   float* d_weights = nullptr;
   int n_weights = 0;
   int n_pairs = 0;
+  bhmel::RoundDesc* d_rounds = nullptr;   // independent-warp kernel tables
+  int* d_g0 = nullptr;
+  float* d_wt = nullptr;
+  int n_rounds = 0;
+  int n_wt4 = 0;
   std::atomic<int64_t> launches{0};
   int use_bulk = 1;
-  int kernel_variant = BHMEL_KERNEL_WARP_SPECIALIZED;
+  int kernel_variant = BHMEL_KERNEL_INDEPENDENT_WARPS;
   // bhmel_forward_host pipeline (lazily created)
   std::mutex host_mu;
   cudaStream_t hs[kHostSlots] = {nullptr, nullptr, nullptr};
@@ -77,6 +82,25 @@ int upload_filterbank(bhmel_handle* h) {
                      cudaMemcpyHostToDevice));
   h->n_weights = static_cast<int>(t.weights.size());
   h->n_pairs = static_cast<int>(t.pairs.size());
+
+  bhmel::RoundTables rt = bhmel::make_rounds(h->fb.data(), h->prm.n_mels);
+  if (rt.rounds.size() > static_cast<size_t>(bhmel::iw::kRoundCap))
+    return fail(BHMEL_EINVAL, "too many filter rounds for the kernel's descriptor table");
+  if (h->d_rounds) cudaFree(h->d_rounds);
+  if (h->d_g0) cudaFree(h->d_g0);
+  if (h->d_wt) cudaFree(h->d_wt);
+  h->d_rounds = nullptr;
+  h->d_g0 = nullptr;
+  h->d_wt = nullptr;
+  BH_CUDA(cudaMalloc(&h->d_rounds, rt.rounds.size() * sizeof(bhmel::RoundDesc)));
+  BH_CUDA(cudaMalloc(&h->d_g0, rt.g0.size() * sizeof(int)));
+  BH_CUDA(cudaMalloc(&h->d_wt, rt.weights.size() * sizeof(float)));
+  BH_CUDA(cudaMemcpy(h->d_rounds, rt.rounds.data(), rt.rounds.size() * sizeof(bhmel::RoundDesc),
+                     cudaMemcpyHostToDevice));
+  BH_CUDA(cudaMemcpy(h->d_g0, rt.g0.data(), rt.g0.size() * sizeof(int), cudaMemcpyHostToDevice));
+  BH_CUDA(cudaMemcpy(h->d_wt, rt.weights.data(), rt.weights.size() * sizeof(float), cudaMemcpyHostToDevice));
+  h->n_rounds = static_cast<int>(rt.rounds.size());
+  h->n_wt4 = static_cast<int>(rt.weights.size() / 4);
   return BHMEL_OK;
 }
 
@@ -117,8 +141,8 @@ int launch(bhmel_handle* h, const float* x, long long row_stride, long long row0
   p.n_total = n_total;
   p.N = N;
   p.T = N / bhmel::kHop + 1;
-  const bool ws = h->kernel_variant == BHMEL_KERNEL_WARP_SPECIALIZED;
-  const int tile_frames = ws ? bhmel::ws::kTile : bhmel::kTileF;
+  const bool iw = h->kernel_variant == BHMEL_KERNEL_INDEPENDENT_WARPS;
+  const int tile_frames = iw ? bhmel::iw::kWTileF : bhmel::kTileF;
   p.tiles_per_row = static_cast<int>((p.T + tile_frames - 1) / tile_frames);
   p.n_tiles = static_cast<long long>(p.tiles_per_row) * B;
   p.y = y;
@@ -134,13 +158,22 @@ int launch(bhmel_handle* h, const float* x, long long row_stride, long long row0
   p.n_weights = h->n_weights;
   p.n_pairs = h->n_pairs;
 
-  const unsigned grid = static_cast<unsigned>(p.n_tiles < h->num_sms ? p.n_tiles : h->num_sms);
-  if (ws) {
+  if (iw) {
+    bhmel::iw::IwParams q{};
+    q.k = p;
+    q.rounds = h->d_rounds;
+    q.g0 = h->d_g0;
+    q.wt = reinterpret_cast<const float4*>(h->d_wt);
+    q.n_rounds = h->n_rounds;
+    q.n_wt4 = h->n_wt4;
+    const long long ctas = (p.n_tiles + bhmel::iw::kIwWarps - 1) / bhmel::iw::kIwWarps;
+    const unsigned grid = static_cast<unsigned>(ctas < h->num_sms ? ctas : h->num_sms);
     if (p.log_scale)
-      bhmel::ws::bhmel_logmel_ws_kernel<true><<<grid, bhmel::ws::kThreadsW, sizeof(bhmel::ws::SmemWS), stream>>>(p);
+      bhmel::iw::bhmel_logmel_iw_kernel<true><<<grid, bhmel::iw::kIwThreads, sizeof(bhmel::iw::SmemIW), stream>>>(q);
     else
-      bhmel::ws::bhmel_logmel_ws_kernel<false><<<grid, bhmel::ws::kThreadsW, sizeof(bhmel::ws::SmemWS), stream>>>(p);
+      bhmel::iw::bhmel_logmel_iw_kernel<false><<<grid, bhmel::iw::kIwThreads, sizeof(bhmel::iw::SmemIW), stream>>>(q);
   } else {
+    const unsigned grid = static_cast<unsigned>(p.n_tiles < h->num_sms ? p.n_tiles : h->num_sms);
     if (p.log_scale)
       bhmel::bhmel_logmel_kernel<true><<<grid, bhmel::kThreads, sizeof(bhmel::SmemLayout), stream>>>(p);
     else
@@ -160,9 +193,9 @@ int bhmel_version(void) { return BHMEL_VERSION; }
 const char* bhmel_last_error(void) { return g_err.c_str(); }
 
 void bhmel_kernel_info(int32_t* smem_bytes, int32_t* threads, int32_t* tile_frames) {
-  if (smem_bytes) *smem_bytes = static_cast<int32_t>(sizeof(bhmel::ws::SmemWS));
-  if (threads) *threads = bhmel::ws::kThreadsW;
-  if (tile_frames) *tile_frames = bhmel::ws::kTile;
+  if (smem_bytes) *smem_bytes = static_cast<int32_t>(sizeof(bhmel::iw::SmemIW));
+  if (threads) *threads = bhmel::iw::kIwThreads;
+  if (tile_frames) *tile_frames = bhmel::iw::kWTileF;
 }
 
 int bhmel_create(const bhmel_params* prm, bhmel_handle** out) {
@@ -190,10 +223,10 @@ int bhmel_create(const bhmel_params* prm, bhmel_handle** out) {
                                static_cast<int>(sizeof(bhmel::SmemLayout))));
   BH_CUDA(cudaFuncSetAttribute(bhmel::bhmel_logmel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(sizeof(bhmel::SmemLayout))));
-  BH_CUDA(cudaFuncSetAttribute(bhmel::ws::bhmel_logmel_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               static_cast<int>(sizeof(bhmel::ws::SmemWS))));
-  BH_CUDA(cudaFuncSetAttribute(bhmel::ws::bhmel_logmel_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               static_cast<int>(sizeof(bhmel::ws::SmemWS))));
+  BH_CUDA(cudaFuncSetAttribute(bhmel::iw::bhmel_logmel_iw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(sizeof(bhmel::iw::SmemIW))));
+  BH_CUDA(cudaFuncSetAttribute(bhmel::iw::bhmel_logmel_iw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(sizeof(bhmel::iw::SmemIW))));
 
   bhmel_handle* h = new bhmel_handle();
   h->device = dev;
@@ -238,6 +271,9 @@ void bhmel_destroy(bhmel_handle* h) {
   if (h->d_tw) cudaFree(h->d_tw);
   if (h->d_pairs) cudaFree(h->d_pairs);
   if (h->d_weights) cudaFree(h->d_weights);
+  if (h->d_rounds) cudaFree(h->d_rounds);
+  if (h->d_g0) cudaFree(h->d_g0);
+  if (h->d_wt) cudaFree(h->d_wt);
   if (prev >= 0) cudaSetDevice(prev);
   delete h;
 }
@@ -280,7 +316,7 @@ int bhmel_set_option(bhmel_handle* h, int32_t option, int64_t value) {
       h->use_bulk = value != 0;
       return BHMEL_OK;
     case BHMEL_OPT_KERNEL:
-      if (value != BHMEL_KERNEL_BARRIER && value != BHMEL_KERNEL_WARP_SPECIALIZED)
+      if (value != BHMEL_KERNEL_BARRIER && value != BHMEL_KERNEL_INDEPENDENT_WARPS)
         return fail(BHMEL_EINVAL, "unknown kernel variant");
       h->kernel_variant = static_cast<int>(value);
       return BHMEL_OK;

@@ -169,4 +169,77 @@ inline PairTables make_pairs(const float* fb, int n_mels) {
   return t;
 }
 
+// ---- round tables (independent-warp kernel) ------------------------------------------------
+// In the independent-warp kernel one warp projects its own frame PAIR: lanes 0-15 take frame A,
+// lanes 16-31 frame B, and lane i (mod 16) owns filter 16*r + i in round r.  All 16 filters of a
+// round are zero padded to the longest band of the round, so the dot-product loop is warp
+// uniform; weights are stored lane-interleaved ([round][group][lane 0..15] float4) so the 128-bit
+// weight loads are conflict free, and each filter's first group is shifted (inside the slack the
+// padding gives) so that the 8 lanes of a shared-memory phase hit different bank quads of P.
+struct RoundDesc {
+  int32_t woff4;   // offset of the round's weights in float4 units
+  int32_t ng;      // groups per filter in this round
+};
+
+struct RoundTables {
+  std::vector<RoundDesc> rounds;      // [ceil(n_mels / 16)]
+  std::vector<int32_t> g0;            // [rounds * 16] first 4-bin group per (round, lane)
+  std::vector<float> weights;         // float4-granular, [round][group][16 lanes][4]
+};
+
+inline RoundTables make_rounds(const float* fb, int n_mels) {
+  const BandTables bt = make_bands(fb, n_mels);
+  constexpr int kGroups = (kBins + 3) / 4;   // 129
+  RoundTables t;
+  const int n_rounds = (n_mels + 15) / 16;
+  t.g0.assign(static_cast<size_t>(n_rounds) * 16, 0);
+  for (int r = 0; r < n_rounds; ++r) {
+    int ng = 0;
+    for (int i = 0; i < 16; ++i) {
+      const int m = 16 * r + i;
+      if (m < n_mels && bt.bands[m].ng > ng) ng = bt.bands[m].ng;
+    }
+    RoundDesc rd{static_cast<int32_t>(t.weights.size() / 4), ng};
+    // choose the (shifted) first group of every filter; tightest intervals first
+    int lo[16], hi[16], order[16], chosen[16];
+    for (int i = 0; i < 16; ++i) {
+      const int m = 16 * r + i;
+      const FilterBand f = (m < n_mels) ? bt.bands[m] : FilterBand{0, 0, 0, 0};
+      lo[i] = f.g0 + f.ng - ng;
+      if (lo[i] < 0) lo[i] = 0;
+      hi[i] = f.g0;
+      if (hi[i] > kGroups - ng) hi[i] = kGroups - ng;
+      if (hi[i] < lo[i]) hi[i] = lo[i];
+      order[i] = i;
+    }
+    for (int a = 1; a < 16; ++a)
+      for (int b = a; b > 0 && (hi[order[b]] - lo[order[b]]) < (hi[order[b - 1]] - lo[order[b - 1]]); --b)
+        std::swap(order[b], order[b - 1]);
+    bool used[2][8] = {{false}};
+    for (int a = 0; a < 16; ++a) {
+      const int i = order[a], grp = i >> 3;
+      int pick = hi[i];
+      for (int c = hi[i]; c >= lo[i]; --c)
+        if (!used[grp][c & 7]) { pick = c; break; }
+      used[grp][pick & 7] = true;
+      chosen[i] = pick;
+      t.g0[static_cast<size_t>(r) * 16 + i] = pick;
+    }
+    for (int g = 0; g < ng; ++g)
+      for (int i = 0; i < 16; ++i) {
+        const int m = 16 * r + i;
+        const FilterBand f = (m < n_mels) ? bt.bands[m] : FilterBand{0, 0, 0, 0};
+        const int grp = chosen[i] + g;
+        for (int e = 0; e < 4; ++e) {
+          float w = 0.f;
+          if (grp >= f.g0 && grp < f.g0 + f.ng) w = bt.weights[f.woff + (grp - f.g0) * 4 + e];
+          t.weights.push_back(w);
+        }
+      }
+    t.rounds.push_back(rd);
+  }
+  if (t.weights.empty()) t.weights.assign(64, 0.f);
+  return t;
+}
+
 }  // namespace bhmel

@@ -145,7 +145,7 @@ class MelSpectrogram(nn.Module):
         self._handles: dict[int, int] = {}        # device index -> bhmel_handle*
         self._stamp: dict[int, tuple] = {}        # device index -> buffer versions the handle was built from
         self._bulk = True
-        self._variant = _lib.KERNEL_WARP_SPECIALIZED
+        self._variant = _lib.KERNEL_INDEPENDENT_WARPS
         self._register()
 
     def _register(self) -> None:
@@ -222,9 +222,9 @@ class MelSpectrogram(nn.Module):
             _lib.check(_lib.lib().bhmel_set_option(h, _lib.OPT_BULK_COPY, int(enabled)))
 
     def set_kernel_variant(self, variant: str) -> None:
-        """'ws' (default, warp-specialised schedule) or 'barrier' (stage-by-stage schedule); the two
-        produce bit-identical results."""
-        self._variant = {"ws": _lib.KERNEL_WARP_SPECIALIZED, "barrier": _lib.KERNEL_BARRIER}[variant]
+        """'warp' (default: independent per-warp pipelines) or 'barrier' (stage-by-stage CTA
+        schedule); the two produce bit-identical results."""
+        self._variant = {"warp": _lib.KERNEL_INDEPENDENT_WARPS, "barrier": _lib.KERNEL_BARRIER}[variant]
         for h in self._handles.values():
             _lib.check(_lib.lib().bhmel_set_option(h, _lib.OPT_KERNEL, self._variant))
 

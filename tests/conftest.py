@@ -101,7 +101,7 @@ def emu_lib():
     lib.bhmel_emu_forward.restype = ctypes.c_int
 
     def run(x, n_mels, fb=None, window=None, f_min=20.0, f_max=8000.0, reflect=True, log=True,
-            gather=None):
+            gather=None, rounds=False):
         """gather = (first_offset, stride, W, window_len) treats x as a 1-D song."""
         x = np.ascontiguousarray(x, np.float32)
         if gather is None:
@@ -114,7 +114,7 @@ def emu_lib():
         fbp = fb.ctypes.data_as(fp) if fb is not None else None
         wp = window.ctypes.data_as(fp) if window is not None else None
         rc = lib.bhmel_emu_forward(x.ctypes.data_as(fp), B, N, stride, row0, n_total, n_mels, fbp, wp,
-                                   float(f_min), float(f_max), 16000, int(reflect), int(log), 0,
+                                   float(f_min), float(f_max), 16000, int(reflect), int(log), 2 if rounds else 0,
                                    y.ctypes.data_as(fp))
         assert rc == 0
         return y

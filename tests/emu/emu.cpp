@@ -29,6 +29,9 @@ extern "C" int bhmel_emu_forward(const float* x, long long B, long long N, long 
   for (int i = 0; i < kNfft; ++i) win_half[i] = 0.5f * win[i];
   std::vector<float> tw = make_twiddles();
   PairTables pt = make_pairs(fb.data(), n_mels);
+  RoundTables rt = make_rounds(fb.data(), n_mels);
+  const bool use_rounds = (exact_log1p & 2) != 0;   // bit 1: independent-warp kernel's round tables
+  exact_log1p &= 1;
 
   const long long T = N / kHop + 1;
   const int tiles_per_row = (int)((T + kTileF - 1) / kTileF);
@@ -100,6 +103,20 @@ extern "C" int bhmel_emu_forward(const float* x, long long B, long long N, long 
       for (int f = 0; f < nf; ++f) {
         const float* prow = P.data() + (size_t)f * kPPitch;
         float* yrow = y + ((r * T + t0 + f) * (long long)n_mels);
+        if (use_rounds) {
+          for (size_t r = 0; r < rt.rounds.size(); ++r)
+            for (int li = 0; li < 16; ++li) {
+              const int m = (int)r * 16 + li;
+              const float* pp = prow + 4 * rt.g0[r * 16 + li];
+              const float* wp = rt.weights.data() + 4 * ((size_t)rt.rounds[r].woff4 + li);
+              float a[4] = {0, 0, 0, 0};
+              for (int g = 0; g < rt.rounds[r].ng; ++g)
+                for (int e = 0; e < 4; ++e) a[e] = fmaf(pp[4 * g + e], wp[64 * g + e], a[e]);
+              float v = (a[0] + a[1]) + (a[2] + a[3]);
+              if (log_scale) v = exact_log1p ? log1pf(v) : logf(1.0f + v);
+              if (m < n_mels) yrow[m] = v;
+            }
+        } else
         for (int mc = 0, c = 0; mc < n_mels; mc += kMelChunk, ++c) {
           for (int q = pt.chunk_start[c]; q < pt.chunk_start[c + 1]; ++q) {
             const PairDesc d = pt.pairs[q];

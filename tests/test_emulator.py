@@ -83,3 +83,29 @@ def test_emulator_dense_filterbank(emu_lib):
     ref = mel_oracle.mel_forward(x, fb=fb, window=window, log_scale=False, dtype=np.float64)
     assert np.all(y[..., 3] == 0)
     assert np.abs(y - ref).max() / ref.max() < 1e-5
+
+
+@pytest.mark.parametrize("pset", sorted(PSET_ARGS))
+def test_round_tables_equal_pair_tables(emu_lib, pset):
+    """The two mel table layouts (paired bands for the barrier kernel, lane-interleaved rounds for
+    the independent-warp kernel) must give bit-identical projections."""
+    log, n_mels, f_min, f_max, pad = PSET_ARGS[pset]
+    window, fb = load_params(pset)
+    x = signals.noise(2, 5000, 31)
+    a = emu_lib(x, n_mels, fb=fb, window=window, reflect=(pad == "reflect"), log=log)
+    b = emu_lib(x, n_mels, fb=fb, window=window, reflect=(pad == "reflect"), log=log, rounds=True)
+    assert np.array_equal(a, b)
+
+
+def test_round_tables_dense_and_odd_filter_counts(emu_lib):
+    rng = np.random.default_rng(4)
+    window, _ = load_params("P0")
+    x = signals.noise(1, 3000, 2)
+    for n_mels in (1, 7, 17, 33):
+        fb = np.ascontiguousarray(rng.random((513, n_mels), dtype=np.float32))
+        fb[rng.random((513, n_mels)) < 0.5] = 0.0
+        a = emu_lib(x, n_mels, fb=fb, window=window, log=False)
+        b = emu_lib(x, n_mels, fb=fb, window=window, log=False, rounds=True)
+        ref = mel_oracle.mel_forward(x, fb=fb, window=window, log_scale=False, dtype=np.float64)
+        assert np.array_equal(a, b)
+        assert np.abs(b - ref).max() / ref.max() < 1e-5

@@ -72,12 +72,12 @@ def test_golden_fixtures(mods, dev, name):
 @pytest.mark.parametrize("pset,shape", [("P0", (3, 40000)), ("P0", (2, 524160)), ("P0", (5, 513)), ("P0C", (2, 100)),
                                         ("P1", (2, 30000)), ("T5", (1, 20000)), ("P128", (3, 9999))])
 def test_kernel_variants_are_bit_identical(mods, dev, pset, shape):
-    """The warp-specialised schedule (default) and the barrier schedule run the same arithmetic."""
+    """The independent-warps schedule (default) and the barrier schedule run the same arithmetic."""
     m = mods[pset]
     x = signals.noise(shape[0], shape[1], 77 + shape[1])
     m.set_kernel_variant("barrier")
     y_bar = run(m, x, dev)
-    m.set_kernel_variant("ws")
+    m.set_kernel_variant("warp")
     y_ws = run(m, x, dev)
     assert np.array_equal(y_ws, y_bar)
     log, n_mels, f_min, f_max, pad = PSET_ARGS[pset]
@@ -90,15 +90,15 @@ def test_kernel_variants_gather_unaligned(mods, dev):
     m = mods["P0"]
     song = torch.from_numpy(signals.noise(1, 700001, 5)[0]).to(dev)
     outs = {}
-    for variant in ("barrier", "ws"):
+    for variant in ("barrier", "warp"):
         m.set_kernel_variant(variant)
         outs[variant] = m.forward_gather(song[1:], 3, 52415, 9, 262144).cpu().numpy()
-    m.set_kernel_variant("ws")
-    assert np.array_equal(outs["ws"], outs["barrier"])
+    m.set_kernel_variant("warp")
+    assert np.array_equal(outs["warp"], outs["barrier"])
     window, fb = load_params("P0")
     seq = np.stack([np.pad(song[1:].cpu().numpy(), (0, 600000))[3 + w * 52415: 3 + w * 52415 + 262144] for w in range(9)])
     ref = mel_oracle.mel_forward(seq, fb=fb, window=window, dtype=np.float64)
-    assert parity_error(outs["ws"], ref, True) < TARGET
+    assert parity_error(outs["warp"], ref, True) < TARGET
 
 
 @pytest.mark.parametrize("bulk", [True, False])
