@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_PKG, "libbhmel.so")
 PAD_CONSTANT, PAD_REFLECT = 0, 1
 OPT_BULK_COPY = 1
 OPT_KERNEL = 2
-KERNEL_BARRIER, KERNEL_INDEPENDENT_WARPS = 0, 1
+KERNEL_BARRIER, KERNEL_INDEPENDENT_WARPS, KERNEL_WARP_SPECIALIZED = 0, 1, 2
 OK, EINVAL, ECUDA, ESHAPE, EDEVICE = 0, 1, 2, 3, 4
 
 

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "bhmel_kernel_iw.cuh"
+#include "bhmel_kernel_ws.cuh"
 
 namespace {
 
@@ -53,7 +54,7 @@ struct bhmel_handle {
   int n_wt4 = 0;
   std::atomic<int64_t> launches{0};
   int use_bulk = 1;
-  int kernel_variant = BHMEL_KERNEL_INDEPENDENT_WARPS;
+  int kernel_variant = BHMEL_KERNEL_BARRIER;
   // bhmel_forward_host pipeline (lazily created)
   std::mutex host_mu;
   cudaStream_t hs[kHostSlots] = {nullptr, nullptr, nullptr};
@@ -142,6 +143,7 @@ int launch(bhmel_handle* h, const float* x, long long row_stride, long long row0
   p.N = N;
   p.T = N / bhmel::kHop + 1;
   const bool iw = h->kernel_variant == BHMEL_KERNEL_INDEPENDENT_WARPS;
+  const bool ws = h->kernel_variant == BHMEL_KERNEL_WARP_SPECIALIZED;
   const int tile_frames = iw ? bhmel::iw::kWTileF : bhmel::kTileF;
   p.tiles_per_row = static_cast<int>((p.T + tile_frames - 1) / tile_frames);
   p.n_tiles = static_cast<long long>(p.tiles_per_row) * B;
@@ -172,6 +174,12 @@ int launch(bhmel_handle* h, const float* x, long long row_stride, long long row0
       bhmel::iw::bhmel_logmel_iw_kernel<true><<<grid, bhmel::iw::kIwThreads, sizeof(bhmel::iw::SmemIW), stream>>>(q);
     else
       bhmel::iw::bhmel_logmel_iw_kernel<false><<<grid, bhmel::iw::kIwThreads, sizeof(bhmel::iw::SmemIW), stream>>>(q);
+  } else if (ws) {
+    const unsigned grid = static_cast<unsigned>(p.n_tiles < h->num_sms ? p.n_tiles : h->num_sms);
+    if (p.log_scale)
+      bhmel::ws::bhmel_logmel_ws_kernel<true><<<grid, bhmel::ws::kThreadsW, sizeof(bhmel::ws::SmemWS), stream>>>(p);
+    else
+      bhmel::ws::bhmel_logmel_ws_kernel<false><<<grid, bhmel::ws::kThreadsW, sizeof(bhmel::ws::SmemWS), stream>>>(p);
   } else {
     const unsigned grid = static_cast<unsigned>(p.n_tiles < h->num_sms ? p.n_tiles : h->num_sms);
     if (p.log_scale)
@@ -223,6 +231,10 @@ int bhmel_create(const bhmel_params* prm, bhmel_handle** out) {
                                static_cast<int>(sizeof(bhmel::SmemLayout))));
   BH_CUDA(cudaFuncSetAttribute(bhmel::bhmel_logmel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(sizeof(bhmel::SmemLayout))));
+  BH_CUDA(cudaFuncSetAttribute(bhmel::ws::bhmel_logmel_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(sizeof(bhmel::ws::SmemWS))));
+  BH_CUDA(cudaFuncSetAttribute(bhmel::ws::bhmel_logmel_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(sizeof(bhmel::ws::SmemWS))));
   BH_CUDA(cudaFuncSetAttribute(bhmel::iw::bhmel_logmel_iw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(sizeof(bhmel::iw::SmemIW))));
   BH_CUDA(cudaFuncSetAttribute(bhmel::iw::bhmel_logmel_iw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -316,7 +328,8 @@ int bhmel_set_option(bhmel_handle* h, int32_t option, int64_t value) {
       h->use_bulk = value != 0;
       return BHMEL_OK;
     case BHMEL_OPT_KERNEL:
-      if (value != BHMEL_KERNEL_BARRIER && value != BHMEL_KERNEL_INDEPENDENT_WARPS)
+      if (value != BHMEL_KERNEL_BARRIER && value != BHMEL_KERNEL_INDEPENDENT_WARPS &&
+          value != BHMEL_KERNEL_WARP_SPECIALIZED)
         return fail(BHMEL_EINVAL, "unknown kernel variant");
       h->kernel_variant = static_cast<int>(value);
       return BHMEL_OK;

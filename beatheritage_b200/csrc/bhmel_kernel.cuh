@@ -203,14 +203,14 @@ __device__ __forceinline__ void band_dot2_n(const float4* __restrict__ pa, const
 
 // One chunk (<= kMChunk output columns) of the mel projection for the 32 frames of the tile:
 // warp w takes pairs w, w + kWarps, ...; results go to the staging buffer [frame][column].
-template <bool kSmemW, bool kLog>
+template <bool kSmemW, bool kLog, int kStride = kWarps>
 __device__ __forceinline__ void mel_chunk(const float4* __restrict__ prow, const int4* __restrict__ pd, int npairs,
                                           const float* __restrict__ wbase, float* __restrict__ orow, int warp) {
   int4 dnext = pd[warp < npairs ? warp : 0];              // PairDesc, warp-uniform; prefetched one step ahead
 #pragma unroll 1
-  for (int q = warp; q < npairs; q += kWarps) {
+  for (int q = warp; q < npairs; q += kStride) {
     const int4 d = dnext;
-    if (q + kWarps < npairs) dnext = pd[q + kWarps];
+    if (q + kStride < npairs) dnext = pd[q + kStride];
     const float4* wp = reinterpret_cast<const float4*>(wbase + d.y);
     const float4* pa = prow + (d.x & 0xFFFF);
     const float4* pb = prow + (static_cast<unsigned>(d.x) >> 16);

@@ -1,0 +1,254 @@
+// bhmel_kernel_ws.cuh -- warp-specialised schedule of the fused log-mel kernel (sm_100a).
+//
+// Same arithmetic as bhmel_logmel_kernel (bhmel_kernel.cuh: identical FFT passes, pair
+// separation, paired banded mel, log epilogue -- results are bit-identical), different schedule:
+// the stages run concurrently on different warps of one persistent 512-thread CTA per SM and
+// hand 32-frame tiles to each other through mbarriers, so the latency-bound mel / store stage
+// fills the issue slots the FFT warps leave idle instead of alternating with them.
+//
+//   warps 0-7   (2 warpgroups, setmaxnreg -> 192)  FFT role: two frame pairs per warp per tile
+//   warps 8-15  (2 warpgroups, setmaxnreg ->  64)  producer + mel + store role
+//
+//   span[2]   4992-sample spans filled by the producer role one tile ahead of the FFT warps
+//             (TMA bulk copy, or per-element cp.async with the reflect / zero mapping) -> span_full[2]
+//   P[2]      power spectra [32][532] double buffered: FFT warps fill -> p_full[2], mel warps
+//             release -> p_empty[2].  The two rows a frame pair will write double as that pair's
+//             transpose scratch (real and imaginary planes are transposed one after the other), so
+//             the double buffer costs no extra shared memory.
+//   mel role  lane = frame, warp-uniform broadcast weights, statically unrolled pair dot
+//             products (mel_chunk of bhmel_kernel.cuh), staging + coalesced store inside the
+//             256-thread role group (named barrier 1).
+#pragma once
+#include "bhmel_kernel.cuh"
+
+namespace bhmel {
+namespace ws {
+
+constexpr int kPPitchW = 532;                          // 532/4 odd -> LDS.128 conflict free; 2 rows >= 4224 B
+constexpr int kFftWarps = 8;
+constexpr int kMelWarps = 8;
+constexpr int kMelThreads = kMelWarps * 32;
+constexpr int kThreadsW = (kFftWarps + kMelWarps) * 32;   // 512
+constexpr int kPlanePitch = 33;                        // floats per row of a transposed plane
+// setmaxnreg budget: the CTA is launched with 128 registers/thread (65536 / 512); registers only
+// move between the warpgroups of the CTA, so 2 * kFftRegs + 2 * kMelRegs must not exceed 4 * 128.
+constexpr int kLaunchRegs = 128;
+constexpr int kFftRegs = 192;
+constexpr int kMelRegs = 64;
+static_assert(2 * kFftRegs + 2 * kMelRegs <= 4 * kLaunchRegs, "setmaxnreg pool would deadlock");
+static_assert(2 * kPPitchW * 4 >= 32 * kPlanePitch * 4, "a pair's two P rows must hold one transposed plane");
+
+struct SmemWS {
+  float P[2][kTileF * kPPitchW];              // 136 192 B
+  float span[2][kSpan];                       //  39 936 B
+  float out[kTileF * kOutPitch];              //  12 416 B
+  float fw[kFwCap];                           //  16 384 B
+  int4 pairs[kPairCap];                       //   8 192 B
+  unsigned long long span_full[2];
+  unsigned long long p_full[2];
+  unsigned long long p_empty[2];
+};
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(unsigned long long* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mel_group_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(kMelThreads) : "memory"); }
+
+// Producer: every thread of the mel role takes part, so span_full always sees kMelThreads arrivals.
+__device__ __forceinline__ void issue_span(const KParams& p, long long tile, float* dst, unsigned long long* bar,
+                                           int mt) {
+  const long long r = tile / p.tiles_per_row;
+  const int tb = static_cast<int>(tile - r * p.tiles_per_row);
+  const long long s0 = static_cast<long long>(tb) * (kTileF * kHop) - kNfft / 2;
+  const long long row_off = p.row0 + r * p.row_stride;
+  long long valid = p.n_total - row_off;
+  valid = valid < 0 ? 0 : (valid > p.N ? p.N : valid);
+  const float* row = p.x + row_off;
+  const bool interior = s0 >= 0 && s0 + kSpan <= valid;
+  if (p.use_bulk && interior && ((reinterpret_cast<uintptr_t>(row + s0) & 15) == 0)) {
+    if (mt == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(bar, kSpanBytes);
+      bulk_g2s(dst, row + s0, kSpanBytes, bar);
+    } else {
+      mbar_arrive(bar);
+    }
+    return;
+  }
+  if (interior) {   // unaligned but fully inside the row: plain element copies
+    const float* src = row + s0;
+    for (int e = mt; e < kSpan; e += kMelThreads) cp_async_4(dst + e, src + e, 4);
+  } else {
+    const long long N = p.N;
+    for (int e = mt; e < kSpan; e += kMelThreads) {
+      long long i = s0 + e;
+      if (i < 0) i = p.pad_reflect ? -i : -1;
+      else if (i >= N) i = p.pad_reflect ? 2 * (N - 1) - i : -1;
+      const bool ok = (i >= 0) && (i < valid);
+      cp_async_4(dst + e, row + (ok ? i : 0), ok ? 4 : 0);
+    }
+  }
+  cp_async_arrive_noinc(bar);
+}
+
+template <bool kLog>
+__global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __grid_constant__ KParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SmemWS& S = *reinterpret_cast<SmemWS*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  const bool fw_in_smem = p.n_weights <= kFwCap;
+  if (fw_in_smem)
+    for (int i = tid; i < p.n_weights; i += kThreadsW) S.fw[i] = p.weights[i];
+  for (int i = tid; i < p.n_pairs; i += kThreadsW) S.pairs[i] = reinterpret_cast<const int4*>(p.pairs)[i];
+  if (tid == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&S.span_full[b], kMelThreads);
+      mbar_init(&S.p_full[b], kFftWarps);
+      mbar_init(&S.p_empty[b], kMelWarps);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp < kFftWarps) {
+    // =============================== FFT role ===============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(kFftRegs));
+    float wreg[32], twr[32], twi[32];
+#pragma unroll
+    for (int m = 0; m < 32; ++m) {
+      wreg[m] = __ldg(p.win_half + lane + 32 * m);
+      const float2 t = __ldg(p.tw + m * 32 + lane);
+      twr[m] = t.x;
+      twi[m] = t.y;
+    }
+    const int src = (32 - lane) & 31;
+    int it = 0;
+#pragma unroll 1
+    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int b = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      mbar_wait(&S.span_full[b], ph);
+      mbar_wait(&S.p_empty[b], ph ^ 1);   // the mel role has released this P buffer (tile it-2)
+#pragma unroll 1
+      for (int j = warp; j < kPairs; j += kFftWarps) {
+        float* rows = S.P[b] + (2 * j) * kPPitchW;      // this pair's two P rows; scratch until written
+        float ar[32], ai[32];
+        {
+          float v[36];
+          const float* sp = S.span[b] + (2 * j) * kHop + lane;
+#pragma unroll
+          for (int m = 0; m < 36; ++m) v[m] = sp[32 * m];
+          fft32_pass_a(v, wreg, ar, ai);
+        }
+        // transpose the real plane, then the imaginary plane, through the pair's own rows
+        float ur[32], ui[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) rows[k * kPlanePitch + lane] = ar[k];
+        __syncwarp();
+#pragma unroll
+        for (int n = 0; n < 32; ++n) ur[n] = rows[lane * kPlanePitch + n];
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) rows[k * kPlanePitch + lane] = ai[k];
+        __syncwarp();
+#pragma unroll
+        for (int n = 0; n < 32; ++n) ui[n] = rows[lane * kPlanePitch + n];
+        __syncwarp();
+        float br[32], bi[32];
+        fft32_pass_b(ur, ui, twr, twi, br, bi);
+        float* Pa = rows + lane;
+        float* Pb = Pa + kPPitchW;
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) {
+          const int s = 31 - k2;
+          float pr = __shfl_sync(0xffffffffu, br[s], src);
+          float pi = __shfl_sync(0xffffffffu, bi[s], src);
+          if (lane == 0) {
+            pr = br[(s + 1) & 31];
+            pi = bi[(s + 1) & 31];
+          }
+          const float a1 = br[k2] + pr, a2 = bi[k2] - pi;
+          const float b1 = bi[k2] + pi, b2 = pr - br[k2];
+          Pa[32 * k2] = fmaf(a1, a1, a2 * a2);
+          Pb[32 * k2] = fmaf(b1, b1, b2 * b2);
+        }
+        if (lane == 0) {
+          const float zr = 2.f * br[16], zi = 2.f * bi[16];
+          Pa[512] = zr * zr;
+          Pb[512] = zi * zi;
+        }
+        if (lane < 6) rows[(lane / 3) * kPPitchW + kBins + lane % 3] = 0.f;   // bins 513..515 read as zero weights' partners
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.p_full[b]);
+    }
+  } else {
+    // ======================= producer + mel + store role =======================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(kMelRegs));
+    const int mt = tid - kFftWarps * 32;
+    const int mw = warp - kFftWarps;
+    {
+      long long t0 = blockIdx.x;
+      if (t0 < p.n_tiles) issue_span(p, t0, S.span[0], &S.span_full[0], mt);
+      t0 += gridDim.x;
+      if (t0 < p.n_tiles) issue_span(p, t0, S.span[1], &S.span_full[1], mt);
+    }
+    int it = 0;
+#pragma unroll 1
+    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int b = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      mbar_wait(&S.p_full[b], ph);
+      // every FFT warp is done with tile `it`, so span[b] is free: fetch the tile two steps ahead
+      const long long tile2 = tile + 2 * static_cast<long long>(gridDim.x);
+      if (tile2 < p.n_tiles) issue_span(p, tile2, S.span[b], &S.span_full[b], mt);
+
+      const long long r = tile / p.tiles_per_row;
+      const int t0 = static_cast<int>(tile - r * p.tiles_per_row) * kTileF;
+      const long long frames_left = p.T - t0;
+      const int nf = frames_left < kTileF ? static_cast<int>(frames_left) : kTileF;
+      float* ybase = p.y + (r * p.T + t0) * static_cast<long long>(p.n_mels);
+      const float4* prow = reinterpret_cast<const float4*>(S.P[b] + lane * kPPitchW);
+      float* orow = S.out + lane * kOutPitch;
+      for (int mc = 0, c = 0; mc < p.n_mels; mc += kMChunk, ++c) {
+        const int mcount = (p.n_mels - mc) < kMChunk ? (p.n_mels - mc) : kMChunk;
+        const int4* pd = S.pairs + c * (kMChunk / 2);
+        if (fw_in_smem) mel_chunk<true, kLog, kMelWarps>(prow, pd, (mcount + 1) >> 1, S.fw, orow, mw);
+        else mel_chunk<false, kLog, kMelWarps>(prow, pd, (mcount + 1) >> 1, p.weights, orow, mw);
+        if (mc + kMChunk >= p.n_mels) {   // last chunk: this warp no longer reads P[b]
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&S.p_empty[b]);
+        }
+        mel_group_sync();   // staging complete
+        {
+          constexpr int kFr = kTileF / kMelWarps, kCo = kMChunk / 32;   // 4 frames x 3 column steps
+          float vals[kFr][kCo];
+#pragma unroll
+          for (int a = 0; a < kFr; ++a)
+#pragma unroll
+            for (int bb = 0; bb < kCo; ++bb) vals[a][bb] = S.out[(mw + a * kMelWarps) * kOutPitch + lane + 32 * bb];
+#pragma unroll
+          for (int a = 0; a < kFr; ++a) {
+            const int fr = mw + a * kMelWarps;
+            float* yrow = ybase + static_cast<long long>(fr) * p.n_mels + mc;
+#pragma unroll
+            for (int bb = 0; bb < kCo; ++bb) {
+              const int c2 = lane + 32 * bb;
+              if (fr < nf && c2 < mcount) yrow[c2] = vals[a][bb];
+            }
+          }
+        }
+        mel_group_sync();   // staging free again
+      }
+    }
+  }
+}
+
+}  // namespace ws
+}  // namespace bhmel

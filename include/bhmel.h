@@ -111,6 +111,7 @@ int bhmel_forward_host(bhmel_handle* h, const float* x_host, int64_t B, int64_t 
 #define BHMEL_OPT_KERNEL 2
 #define BHMEL_KERNEL_BARRIER 0
 #define BHMEL_KERNEL_INDEPENDENT_WARPS 1
+#define BHMEL_KERNEL_WARP_SPECIALIZED 2
 int bhmel_set_option(bhmel_handle* h, int32_t option, int64_t value);
 
 /* Introspection used by tests and bench.py. */

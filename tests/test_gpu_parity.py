@@ -16,6 +16,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-3
 TARGET = 2e-5
 WINDOW = 524160
+DEFAULT_VARIANT = "barrier"
 
 
 @pytest.fixture(scope="module")
@@ -78,7 +79,11 @@ def test_kernel_variants_are_bit_identical(mods, dev, pset, shape):
     m.set_kernel_variant("barrier")
     y_bar = run(m, x, dev)
     m.set_kernel_variant("warp")
+    y_iw = run(m, x, dev)
+    m.set_kernel_variant("ws")
     y_ws = run(m, x, dev)
+    m.set_kernel_variant(DEFAULT_VARIANT)
+    assert np.array_equal(y_iw, y_bar)
     assert np.array_equal(y_ws, y_bar)
     log, n_mels, f_min, f_max, pad = PSET_ARGS[pset]
     window, fb = load_params(pset)
@@ -90,11 +95,12 @@ def test_kernel_variants_gather_unaligned(mods, dev):
     m = mods["P0"]
     song = torch.from_numpy(signals.noise(1, 700001, 5)[0]).to(dev)
     outs = {}
-    for variant in ("barrier", "warp"):
+    for variant in ("barrier", "warp", "ws"):
         m.set_kernel_variant(variant)
         outs[variant] = m.forward_gather(song[1:], 3, 52415, 9, 262144).cpu().numpy()
-    m.set_kernel_variant("warp")
+    m.set_kernel_variant(DEFAULT_VARIANT)
     assert np.array_equal(outs["warp"], outs["barrier"])
+    assert np.array_equal(outs["ws"], outs["barrier"])
     window, fb = load_params("P0")
     seq = np.stack([np.pad(song[1:].cpu().numpy(), (0, 600000))[3 + w * 52415: 3 + w * 52415 + 262144] for w in range(9)])
     ref = mel_oracle.mel_forward(seq, fb=fb, window=window, dtype=np.float64)

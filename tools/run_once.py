@@ -13,9 +13,12 @@ ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--reps", type=int, default=4)
 ap.add_argument("--samples", type=int, default=524160)
 ap.add_argument("--mels", type=int, default=80)
+ap.add_argument("--variant", default=None)
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 mel = MelSpectrogram("torchaudio", True, 16000, 1024, a.mels, 128, 20, 8000, "reflect").to(dev)
+if a.variant:
+    mel.set_kernel_variant(a.variant)
 g = torch.Generator(device=dev).manual_seed(1234)
 x = torch.rand(a.batch, a.samples, device=dev, generator=g).mul_(2).sub_(1)
 torch.cuda.synchronize()
