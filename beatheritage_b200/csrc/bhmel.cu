@@ -54,7 +54,7 @@ struct bhmel_handle {
   int n_wt4 = 0;
   std::atomic<int64_t> launches{0};
   int use_bulk = 1;
-  int kernel_variant = BHMEL_KERNEL_BARRIER;
+  int kernel_variant = BHMEL_KERNEL_WARP_SPECIALIZED;
   // bhmel_forward_host pipeline (lazily created)
   std::mutex host_mu;
   cudaStream_t hs[kHostSlots] = {nullptr, nullptr, nullptr};
@@ -201,9 +201,9 @@ int bhmel_version(void) { return BHMEL_VERSION; }
 const char* bhmel_last_error(void) { return g_err.c_str(); }
 
 void bhmel_kernel_info(int32_t* smem_bytes, int32_t* threads, int32_t* tile_frames) {
-  if (smem_bytes) *smem_bytes = static_cast<int32_t>(sizeof(bhmel::iw::SmemIW));
-  if (threads) *threads = bhmel::iw::kIwThreads;
-  if (tile_frames) *tile_frames = bhmel::iw::kWTileF;
+  if (smem_bytes) *smem_bytes = static_cast<int32_t>(sizeof(bhmel::ws::SmemWS));
+  if (threads) *threads = bhmel::ws::kThreadsW;
+  if (tile_frames) *tile_frames = bhmel::kTileF;
 }
 
 int bhmel_create(const bhmel_params* prm, bhmel_handle** out) {

@@ -145,7 +145,7 @@ class MelSpectrogram(nn.Module):
         self._handles: dict[int, int] = {}        # device index -> bhmel_handle*
         self._stamp: dict[int, tuple] = {}        # device index -> buffer versions the handle was built from
         self._bulk = True
-        self._variant = _lib.KERNEL_BARRIER
+        self._variant = _lib.KERNEL_WARP_SPECIALIZED
         self._register()
 
     def _register(self) -> None:
@@ -222,8 +222,8 @@ class MelSpectrogram(nn.Module):
             _lib.check(_lib.lib().bhmel_set_option(h, _lib.OPT_BULK_COPY, int(enabled)))
 
     def set_kernel_variant(self, variant: str) -> None:
-        """'warp' (default: independent per-warp pipelines) or 'barrier' (stage-by-stage CTA
-        schedule); the two produce bit-identical results."""
+        """'ws' (default: warp-specialised FFT / mel roles), 'barrier' (stage-by-stage CTA schedule)
+        or 'warp' (independent per-warp pipelines); all three produce bit-identical results."""
         self._variant = {"warp": _lib.KERNEL_INDEPENDENT_WARPS, "barrier": _lib.KERNEL_BARRIER,
                          "ws": _lib.KERNEL_WARP_SPECIALIZED}[variant]
         for h in self._handles.values():

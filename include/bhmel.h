@@ -104,10 +104,14 @@ int bhmel_forward_host(bhmel_handle* h, const float* x_host, int64_t B, int64_t 
 /* Tuning / debugging switches (per handle).  BHMEL_OPT_BULK_COPY: 1 (default) stages aligned
  * interior tiles with the TMA bulk copy, 0 forces the per-element cp.async path everywhere. */
 #define BHMEL_OPT_BULK_COPY 1
-/* BHMEL_OPT_KERNEL: which schedule of the (arithmetically identical, bit-identical) fused kernel to
- * launch: BHMEL_KERNEL_INDEPENDENT_WARPS (default: every warp is its own load -> FFT -> mel -> store
- * pipeline over 8-frame tiles, no CTA barriers) or BHMEL_KERNEL_BARRIER (32-frame CTA tiles, all
- * warps step through the stages together, separated by CTA barriers). */
+/* BHMEL_OPT_KERNEL: which schedule of the fused kernel to launch.  All three run the same
+ * arithmetic and produce bit-identical results:
+ *   BHMEL_KERNEL_WARP_SPECIALIZED (default) 32-frame tiles; 8 FFT warps and 8 producer/mel/store
+ *       warps of one 512-thread CTA run concurrently and hand tiles over through mbarriers;
+ *   BHMEL_KERNEL_BARRIER            32-frame tiles; 8 warps step through the stages together,
+ *       separated by CTA barriers;
+ *   BHMEL_KERNEL_INDEPENDENT_WARPS  8-frame per-warp tiles; every warp is its own
+ *       load -> FFT -> mel -> store pipeline, no CTA barriers. */
 #define BHMEL_OPT_KERNEL 2
 #define BHMEL_KERNEL_BARRIER 0
 #define BHMEL_KERNEL_INDEPENDENT_WARPS 1
@@ -119,7 +123,7 @@ int bhmel_version(void);
 const char* bhmel_last_error(void);
 /* Number of kernel launches issued through this handle so far (bench.py's gpu_launches). */
 int64_t bhmel_launch_count(const bhmel_handle* h);
-/* Static facts about the default (independent-warps) kernel: dynamic shared memory bytes,
+/* Static facts about the default (warp-specialised) kernel: dynamic shared memory bytes,
  * threads per CTA, frames per tile. Any pointer may be NULL. */
 void bhmel_kernel_info(int32_t* smem_bytes, int32_t* threads, int32_t* tile_frames);
 

@@ -37,7 +37,7 @@ def test_version_and_kernel_info(lib):
     assert lib.bhmel_version() == 100
     smem, threads, tile = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
     lib.bhmel_kernel_info(ctypes.byref(smem), ctypes.byref(threads), ctypes.byref(tile))
-    assert threads.value == 256 and tile.value == 8
+    assert threads.value == 512 and tile.value == 32
     assert 0 < smem.value <= 227 * 1024          # fits one CTA per SM on sm_100
 
 

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-3
 TARGET = 2e-5
 WINDOW = 524160
-DEFAULT_VARIANT = "barrier"
+DEFAULT_VARIANT = "ws"
 
 
 @pytest.fixture(scope="module")
