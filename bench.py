@@ -330,7 +330,7 @@ def run_ours(args):
                     "finite": e2e_ok},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "bhmel_logmel_kernel",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "bhmel_logmel_ws_kernel",
                          "algorithmic_bytes_per_launch": BATCH * ALGO_BYTES_PER_WINDOW,
                          "note": "fp32 CUDA-core FFT: the FP32 issue rate, not HBM, bounds this kernel (DESIGN.md)"},
             "cpu_baseline": cpu,
