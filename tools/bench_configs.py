@@ -1,0 +1,211 @@
+#!/usr/bin/env python3
+"""Measurement configs C1..C5 of SURVEY.md section 8(d) on one B200 (bench.py covers C3, the headline).
+
+    python tools/bench_configs.py [--out profiles/r1_configs.json] [--skip-c5]
+
+C1  10 s clip: latency (us) of one call, ours vs torchaudio on the same GPU vs the CPU port.
+C2  3-min song: 6 (parallel) and 46 (sequential, stride 52 415) windows; module mode and fused gather.
+C4  1-hour audio streamed in overlapping windows: stride sweep x {materialised batch, fused gather},
+    and a batch-size sweep of the module interface (achieved algorithmic GB/s vs batch).
+C5  inference slice: song -> segment -> H2D -> frontend -> bf16 -> cat 384 conditioning channels ->
+    swapaxes -> random-init HF WhisperEncoder (whisper-small dims, 464 input channels); frontend
+    share of wall time for the reference's GPU frontend (torchaudio: cuFFT + cuBLAS) and ours.
+The "reference GPU path" is torchaudio.transforms.MelSpectrogram + log1p + permute on CUDA, i.e.
+what the reference module runs when the model sits on a GPU; informative, not the published baseline.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from beatheritage_b200 import MelSpectrogram  # noqa: E402
+from beatheritage_b200.segment import segment_plan  # noqa: E402
+from oracle import mel_oracle  # noqa: E402
+from oracle.torch_port import TorchPortMel  # noqa: E402
+
+WINDOW, SR, HOP, M = 524160, 16000, 128, 80
+P0 = ("torchaudio", True, SR, 1024, M, HOP, 20, 8000, "reflect")
+dev = torch.device("cuda", 0)
+
+
+def timed(fn, reps, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+class TorchaudioGpu(torch.nn.Module):
+    """The reference module's own arithmetic on CUDA (spectrogram.py:38-49, 79-82)."""
+
+    def __init__(self):
+        super().__init__()
+        import torchaudio
+        self.t = torchaudio.transforms.MelSpectrogram(sample_rate=SR, n_fft=1024, n_mels=M, hop_length=HOP,
+                                                      center=True, f_min=20, f_max=8000, pad_mode="reflect")
+
+    def forward(self, x):
+        return torch.log1p(self.t(x)).permute(0, 2, 1)
+
+
+def algo_bytes(n_in_samples, n_windows):
+    return 4 * n_in_samples + 4 * n_windows * (WINDOW // HOP + 1) * M
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r1_configs.json"))
+    ap.add_argument("--skip-c5", action="store_true")
+    args = ap.parse_args()
+    res = {"gpu": torch.cuda.get_device_name(0), "torch": torch.__version__}
+    mel = MelSpectrogram(*P0).to(dev)
+    try:
+        ta = TorchaudioGpu().to(dev)
+    except Exception as e:   # torchaudio missing
+        ta = None
+        res["torchaudio_gpu"] = f"unavailable: {e}"
+    torch.set_num_threads(os.cpu_count() or 1)
+    port = TorchPortMel()
+
+    # ------------------------------------------------------------------ C1
+    g = torch.Generator().manual_seed(0)
+    x1 = torch.rand(1, 160000, generator=g) * 2 - 1
+    x1d = x1.to(dev)
+    c1 = {"ours_us": 1e3 * timed(lambda: mel(x1d), 200)}
+    if ta is not None:
+        c1["torchaudio_gpu_us"] = 1e3 * timed(lambda: ta(x1d), 200)
+        c1["max_abs_diff_vs_torchaudio_gpu"] = float((mel(x1d) - ta(x1d)).abs().max())
+    t0 = time.perf_counter()
+    for _ in range(20):
+        yc = port(x1)
+    c1["cpu_port_us"] = 1e6 * (time.perf_counter() - t0) / 20
+    c1["cpu_threads"] = torch.get_num_threads()
+    c1["max_abs_err_vs_cpu_port"] = float((mel(x1d).cpu() - yc).abs().max())
+    res["C1_clip_10s"] = c1
+
+    # ------------------------------------------------------------------ C2
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from tests.golden import signals
+    song = signals.music(2_880_000, seed=1)
+    song_d = torch.from_numpy(song).to(dev)
+    c2 = {}
+    for name, parallel in (("sequential_46", False), ("parallel_6", True)):
+        plan = segment_plan(len(song), parallel=parallel)
+        seq = torch.from_numpy(mel_oracle.segment(song, plan.window_len, plan.stride)).to(dev)
+        assert seq.shape[0] == plan.n_windows
+        ms_mod = timed(lambda: mel(seq), 50)
+        ms_gat = timed(lambda: mel.forward_gather(song_d, 0, plan.stride, plan.n_windows, plan.window_len), 50)
+        same = bool(torch.equal(mel(seq), mel.forward_gather(song_d, 0, plan.stride, plan.n_windows, plan.window_len)))
+        entry = {"windows": plan.n_windows, "module_ms": ms_mod, "gather_ms": ms_gat, "gather_equals_module": same,
+                 "window_audio_s_per_s_module": plan.n_windows * WINDOW / SR / (ms_mod / 1e3),
+                 "song_s_per_s_gather": len(song) / SR / (ms_gat / 1e3)}
+        if ta is not None:
+            entry["torchaudio_gpu_ms"] = timed(lambda: ta(seq), 20)
+        c2[name] = entry
+    res["C2_song_3min"] = c2
+
+    # ------------------------------------------------------------------ C4
+    n_hour = 57_600_000
+    gd = torch.Generator(device=dev).manual_seed(2)
+    hour = torch.rand(n_hour, device=dev, generator=gd).mul_(2).sub_(1)
+    c4 = {"stride_sweep": [], "batch_sweep": []}
+    for stride in (52415, 131040, 262080, 524160):
+        rem = (n_hour - WINDOW) % stride
+        padded = n_hour + (0 if rem == 0 else stride - rem)
+        W = (padded - WINDOW) // stride + 1
+        ms_g = timed(lambda: mel.forward_gather(hour, 0, stride, W, WINDOW), 5, warm=2)
+        entry = {"stride": stride, "windows": W, "gather_ms": ms_g,
+                 "gather_window_audio_s_per_s": W * WINDOW / SR / (ms_g / 1e3),
+                 "gather_song_s_per_s": n_hour / SR / (ms_g / 1e3),
+                 "gather_algorithmic_GBps": algo_bytes(n_hour, W) / (ms_g / 1e3) / 1e9}
+        # materialised batch (what Preprocessor.segment builds): [W, 524160] f32
+        hp = torch.nn.functional.pad(hour, (0, padded - n_hour))
+        batch = hp.as_strided((W, WINDOW), (stride, 1)).contiguous()
+        ms_m = timed(lambda: mel(batch), 5, warm=2)
+        entry.update({"module_ms": ms_m, "module_window_audio_s_per_s": W * WINDOW / SR / (ms_m / 1e3),
+                      "module_algorithmic_GBps": algo_bytes(W * WINDOW, W) / (ms_m / 1e3) / 1e9,
+                      "materialised_input_MB": W * WINDOW * 4 / 1e6})
+        if stride == 52415:
+            entry["gather_equals_module"] = bool(torch.equal(mel(batch[:64]), mel.forward_gather(hour, 0, stride, 64, WINDOW)))
+            for b in (1, 4, 16, 64, 256, W):
+                xb = batch[:b]
+                ms = timed(lambda: mel(xb), 20 if b <= 64 else 5, warm=2)
+                c4["batch_sweep"].append({"batch": b, "ms": ms, "window_audio_s_per_s": b * WINDOW / SR / (ms / 1e3),
+                                          "algorithmic_GBps": algo_bytes(b * WINDOW, b) / (ms / 1e3) / 1e9})
+        del batch, hp
+        c4["stride_sweep"].append(entry)
+    res["C4_one_hour_stream"] = c4
+    del hour
+    torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------------ C5
+    if not args.skip_c5:
+        try:
+            from transformers import WhisperConfig
+            from transformers.models.whisper.modeling_whisper import WhisperEncoder
+            torch.manual_seed(0)
+            cfg = WhisperConfig(d_model=768, encoder_layers=12, encoder_attention_heads=12, encoder_ffn_dim=3072,
+                                num_mel_bins=M + 384, max_source_positions=2048)
+            enc = WhisperEncoder(cfg).to(dev).to(torch.bfloat16).eval()
+            plan = segment_plan(len(song))
+            seq_host = torch.from_numpy(mel_oracle.segment(song, plan.window_len, plan.stride)).pin_memory()
+            cond = torch.randn(1, 1, 384, device=dev, dtype=torch.bfloat16)
+
+            def run(frontend, batch):
+                t_front = t_total = 0.0
+                for i in range(0, seq_host.shape[0], batch):
+                    xb = seq_host[i:i + batch]
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    xd = xb.to(dev, non_blocking=True)                    # server.py:42
+                    fr = frontend(xd)                                     # modeling_mapperatorinator.py:351
+                    torch.cuda.synchronize()
+                    t1 = time.perf_counter()
+                    fr = fr.to(torch.bfloat16)                            # :352
+                    fr = torch.cat([fr, cond.expand(fr.shape[0], fr.shape[1], -1)], dim=-1)   # :369-370
+                    with torch.no_grad():
+                        enc(fr.swapaxes(1, 2))                            # :375-376 + encoder
+                    torch.cuda.synchronize()
+                    t2 = time.perf_counter()
+                    t_front += t1 - t0
+                    t_total += t2 - t0
+                return t_front, t_total
+
+            c5 = {"encoder": "HF WhisperEncoder random init, d_model 768, 12 layers, 464 input channels, bf16",
+                  "windows": int(seq_host.shape[0])}
+            fronts = {"ours": mel}
+            if ta is not None:
+                fronts["torchaudio_gpu"] = ta
+            with torch.no_grad():
+                for fname, f in fronts.items():
+                    for mode, batch in (("sequential_b1", 1), ("parallel_b6", 6)):
+                        run(f, batch)
+                        tf, tt = run(f, batch)
+                        c5[f"{fname}_{mode}"] = {"frontend_ms_incl_h2d": 1e3 * tf, "total_ms": 1e3 * tt,
+                                                 "frontend_share": tf / tt}
+            res["C5_inference_slice"] = c5
+        except Exception as e:
+            res["C5_inference_slice"] = {"unavailable": f"{type(e).__name__}: {e}"}
+
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    json.dump(res, open(args.out, "w"), indent=1)
+    print(json.dumps(res, indent=1))
+
+
+if __name__ == "__main__":
+    main()
