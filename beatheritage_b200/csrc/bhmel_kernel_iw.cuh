@@ -116,7 +116,7 @@ __device__ __forceinline__ void mel_rounds(const float* __restrict__ prows, cons
       a3 = fmaf(x4.w, w4.w, a3);
     }
     float v = (a0 + a1) + (a2 + a3);
-    if constexpr (kLog) v = __logf(1.0f + v);
+    if constexpr (kLog) v = fast_log1p(v);
     const int m = r * 16 + li;
     if (frame_ok && m < q.k.n_mels) yrow[m] = v;
   }
