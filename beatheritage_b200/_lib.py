@@ -33,6 +33,14 @@ class BhmelParams(ctypes.Structure):
     ]
 
 
+class BhmelOutDesc(ctypes.Structure):
+    _fields_ = [("y", ctypes.c_void_p), ("dtype", ctypes.c_int32), ("frame_pitch", ctypes.c_int64),
+                ("row_pitch", ctypes.c_int64)]
+
+
+OUT_F32, OUT_BF16 = 0, 1
+
+
 class BhmelError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"libbhmel error {code}: {message}")
@@ -55,6 +63,7 @@ SIGNATURES = {
     "bhmel_get_window": (ctypes.c_int, [_vp, _fp]),
     "bhmel_num_frames": (_i64, [_vp, _i64]),
     "bhmel_forward": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
+    "bhmel_forward_ex": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, ctypes.POINTER(BhmelOutDesc), _vp]),
     "bhmel_forward_gather": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
     "bhmel_forward_host": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _vp]),
     "bhmel_set_option": (ctypes.c_int, [_vp, _i32, _i64]),

@@ -123,8 +123,16 @@ int check_device(const bhmel_handle* h) {
   return BHMEL_OK;
 }
 
+struct OutSpec {
+  void* y;
+  int bf16;
+  long long frame_pitch;   // 0 -> n_mels
+  long long row_pitch;     // 0 -> T * frame_pitch
+};
+
 int launch(bhmel_handle* h, const float* x, long long row_stride, long long row0, long long n_total,
-           long long B, long long N, float* y, cudaStream_t stream) {
+           long long B, long long N, OutSpec out, cudaStream_t stream) {
+  void* y = out.y;
   if (!h) return fail(BHMEL_EINVAL, "null handle");
   if (!x || !y) return fail(BHMEL_EINVAL, "null data pointer");
   if (B <= 0 || N <= 0) return fail(BHMEL_ESHAPE, "batch and sample count must be positive");
@@ -147,7 +155,12 @@ int launch(bhmel_handle* h, const float* x, long long row_stride, long long row0
   const int tile_frames = iw ? bhmel::iw::kWTileF : bhmel::kTileF;
   p.tiles_per_row = static_cast<int>((p.T + tile_frames - 1) / tile_frames);
   p.n_tiles = static_cast<long long>(p.tiles_per_row) * B;
-  p.y = y;
+  p.y = static_cast<float*>(y);
+  p.y_frame_pitch = out.frame_pitch > 0 ? out.frame_pitch : h->prm.n_mels;
+  p.y_row_pitch = out.row_pitch > 0 ? out.row_pitch : p.T * p.y_frame_pitch;
+  p.y_bf16 = out.bf16;
+  if (p.y_frame_pitch < h->prm.n_mels || p.y_row_pitch < p.T * p.y_frame_pitch)
+    return fail(BHMEL_EINVAL, "output pitches too small for [T][n_mels]");
   p.win_half = h->d_win;
   p.tw = h->d_tw;
   p.pairs = h->d_pairs;
@@ -343,14 +356,25 @@ int64_t bhmel_launch_count(const bhmel_handle* h) { return h ? h->launches.load(
 int bhmel_forward(bhmel_handle* h, const float* x, int64_t B, int64_t N, int64_t x_row_stride, float* y,
                   void* stream) {
   if (x_row_stride < N) return fail(BHMEL_EINVAL, "x_row_stride must be >= N");
-  return launch(h, x, x_row_stride, 0, LLONG_MAX, B, N, y, static_cast<cudaStream_t>(stream));
+  return launch(h, x, x_row_stride, 0, LLONG_MAX, B, N, OutSpec{y, 0, 0, 0}, static_cast<cudaStream_t>(stream));
+}
+
+int bhmel_forward_ex(bhmel_handle* h, const float* x, int64_t B, int64_t N, int64_t x_row_stride,
+                     const bhmel_out_desc* out, void* stream) {
+  if (!out) return fail(BHMEL_EINVAL, "null output descriptor");
+  if (x_row_stride < N) return fail(BHMEL_EINVAL, "x_row_stride must be >= N");
+  if (out->dtype != BHMEL_OUT_F32 && out->dtype != BHMEL_OUT_BF16) return fail(BHMEL_EINVAL, "unknown output dtype");
+  return launch(h, x, x_row_stride, 0, LLONG_MAX, B, N,
+                OutSpec{out->y, out->dtype == BHMEL_OUT_BF16, out->frame_pitch, out->row_pitch},
+                static_cast<cudaStream_t>(stream));
 }
 
 int bhmel_forward_gather(bhmel_handle* h, const float* song, int64_t n_song, int64_t first_offset,
                          int64_t stride, int64_t W, int64_t window_len, float* y, void* stream) {
   if (n_song < 0 || first_offset < 0 || stride <= 0)
     return fail(BHMEL_EINVAL, "need n_song >= 0, first_offset >= 0, stride > 0");
-  return launch(h, song, stride, first_offset, n_song, W, window_len, y, static_cast<cudaStream_t>(stream));
+  return launch(h, song, stride, first_offset, n_song, W, window_len, OutSpec{y, 0, 0, 0},
+                static_cast<cudaStream_t>(stream));
 }
 
 int bhmel_forward_host(bhmel_handle* h, const float* x_host, int64_t B, int64_t N, int64_t x_row_stride,
@@ -396,7 +420,7 @@ int bhmel_forward_host(bhmel_handle* h, const float* x_host, int64_t B, int64_t 
     BH_CUDA(cudaMemcpy2DAsync(h->d_in[slot], row_in, x_host + b0 * x_row_stride,
                               static_cast<size_t>(x_row_stride) * sizeof(float), row_in,
                               static_cast<size_t>(nb), cudaMemcpyHostToDevice, s));
-    if (int rc = launch(h, h->d_in[slot], N, 0, LLONG_MAX, nb, N, h->d_out[slot], s)) return rc;
+    if (int rc = launch(h, h->d_in[slot], N, 0, LLONG_MAX, nb, N, OutSpec{h->d_out[slot], 0, 0, 0}, s)) return rc;
     BH_CUDA(cudaMemcpyAsync(y_host + static_cast<size_t>(b0) * T * h->prm.n_mels, h->d_out[slot],
                             static_cast<size_t>(nb) * row_out, cudaMemcpyDeviceToHost, s));
   }

@@ -22,6 +22,7 @@
 //                 read with conflict-free 128-bit loads), log1p epilogue, staged through shared
 //                 memory so the [frames, n_mels] tile is written with coalesced stores.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -65,7 +66,9 @@ struct KParams {
   long long N;             // logical row length (samples per window)
   long long T;             // frames per row = N / hop + 1
   long long n_tiles;
-  float* y;                // [B][T][n_mels]
+  float* y;                // output base: element (row r, frame t, mel m) at r*y_row_pitch + t*y_frame_pitch + m
+  long long y_row_pitch;   // elements between rows     (T * n_mels for the plain [B][T][n_mels] layout)
+  long long y_frame_pitch; // elements between frames   (n_mels for the plain layout)
   const float* win_half;   // [1024]
   const float2* tw;        // [32*32]
   const PairDesc* pairs;   // [n_pairs]  (bhmel_tables.h make_pairs)
@@ -78,7 +81,15 @@ struct KParams {
   int use_bulk;
   int n_weights;           // floats in `weights` (multiple of 8)
   int n_pairs;
+  int y_bf16;              // 0: float32 output, 1: bfloat16 (round to nearest even)
 };
+
+// Output element store: float32 or bfloat16, any frame / row pitch (N1: writes the mel channels
+// straight into a wider encoder-input buffer).
+__device__ __forceinline__ void store_out(const KParams& p, long long idx, float v) {
+  if (p.y_bf16) reinterpret_cast<__nv_bfloat16*>(p.y)[idx] = __float2bfloat16_rn(v);
+  else p.y[idx] = v;
+}
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -366,7 +377,7 @@ __global__ void __launch_bounds__(kThreads, 1) bhmel_logmel_kernel(const __grid_
     const int t0 = static_cast<int>(tile - r * p.tiles_per_row) * kTileF;
     const long long frames_left = p.T - t0;
     const int nf = frames_left < kTileF ? static_cast<int>(frames_left) : kTileF;
-    float* ybase = p.y + (r * p.T + t0) * static_cast<long long>(p.n_mels);
+    const long long ybase = r * p.y_row_pitch + static_cast<long long>(t0) * p.y_frame_pitch;
     const float4* prow = reinterpret_cast<const float4*>(S.P + lane * kPPitch);
     for (int mc = 0, c = 0; mc < p.n_mels; mc += kMChunk, ++c) {
       const int mcount = (p.n_mels - mc) < kMChunk ? (p.n_mels - mc) : kMChunk;
@@ -387,11 +398,11 @@ __global__ void __launch_bounds__(kThreads, 1) bhmel_logmel_kernel(const __grid_
 #pragma unroll
         for (int a = 0; a < kFr; ++a) {
           const int f = warp + a * kWarps;
-          float* yrow = ybase + static_cast<long long>(f) * p.n_mels + mc;
+          const long long yrow = ybase + static_cast<long long>(f) * p.y_frame_pitch + mc;
 #pragma unroll
           for (int b = 0; b < kCo; ++b) {
             const int c2 = lane + 32 * b;
-            if (f < nf && c2 < mcount) yrow[c2] = vals[a][b];
+            if (f < nf && c2 < mcount) store_out(p, yrow + c2, vals[a][b]);
           }
         }
       }

@@ -96,7 +96,7 @@ __device__ __forceinline__ bool issue_warp_span(const KParams& p, long long tile
 
 template <bool kLog, bool kSmemW>
 __device__ __forceinline__ void mel_rounds(const float* __restrict__ prows, const SmemIW& S, const IwParams& q,
-                                           float* __restrict__ yrow, bool frame_ok, int lane) {
+                                           long long yrow, bool frame_ok, int lane) {
   const int li = lane & 15;
   const float4* prow = reinterpret_cast<const float4*>(prows + (lane >> 4) * kPPitch);
   const float4* wt = kSmemW ? S.wt : q.wt;
@@ -118,7 +118,7 @@ __device__ __forceinline__ void mel_rounds(const float* __restrict__ prows, cons
     float v = (a0 + a1) + (a2 + a3);
     if constexpr (kLog) v = fast_log1p(v);
     const int m = r * 16 + li;
-    if (frame_ok && m < q.k.n_mels) yrow[m] = v;
+    if (frame_ok && m < q.k.n_mels) store_out(q.k, yrow + m, v);
   }
 }
 
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kIwThreads, 1) bhmel_logmel_iw_kernel(const __
     const float* span = S.span[warp][b];
     const long long r = tile / p.tiles_per_row;
     const int t0 = static_cast<int>(tile - r * p.tiles_per_row) * kWTileF;
-    float* ytile = p.y + (r * p.T + t0) * static_cast<long long>(p.n_mels);
+    const long long ytile = r * p.y_row_pitch + static_cast<long long>(t0) * p.y_frame_pitch;
 
 #pragma unroll 1
     for (int j = 0; j < kWPairs; ++j) {
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(kIwThreads, 1) bhmel_logmel_iw_kernel(const __
       }
       __syncwarp();
       const int tf = t0 + 2 * j + (lane >> 4);            // this lane's frame
-      float* yrow = ytile + static_cast<long long>(2 * j + (lane >> 4)) * p.n_mels;
+      const long long yrow = ytile + static_cast<long long>(2 * j + (lane >> 4)) * p.y_frame_pitch;
       if (wt_in_smem) mel_rounds<kLog, true>(prows, S, q, yrow, tf < p.T, lane);
       else mel_rounds<kLog, false>(prows, S, q, yrow, tf < p.T, lane);
     }

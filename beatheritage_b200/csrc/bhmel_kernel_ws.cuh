@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
       const int t0 = static_cast<int>(tile - r * p.tiles_per_row) * kTileF;
       const long long frames_left = p.T - t0;
       const int nf = frames_left < kTileF ? static_cast<int>(frames_left) : kTileF;
-      float* ybase = p.y + (r * p.T + t0) * static_cast<long long>(p.n_mels);
+      const long long ybase = r * p.y_row_pitch + static_cast<long long>(t0) * p.y_frame_pitch;
       const float4* prow = reinterpret_cast<const float4*>(S.P[b] + lane * kPPitchW);
       float* orow = S.out + lane * kOutPitch;
       for (int mc = 0, c = 0; mc < p.n_mels; mc += kMChunk, ++c) {
@@ -236,11 +236,11 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
 #pragma unroll
           for (int a = 0; a < kFr; ++a) {
             const int fr = mw + a * kMelWarps;
-            float* yrow = ybase + static_cast<long long>(fr) * p.n_mels + mc;
+            const long long yrow = ybase + static_cast<long long>(fr) * p.y_frame_pitch + mc;
 #pragma unroll
             for (int bb = 0; bb < kCo; ++bb) {
               const int c2 = lane + 32 * bb;
-              if (fr < nf && c2 < mcount) yrow[c2] = vals[a][bb];
+              if (fr < nf && c2 < mcount) store_out(p, yrow + c2, vals[a][bb]);
             }
           }
         }

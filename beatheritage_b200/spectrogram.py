@@ -270,6 +270,37 @@ class MelSpectrogram(nn.Module):
         return _mel_forward_op(samples, self._key, self.n_mels)
 
     @torch.no_grad()
+    def forward_into(self, samples: torch.Tensor, out: torch.Tensor, channel_offset: int = 0) -> torch.Tensor:
+        """Write the mel frames of `samples` [B, N] into `out[:, :, channel_offset:channel_offset+n_mels]`
+        where `out` is a float32 or bfloat16 CUDA tensor [B, N // hop + 1, C >= n_mels] whose last dim
+        is contiguous.  This is the reference's `frames.to(dtype)` + `torch.cat([frames, cond...])`
+        (modeling_mapperatorinator.py:352, 369-370) without the extra passes: allocate the encoder
+        input once, let the frontend fill the mel channels, fill the conditioning channels yourself."""
+        self._check_input(samples)
+        if not (samples.is_cuda and out.is_cuda and out.device == samples.device):
+            raise RuntimeError("forward_into expects CUDA tensors on the same device")
+        B, N = samples.shape
+        T = N // self.hop_length + 1
+        if out.dim() != 3 or out.shape[0] != B or out.shape[1] != T or out.stride(2) != 1:
+            raise RuntimeError(f"out must be [B={B}, T={T}, C] with a contiguous last dim, got {tuple(out.shape)}")
+        if not (0 <= channel_offset and channel_offset + self.n_mels <= out.shape[2]):
+            raise RuntimeError("channel_offset + n_mels exceeds out's channel count")
+        if out.dtype not in (torch.float32, torch.bfloat16):
+            raise RuntimeError("out must be float32 or bfloat16")
+        x = samples if samples.dtype == torch.float32 else samples.to(torch.float32)
+        if x.stride(1) != 1 or (B > 1 and x.stride(0) < N):
+            x = x.contiguous()
+        h = self._handle_for(x.device)
+        desc = _lib.BhmelOutDesc(out.data_ptr() + channel_offset * out.element_size(),
+                                 _lib.OUT_BF16 if out.dtype == torch.bfloat16 else _lib.OUT_F32,
+                                 out.stride(1), out.stride(0) if B > 1 else T * out.stride(1))
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            _lib.check(_lib.lib().bhmel_forward_ex(h, x.data_ptr(), B, N, x.stride(0) if B > 1 else N,
+                                                   ctypes.byref(desc), stream))
+        return out
+
+    @torch.no_grad()
     def forward_host(self, samples: torch.Tensor, out: torch.Tensor | None = None,
                      device: int | None = None) -> torch.Tensor:
         """End-to-end call for HOST batches (reference osuT5/dataloading.py:128-130 calls the module

@@ -34,6 +34,7 @@ extern "C" {
 /* Output element type of the forward calls (the reference always returns float32,
  * ref: osuT5/osuT5/model/spectrogram.py:79-83). */
 #define BHMEL_OUT_F32 0
+#define BHMEL_OUT_BF16 1
 
 typedef struct bhmel_handle bhmel_handle;
 
@@ -84,6 +85,24 @@ int64_t bhmel_num_frames(const bhmel_handle* h, int64_t n_samples);
  * from F.pad), or B/N <= 0. */
 int bhmel_forward(bhmel_handle* h, const float* x, int64_t B, int64_t N, int64_t x_row_stride,
                   float* y, void* stream);
+
+/* Output descriptor for bhmel_forward_ex: element (row r, frame t, mel m) is written at
+ * y[r * row_pitch + t * frame_pitch + m] (pitches in ELEMENTS of dtype; 0 selects the dense
+ * [B][T][n_mels] layout).  With frame_pitch > n_mels the mel channels land inside a wider
+ * per-frame record, e.g. the encoder input [B][T][n_mels + cond] the reference builds with
+ * `.to(dtype)` + `torch.cat` (ref: osuT5/osuT5/model/modeling_mapperatorinator.py:352, 369-370). */
+typedef struct bhmel_out_desc {
+  void* y;               /* DEVICE pointer to element (0, 0, 0) */
+  int32_t dtype;         /* BHMEL_OUT_F32 or BHMEL_OUT_BF16 (round to nearest even, == tensor.to(bfloat16)) */
+  int64_t frame_pitch;   /* >= n_mels, or 0 */
+  int64_t row_pitch;     /* >= T * frame_pitch, or 0 */
+} bhmel_out_desc;
+
+/* bhmel_forward with a typed / pitched output (next-row N1 of SURVEY.md 8f: removes the caller's
+ * dtype cast and concat passes over the encoder input).  Same arithmetic; the fp32 result is
+ * converted once at the store. */
+int bhmel_forward_ex(bhmel_handle* h, const float* x, int64_t B, int64_t N, int64_t x_row_stride,
+                     const bhmel_out_desc* out, void* stream);
 
 /* Fused segmentation + forward.  Replaces Preprocessor.segment/window followed by forward
  * (ref: osuT5/osuT5/inference/preprocessor.py:58-71, 94-102): window w (0 <= w < W) covers

@@ -229,6 +229,33 @@ def test_properties_at_full_size(mods, dev):
     assert parity_error(y[idx].cpu().numpy(), ref, True) < TARGET
 
 
+@pytest.mark.parametrize("variant", ["ws", "barrier", "warp"])
+def test_forward_into_typed_pitched_output(mods, dev, variant):
+    """N1: bf16 / wider-record output equals forward() followed by .to(dtype) + cat, bit for bit."""
+    m = mods["P0"]
+    m.set_kernel_variant(variant)
+    x = torch.from_numpy(signals.noise(3, 20000, 12)).to(dev)
+    y = m(x)                                                   # [3, 157, 80] f32
+    T = y.shape[1]
+    cond = torch.randn(3, T, 384, device=dev)
+    # encoder input [B, T, 464] in bf16, mel channels first (modeling_mapperatorinator.py:352, 369-370)
+    ref = torch.cat([y.to(torch.bfloat16), cond.to(torch.bfloat16)], dim=-1)
+    buf = torch.empty(3, T, 464, device=dev, dtype=torch.bfloat16)
+    buf[:, :, 80:] = cond.to(torch.bfloat16)
+    m.forward_into(x, buf, channel_offset=0)
+    assert torch.equal(buf, ref)
+    # float32, mel channels in the middle of the record
+    buf32 = torch.zeros(3, T, 100, device=dev)
+    m.forward_into(x, buf32, channel_offset=7)
+    assert torch.equal(buf32[:, :, 7:87], y) and torch.all(buf32[:, :, :7] == 0) and torch.all(buf32[:, :, 87:] == 0)
+    # dense bf16 == .to(bfloat16)
+    dense = torch.empty(3, T, 80, device=dev, dtype=torch.bfloat16)
+    assert torch.equal(m.forward_into(x, dense), y.to(torch.bfloat16))
+    m.set_kernel_variant(DEFAULT_VARIANT)
+    with pytest.raises(RuntimeError):
+        m.forward_into(x, torch.empty(3, T, 60, device=dev))
+
+
 def test_state_dict_reload_rebuilds_device_tables(dev):
     from beatheritage_b200 import MelSpectrogram
     m = MelSpectrogram("torchaudio", False, 16000, 1024, 80, 128, 20, 8000, "reflect").to(dev)
