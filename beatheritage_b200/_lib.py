@@ -39,6 +39,12 @@ class BhmelOutDesc(ctypes.Structure):
 
 
 OUT_F32, OUT_BF16 = 0, 1
+IN_F32, IN_PCM16 = 0, 1
+
+
+class BhmelHostIO(ctypes.Structure):
+    _fields_ = [("x_host", ctypes.c_void_p), ("x_dtype", ctypes.c_int32), ("scales", ctypes.c_void_p),
+                ("y_host", ctypes.c_void_p), ("y_dtype", ctypes.c_int32)]
 
 
 class BhmelError(RuntimeError):
@@ -66,6 +72,7 @@ SIGNATURES = {
     "bhmel_forward_ex": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, ctypes.POINTER(BhmelOutDesc), _vp]),
     "bhmel_forward_gather": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
     "bhmel_forward_host": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _vp]),
+    "bhmel_forward_host_ex": (ctypes.c_int, [_vp, ctypes.POINTER(BhmelHostIO), _i64, _i64, _i64]),
     "bhmel_set_option": (ctypes.c_int, [_vp, _i32, _i64]),
     "bhmel_version": (ctypes.c_int, []),
     "bhmel_last_error": (ctypes.c_char_p, []),

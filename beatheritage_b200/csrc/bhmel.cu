@@ -35,6 +35,17 @@ constexpr int kHostSlots = 3;
 
 }  // namespace
 
+// int16 PCM -> float32 with a per-row multiplier: float32(pcm) * scale, one rounding, exactly what
+// numpy does for `samples.astype(np.float32) * np.float32(scale)` (ref: data_utils.py:95-97).
+__global__ void bhmel_pcm16_to_f32_kernel(const int16_t* __restrict__ in, float* __restrict__ out,
+                                          const float* __restrict__ scales, long long n_per_row, long long total) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / n_per_row;
+    out[i] = static_cast<float>(in[i]) * (scales ? scales[r] : 1.0f);
+  }
+}
+
 struct bhmel_handle {
   int device = 0;
   int num_sms = 0;
@@ -60,7 +71,9 @@ struct bhmel_handle {
   cudaStream_t hs[kHostSlots] = {nullptr, nullptr, nullptr};
   float* d_in[kHostSlots] = {nullptr, nullptr, nullptr};
   float* d_out[kHostSlots] = {nullptr, nullptr, nullptr};
-  size_t cap_in = 0, cap_out = 0;
+  int16_t* d_pcm[kHostSlots] = {nullptr, nullptr, nullptr};
+  float* d_scales = nullptr;
+  size_t cap_in = 0, cap_out = 0, cap_pcm = 0, cap_scales = 0;
 };
 
 namespace {
@@ -291,7 +304,9 @@ void bhmel_destroy(bhmel_handle* h) {
     }
     if (h->d_in[i]) cudaFree(h->d_in[i]);
     if (h->d_out[i]) cudaFree(h->d_out[i]);
+    if (h->d_pcm[i]) cudaFree(h->d_pcm[i]);
   }
+  if (h->d_scales) cudaFree(h->d_scales);
   if (h->d_win) cudaFree(h->d_win);
   if (h->d_tw) cudaFree(h->d_tw);
   if (h->d_pairs) cudaFree(h->d_pairs);
@@ -377,55 +392,102 @@ int bhmel_forward_gather(bhmel_handle* h, const float* song, int64_t n_song, int
                 static_cast<cudaStream_t>(stream));
 }
 
-int bhmel_forward_host(bhmel_handle* h, const float* x_host, int64_t B, int64_t N, int64_t x_row_stride,
-                       float* y_host) {
+int bhmel_forward_host_ex(bhmel_handle* h, const bhmel_host_io* io, int64_t B, int64_t N, int64_t x_row_stride) {
   if (!h) return fail(BHMEL_EINVAL, "null handle");
-  if (!x_host || !y_host) return fail(BHMEL_EINVAL, "null data pointer");
+  if (!io || !io->x_host || !io->y_host) return fail(BHMEL_EINVAL, "null data pointer");
   if (B <= 0 || N <= 0) return fail(BHMEL_ESHAPE, "batch and sample count must be positive");
   if (x_row_stride < N) return fail(BHMEL_EINVAL, "x_row_stride must be >= N");
+  if (io->x_dtype != BHMEL_IN_F32 && io->x_dtype != BHMEL_IN_PCM16) return fail(BHMEL_EINVAL, "unknown input dtype");
+  if (io->y_dtype != BHMEL_OUT_F32 && io->y_dtype != BHMEL_OUT_BF16) return fail(BHMEL_EINVAL, "unknown output dtype");
   if (int rc = check_device(h)) return rc;
   std::lock_guard<std::mutex> lock(h->host_mu);
 
+  const bool pcm = io->x_dtype == BHMEL_IN_PCM16;
+  const bool bf16 = io->y_dtype == BHMEL_OUT_BF16;
   const int64_t T = N / bhmel::kHop + 1;
-  const size_t row_in = static_cast<size_t>(N) * sizeof(float);
-  const size_t row_out = static_cast<size_t>(T) * h->prm.n_mels * sizeof(float);
-  // ~32 MB of input per chunk keeps three chunks in flight (H2D / kernel / D2H) with small tails.
-  int64_t rows = static_cast<int64_t>((32u << 20) / row_in);
+  const size_t row_f32 = static_cast<size_t>(N) * sizeof(float);
+  const size_t row_src = static_cast<size_t>(N) * (pcm ? sizeof(int16_t) : sizeof(float));
+  const size_t row_out = static_cast<size_t>(T) * h->prm.n_mels * (bf16 ? 2 : 4);
+  // ~32 MB of fp32 input per chunk keeps three chunks in flight (H2D / kernel / D2H) with small tails.
+  int64_t rows = static_cast<int64_t>((32u << 20) / row_f32);
   if (rows < 1) rows = 1;
   if (rows > B) rows = B;
   if (rows * 2 > B && B >= 2 * kHostSlots) rows = (B + 2 * kHostSlots - 1) / (2 * kHostSlots);
-  const size_t need_in = static_cast<size_t>(rows) * row_in, need_out = static_cast<size_t>(rows) * row_out;
-  for (int i = 0; i < kHostSlots; ++i) {
+  const size_t need_in = static_cast<size_t>(rows) * row_f32;
+  const size_t need_out = static_cast<size_t>(rows) * static_cast<size_t>(T) * h->prm.n_mels * 4;
+  const size_t need_pcm = pcm ? static_cast<size_t>(rows) * N * sizeof(int16_t) : 0;
+  for (int i = 0; i < kHostSlots; ++i)
     if (!h->hs[i]) BH_CUDA(cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking));
-  }
-  if (need_in > h->cap_in || need_out > h->cap_out) {
+  if (need_in > h->cap_in || need_out > h->cap_out || need_pcm > h->cap_pcm) {
     for (int i = 0; i < kHostSlots; ++i) {
       BH_CUDA(cudaStreamSynchronize(h->hs[i]));
       if (h->d_in[i]) cudaFree(h->d_in[i]);
       if (h->d_out[i]) cudaFree(h->d_out[i]);
+      if (h->d_pcm[i]) cudaFree(h->d_pcm[i]);
       h->d_in[i] = h->d_out[i] = nullptr;
+      h->d_pcm[i] = nullptr;
     }
-    h->cap_in = h->cap_out = 0;
+    h->cap_in = h->cap_out = h->cap_pcm = 0;
+    const size_t ci = need_in, co = need_out, cp = need_pcm;
     for (int i = 0; i < kHostSlots; ++i) {
-      BH_CUDA(cudaMalloc(&h->d_in[i], need_in));
-      BH_CUDA(cudaMalloc(&h->d_out[i], need_out));
+      BH_CUDA(cudaMalloc(&h->d_in[i], ci));
+      BH_CUDA(cudaMalloc(&h->d_out[i], co));
+      if (cp) BH_CUDA(cudaMalloc(&h->d_pcm[i], cp));
     }
-    h->cap_in = need_in;
-    h->cap_out = need_out;
+    h->cap_in = ci;
+    h->cap_out = co;
+    h->cap_pcm = cp;
+  }
+  const float* d_scales = nullptr;
+  if (pcm && io->scales) {
+    if (static_cast<size_t>(B) * sizeof(float) > h->cap_scales) {
+      if (h->d_scales) cudaFree(h->d_scales);
+      h->d_scales = nullptr;
+      h->cap_scales = 0;
+      BH_CUDA(cudaMalloc(&h->d_scales, static_cast<size_t>(B) * sizeof(float)));
+      h->cap_scales = static_cast<size_t>(B) * sizeof(float);
+    }
+    for (int i = 0; i < kHostSlots; ++i) BH_CUDA(cudaStreamSynchronize(h->hs[i]));
+    BH_CUDA(cudaMemcpy(h->d_scales, io->scales, static_cast<size_t>(B) * sizeof(float), cudaMemcpyHostToDevice));
+    d_scales = h->d_scales;
   }
   int slot = 0;
   for (int64_t b0 = 0; b0 < B; b0 += rows, slot = (slot + 1) % kHostSlots) {
     const int64_t nb = (B - b0) < rows ? (B - b0) : rows;
     cudaStream_t s = h->hs[slot];
-    BH_CUDA(cudaMemcpy2DAsync(h->d_in[slot], row_in, x_host + b0 * x_row_stride,
-                              static_cast<size_t>(x_row_stride) * sizeof(float), row_in,
-                              static_cast<size_t>(nb), cudaMemcpyHostToDevice, s));
-    if (int rc = launch(h, h->d_in[slot], N, 0, LLONG_MAX, nb, N, OutSpec{h->d_out[slot], 0, 0, 0}, s)) return rc;
-    BH_CUDA(cudaMemcpyAsync(y_host + static_cast<size_t>(b0) * T * h->prm.n_mels, h->d_out[slot],
+    if (pcm) {
+      const int16_t* src = static_cast<const int16_t*>(io->x_host) + b0 * x_row_stride;
+      BH_CUDA(cudaMemcpy2DAsync(h->d_pcm[slot], row_src, src, static_cast<size_t>(x_row_stride) * sizeof(int16_t),
+                                row_src, static_cast<size_t>(nb), cudaMemcpyHostToDevice, s));
+      const long long total = static_cast<long long>(nb) * N;
+      const unsigned blocks = static_cast<unsigned>(h->num_sms * 8);
+      bhmel_pcm16_to_f32_kernel<<<blocks, 256, 0, s>>>(h->d_pcm[slot], h->d_in[slot],
+                                                       d_scales ? d_scales + b0 : nullptr, N, total);
+      BH_CUDA(cudaGetLastError());
+      h->launches.fetch_add(1, std::memory_order_relaxed);
+    } else {
+      const float* src = static_cast<const float*>(io->x_host) + b0 * x_row_stride;
+      BH_CUDA(cudaMemcpy2DAsync(h->d_in[slot], row_f32, src, static_cast<size_t>(x_row_stride) * sizeof(float),
+                                row_f32, static_cast<size_t>(nb), cudaMemcpyHostToDevice, s));
+    }
+    if (int rc = launch(h, h->d_in[slot], N, 0, LLONG_MAX, nb, N, OutSpec{h->d_out[slot], bf16 ? 1 : 0, 0, 0}, s))
+      return rc;
+    BH_CUDA(cudaMemcpyAsync(static_cast<char*>(io->y_host) + static_cast<size_t>(b0) * row_out, h->d_out[slot],
                             static_cast<size_t>(nb) * row_out, cudaMemcpyDeviceToHost, s));
   }
   for (int i = 0; i < kHostSlots; ++i) BH_CUDA(cudaStreamSynchronize(h->hs[i]));
   return BHMEL_OK;
+}
+
+int bhmel_forward_host(bhmel_handle* h, const float* x_host, int64_t B, int64_t N, int64_t x_row_stride,
+                       float* y_host) {
+  bhmel_host_io io{};
+  io.x_host = x_host;
+  io.x_dtype = BHMEL_IN_F32;
+  io.scales = nullptr;
+  io.y_host = y_host;
+  io.y_dtype = BHMEL_OUT_F32;
+  return bhmel_forward_host_ex(h, &io, B, N, x_row_stride);
 }
 
 }  // extern "C"

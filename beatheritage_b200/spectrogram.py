@@ -301,27 +301,43 @@ class MelSpectrogram(nn.Module):
         return out
 
     @torch.no_grad()
-    def forward_host(self, samples: torch.Tensor, out: torch.Tensor | None = None,
-                     device: int | None = None) -> torch.Tensor:
+    def forward_host(self, samples: torch.Tensor, out: torch.Tensor | None = None, device: int | None = None,
+                     scales: torch.Tensor | None = None, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
         """End-to-end call for HOST batches (reference osuT5/dataloading.py:128-130 calls the module
         with CPU tensors): chunked H2D copy, kernel and D2H copy overlapped inside the library.
-        `samples` float32 CPU [B, N] (pinned memory recommended); returns a CPU tensor."""
+
+        samples  CPU [B, N], float32 -- or int16 PCM, converted on the device as
+                 float32(pcm) * scales[b] (the reference's cast + peak normalisation,
+                 osuT5/osuT5/dataset/data_utils.py:95-97), so only 2 bytes/sample cross PCIe;
+        scales   CPU float32 [B] for int16 input (None: 1.0);
+        out      optional CPU result buffer [B, T, n_mels], float32 or bfloat16 (pinned recommended).
+        Returns the CPU tensor."""
         self._check_input(samples)
         if samples.is_cuda:
             raise RuntimeError("forward_host expects a CPU tensor")
-        x = samples if samples.dtype == torch.float32 else samples.to(torch.float32)
+        pcm = samples.dtype == torch.int16
+        x = samples if (pcm or samples.dtype == torch.float32) else samples.to(torch.float32)
         if x.stride(1) != 1:
             x = x.contiguous()
         B, N = x.shape
         T = N // self.hop_length + 1
         if out is None:
-            out = torch.empty((B, T, self.n_mels), dtype=torch.float32, pin_memory=True)
-        assert out.is_contiguous() and tuple(out.shape) == (B, T, self.n_mels) and out.dtype == torch.float32
+            out = torch.empty((B, T, self.n_mels), dtype=out_dtype, pin_memory=True)
+        if not (out.is_contiguous() and tuple(out.shape) == (B, T, self.n_mels)
+                and out.dtype in (torch.float32, torch.bfloat16) and not out.is_cuda):
+            raise RuntimeError("out must be a contiguous CPU float32/bfloat16 tensor [B, T, n_mels]")
+        sc_ptr = None
+        if pcm and scales is not None:
+            scales = scales.to(torch.float32).contiguous()
+            if scales.numel() != B or scales.is_cuda:
+                raise RuntimeError("scales must be a CPU tensor with one entry per row")
+            sc_ptr = scales.data_ptr()
         idx = torch.cuda.current_device() if device is None else device
         h = self._handle_for(torch.device("cuda", idx))
+        io = _lib.BhmelHostIO(x.data_ptr(), _lib.IN_PCM16 if pcm else _lib.IN_F32, sc_ptr, out.data_ptr(),
+                              _lib.OUT_BF16 if out.dtype == torch.bfloat16 else _lib.OUT_F32)
         with torch.cuda.device(idx):
-            _lib.check(_lib.lib().bhmel_forward_host(h, x.data_ptr(), B, N, x.stride(0) if B > 1 else N,
-                                                     out.data_ptr()))
+            _lib.check(_lib.lib().bhmel_forward_host_ex(h, ctypes.byref(io), B, N, x.stride(0) if B > 1 else N))
         return out
 
     @torch.no_grad()

@@ -137,6 +137,26 @@ int bhmel_forward_host(bhmel_handle* h, const float* x_host, int64_t B, int64_t 
 #define BHMEL_KERNEL_WARP_SPECIALIZED 2
 int bhmel_set_option(bhmel_handle* h, int32_t option, int64_t value);
 
+/* Host-buffer entry with typed input / output (next rows N1 + N2 of SURVEY.md 8f).
+ *   x_dtype BHMEL_IN_F32   : x_host is float32 [B][x_row_stride], exactly bhmel_forward_host.
+ *   x_dtype BHMEL_IN_PCM16 : x_host is int16 PCM [B][x_row_stride]; row r is converted on the device as
+ *                            float32(pcm) * scales[r] -- the reference's int16 -> float32 cast and
+ *                            peak normalisation `samples *= 1.0 / max(abs(samples))`
+ *                            (ref: osuT5/osuT5/dataset/data_utils.py:95-97) -- so only 2 bytes per sample
+ *                            cross PCIe.  scales: HOST float32 [B], or NULL for 1.0.
+ *   y_dtype BHMEL_OUT_F32 / BHMEL_OUT_BF16 : y_host is [B][N/hop+1][n_mels] of that type.
+ * Synchronous; chunks are pipelined over private streams like bhmel_forward_host. */
+#define BHMEL_IN_F32 0
+#define BHMEL_IN_PCM16 1
+typedef struct bhmel_host_io {
+  const void* x_host;
+  int32_t x_dtype;
+  const float* scales;
+  void* y_host;
+  int32_t y_dtype;
+} bhmel_host_io;
+int bhmel_forward_host_ex(bhmel_handle* h, const bhmel_host_io* io, int64_t B, int64_t N, int64_t x_row_stride);
+
 /* Introspection used by tests and bench.py. */
 int bhmel_version(void);
 const char* bhmel_last_error(void);

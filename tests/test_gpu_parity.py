@@ -197,6 +197,28 @@ def test_forward_host_matches_forward(mods, dev):
     assert torch.equal(y_pageable, y_dev)
 
 
+def test_forward_host_pcm16_and_bf16(mods, dev):
+    """N2 + N1 on the host entry: int16 PCM rows scaled on the device (the reference's
+    astype(float32) * 1/peak, data_utils.py:95-97) and a bfloat16 result."""
+    m = mods["P0"]
+    rng = np.random.default_rng(5)
+    pcm = rng.integers(-20000, 20000, size=(9, 70000), dtype=np.int16)
+    pcm[3] = 0                                                      # a silent row
+    peak = np.abs(pcm.astype(np.float32)).max(axis=1)
+    scales = np.where(peak > 0, np.float32(1.0) / np.maximum(peak, 1), np.float32(0)).astype(np.float32)
+    x_ref = pcm.astype(np.float32) * scales[:, None]                # what load_audio_file produces
+    y_ref = m(torch.from_numpy(x_ref).to(dev)).cpu()
+    y = m.forward_host(torch.from_numpy(pcm), scales=torch.from_numpy(scales))
+    assert torch.equal(y, y_ref)
+    y16 = m.forward_host(torch.from_numpy(pcm).pin_memory(), scales=torch.from_numpy(scales), out_dtype=torch.bfloat16)
+    assert y16.dtype == torch.bfloat16 and torch.equal(y16, y_ref.to(torch.bfloat16))
+    yf16 = m.forward_host(torch.from_numpy(x_ref), out_dtype=torch.bfloat16)
+    assert torch.equal(yf16, y_ref.to(torch.bfloat16))
+    window, fb = load_params("P0")
+    ref = mel_oracle.mel_forward(x_ref[:2], fb=fb, window=window, dtype=np.float64)
+    assert parity_error(y[:2].numpy(), ref, True) < TARGET
+
+
 def test_properties_at_full_size(mods, dev):
     """Size-independent properties on a [64, 524160] batch (no oracle needed at this size):
     batch independence, determinism, power scaling (non-log set), zero rows, time shift."""
