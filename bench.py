@@ -249,6 +249,9 @@ def run_ours(args):
     barrier()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    for ev in [start, stop] + marks:     # events are created lazily at first record(): do that now,
+        ev.record()                      # not inside the timed region
+    torch.cuda.synchronize(dev)
     clocks = ClockSampler(local_rank)
     barrier()
     # untimed runway: a few steps queued ahead of the start event (no synchronisation in between) so
