@@ -9,7 +9,7 @@ import os
 import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libbhmel.so")
+LIB_PATH = os.environ.get("BHMEL_LIB") or os.path.join(_PKG, "libbhmel.so")   # BHMEL_LIB: A/B builds
 
 PAD_CONSTANT, PAD_REFLECT = 0, 1
 OPT_BULK_COPY = 1

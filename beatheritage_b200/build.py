@@ -14,6 +14,7 @@ LIB = os.path.join(PKG, "libbhmel.so")
 GEN = os.path.join(CSRC, "fft32_gen.h")
 
 NVCC_FLAGS = [
+    *os.environ.get("BHMEL_EXTRA_NVCC", "").split(),
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v",
 ]

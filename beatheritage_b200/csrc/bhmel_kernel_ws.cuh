@@ -135,6 +135,9 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
       const uint32_t ph = (it >> 1) & 1;
       mbar_wait(&S.span_full[b], ph);
       mbar_wait(&S.p_empty[b], ph ^ 1);   // the mel role has released this P buffer (tile it-2)
+#ifdef BHMEL_DEBUG_SKIP_FFT
+      if (tile < 0)
+#endif
 #pragma unroll 1
       for (int j = warp; j < kPairs; j += kFftWarps) {
         float* rows = S.P[b] + (2 * j) * kPPitchW;      // this pair's two P rows; scratch until written
@@ -216,6 +219,11 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
       const long long ybase = r * p.y_row_pitch + static_cast<long long>(t0) * p.y_frame_pitch;
       const float4* prow = reinterpret_cast<const float4*>(S.P[b] + lane * kPPitchW);
       float* orow = S.out + lane * kOutPitch;
+#ifdef BHMEL_DEBUG_SKIP_MEL
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.p_empty[b]);
+      if (tile < 0)
+#endif
       for (int mc = 0, c = 0; mc < p.n_mels; mc += kMChunk, ++c) {
         const int mcount = (p.n_mels - mc) < kMChunk ? (p.n_mels - mc) : kMChunk;
         const int4* pd = S.pairs + c * (kMChunk / 2);

@@ -320,6 +320,61 @@ def test_runs_on_a_side_stream_and_under_autocast(mods, dev):
     assert torch.equal(m(x.double()), ref)         # non-fp32 input is converted
 
 
+def test_concurrent_threads_and_streams(mods, dev):
+    """The library is re-entrant: two host threads, each on its own stream and with its own module
+    (different filterbanks), interleave launches and get the same results as when run alone
+    (the reference calls the model from a non-main batch thread, inference/server.py:176)."""
+    import threading
+    from beatheritage_b200 import MelSpectrogram
+    m_a = mods["P0"]
+    m_b = MelSpectrogram("torchaudio", False, 16000, 1024, 128, 128, 0, 8000, "constant").to(dev)
+    xa = torch.from_numpy(signals.noise(4, 50000, 1)).to(dev)
+    xb = torch.from_numpy(signals.noise(5, 30001, 2)).to(dev)
+    ref_a, ref_b = m_a(xa).clone(), m_b(xb).clone()
+    torch.cuda.synchronize()
+    errors = []
+
+    def worker(m, x, ref):
+        try:
+            s = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(s):
+                for _ in range(30):
+                    y = m(x)
+                    if not torch.equal(y, ref):
+                        errors.append("mismatch")
+            s.synchronize()
+        except Exception as e:   # pragma: no cover
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=a) for a in ((m_a, xa, ref_a), (m_b, xb, ref_b))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert errors == []
+
+
+def test_many_windows_and_many_mels(dev):
+    """Upper ends of the shape space: 1 090 windows of a short context in one launch, and a
+    1 024-filter bank (the maximum the tables support; served by the barrier kernel when the
+    warp-specialised kernel's descriptor table is too small is NOT needed -- all variants take it)."""
+    from beatheritage_b200 import MelSpectrogram
+    m = MelSpectrogram("torchaudio", True, 16000, 1024, 1024, 128, 0, 8000, "reflect").to(dev)
+    x = signals.noise(2, 6000, 3)
+    ys = {}
+    for variant in ("ws", "barrier", "warp"):
+        m.set_kernel_variant(variant)
+        ys[variant] = run(m, x, dev)
+    assert np.array_equal(ys["ws"], ys["barrier"]) and np.array_equal(ys["warp"], ys["barrier"])
+    ref = mel_oracle.mel_forward(x, fb=m.transform.mel_scale.fb.cpu().numpy(),
+                                 window=m.transform.spectrogram.window.cpu().numpy(), dtype=np.float64)
+    assert parity_error(ys["ws"], ref, True) < TARGET
+    m0 = MelSpectrogram("torchaudio", True, 16000, 1024, 80, 128, 20, 8000, "reflect").to(dev)
+    xw = torch.from_numpy(signals.noise(1090, 8192, 4)).to(dev)
+    y = m0(xw)
+    assert torch.equal(y[777:778], m0(xw[777:778].clone()))
+
+
 def test_c_abi_errors_on_device(dev):
     from beatheritage_b200 import _lib
     lib = _lib.lib()
