@@ -6,8 +6,8 @@
 // hand 32-frame tiles to each other through mbarriers, so the latency-bound mel / store stage
 // fills the issue slots the FFT warps leave idle instead of alternating with them.
 //
-//   warps 0-7   (2 warpgroups, setmaxnreg -> 192)  FFT role: two frame pairs per warp per tile
-//   warps 8-15  (2 warpgroups, setmaxnreg ->  64)  producer + mel + store role
+//   warps 0-7   (2 warpgroups, setmaxnreg -> 184)  FFT role: two frame pairs per warp per tile
+//   warps 8-15  (2 warpgroups, setmaxnreg ->  72)  producer + mel + store role
 //
 //   span[2]   4992-sample spans filled by the producer role one tile ahead of the FFT warps
 //             (TMA bulk copy, or per-element cp.async with the reflect / zero mapping) -> span_full[2]
@@ -33,20 +33,24 @@ constexpr int kPlanePitch = 33;                        // floats per row of a tr
 // setmaxnreg budget: the CTA is launched with 128 registers/thread (65536 / 512); registers only
 // move between the warpgroups of the CTA, so 2 * kFftRegs + 2 * kMelRegs must not exceed 4 * 128.
 constexpr int kLaunchRegs = 128;
-constexpr int kFftRegs = 192;
-constexpr int kMelRegs = 64;
+#ifndef BHMEL_FFT_REGS
+#define BHMEL_FFT_REGS 184
+#endif
+constexpr int kFftRegs = BHMEL_FFT_REGS;                   // tunable at build time (A/B experiments)
+constexpr int kMelRegs = 4 * kLaunchRegs / 2 - kFftRegs;   // 72 for 184
 static_assert(2 * kFftRegs + 2 * kMelRegs <= 4 * kLaunchRegs, "setmaxnreg pool would deadlock");
 static_assert(2 * kPPitchW * 4 >= 32 * kPlanePitch * 4, "a pair's two P rows must hold one transposed plane");
 
 struct SmemWS {
   float P[2][kTileF * kPPitchW];              // 136 192 B
-  float span[2][kSpan];                       //  39 936 B
+  float span[2][kSpan + 4];                   //  39 968 B  (+4: slack for the aligned-down TMA copy of unaligned rows)
   float out[kTileF * kOutPitch];              //  12 416 B
   float fw[kFwCap];                           //  16 384 B
   int4 pairs[kPairCap];                       //   8 192 B
   unsigned long long span_full[2];
   unsigned long long p_full[2];
   unsigned long long p_empty[2];
+  int span_delta[2];                          // element offset of the tile's first sample inside span[b]
 };
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
@@ -59,7 +63,7 @@ __device__ __forceinline__ void mel_group_sync() { asm volatile("bar.sync 1, %0;
 
 // Producer: every thread of the mel role takes part, so span_full always sees kMelThreads arrivals.
 __device__ __forceinline__ void issue_span(const KParams& p, long long tile, float* dst, unsigned long long* bar,
-                                           int mt) {
+                                           int* delta_out, int mt) {
   const long long r = tile / p.tiles_per_row;
   const int tb = static_cast<int>(tile - r * p.tiles_per_row);
   const long long s0 = static_cast<long long>(tb) * (kTileF * kHop) - kNfft / 2;
@@ -68,17 +72,29 @@ __device__ __forceinline__ void issue_span(const KParams& p, long long tile, flo
   valid = valid < 0 ? 0 : (valid > p.N ? p.N : valid);
   const float* row = p.x + row_off;
   const bool interior = s0 >= 0 && s0 + kSpan <= valid;
-  if (p.use_bulk && interior && ((reinterpret_cast<uintptr_t>(row + s0) & 15) == 0)) {
+  // TMA needs a 16-byte aligned source: copy from the address rounded DOWN to 16 bytes (delta = 0..3
+  // extra leading samples, 16 extra bytes in total) and let the FFT warps read from span + delta.
+  // This keeps windows gathered at odd strides (52 415 in the reference) on the bulk-copy path.
+  const int delta = static_cast<int>((reinterpret_cast<uintptr_t>(row + s0) >> 2) & 3);
+  const bool bulk = p.use_bulk && interior && (reinterpret_cast<uintptr_t>(p.x) & 3) == 0 &&
+                    (delta == 0 || (s0 >= delta && s0 - delta + kSpan + 4 <= valid));
+  if (bulk) {
     if (mt == 0) {
+      const uint32_t bytes = delta ? kSpanBytes + 16 : kSpanBytes;
+      *delta_out = delta;
       fence_proxy_async();
-      mbar_expect_tx(bar, kSpanBytes);
-      bulk_g2s(dst, row + s0, kSpanBytes, bar);
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(dst, row + s0 - delta, bytes, bar);
     } else {
       mbar_arrive(bar);
     }
     return;
   }
-  if (interior) {   // unaligned but fully inside the row: plain element copies
+  if (mt == 0) {
+    *delta_out = 0;
+    __threadfence_block();   // performed before this thread's (asynchronous) arrival below
+  }
+  if (interior) {   // fully inside the row but not coverable by an aligned bulk copy: element copies
     const float* src = row + s0;
     for (int e = mt; e < kSpan; e += kMelThreads) cp_async_4(dst + e, src + e, 4);
   } else {
@@ -135,6 +151,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
       const uint32_t ph = (it >> 1) & 1;
       mbar_wait(&S.span_full[b], ph);
       mbar_wait(&S.p_empty[b], ph ^ 1);   // the mel role has released this P buffer (tile it-2)
+      const float* span_b = S.span[b] + S.span_delta[b];
 #ifdef BHMEL_DEBUG_SKIP_FFT
       if (tile < 0)
 #endif
@@ -144,7 +161,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
         float ar[32], ai[32];
         {
           float v[36];
-          const float* sp = S.span[b] + (2 * j) * kHop + lane;
+          const float* sp = span_b + (2 * j) * kHop + lane;
 #pragma unroll
           for (int m = 0; m < 36; ++m) v[m] = sp[32 * m];
           fft32_pass_a(v, wreg, ar, ai);
@@ -198,9 +215,9 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
     const int mw = warp - kFftWarps;
     {
       long long t0 = blockIdx.x;
-      if (t0 < p.n_tiles) issue_span(p, t0, S.span[0], &S.span_full[0], mt);
+      if (t0 < p.n_tiles) issue_span(p, t0, S.span[0], &S.span_full[0], &S.span_delta[0], mt);
       t0 += gridDim.x;
-      if (t0 < p.n_tiles) issue_span(p, t0, S.span[1], &S.span_full[1], mt);
+      if (t0 < p.n_tiles) issue_span(p, t0, S.span[1], &S.span_full[1], &S.span_delta[1], mt);
     }
     int it = 0;
 #pragma unroll 1
@@ -210,7 +227,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
       mbar_wait(&S.p_full[b], ph);
       // every FFT warp is done with tile `it`, so span[b] is free: fetch the tile two steps ahead
       const long long tile2 = tile + 2 * static_cast<long long>(gridDim.x);
-      if (tile2 < p.n_tiles) issue_span(p, tile2, S.span[b], &S.span_full[b], mt);
+      if (tile2 < p.n_tiles) issue_span(p, tile2, S.span[b], &S.span_full[b], &S.span_delta[b], mt);
 
       const long long r = tile / p.tiles_per_row;
       const int t0 = static_cast<int>(tile - r * p.tiles_per_row) * kTileF;

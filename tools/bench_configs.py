@@ -3,7 +3,8 @@
 
     python tools/bench_configs.py [--out profiles/r1_configs.json] [--skip-c5]
 
-C1  10 s clip: latency (us) of one call, ours vs torchaudio on the same GPU vs the CPU port.
+C1  10 s clip: latency (us) of one call, ours vs torchaudio on the same GPU (the CPU figure is
+    bench.py's cpu_baseline; this script never touches oracle/).
 C2  3-min song: 6 (parallel) and 46 (sequential, stride 52 415) windows; module mode and fused gather.
 C4  1-hour audio streamed in overlapping windows: stride sweep x {materialised batch, fused gather},
     and a batch-size sweep of the module interface (achieved algorithmic GB/s vs batch).
@@ -29,8 +30,6 @@ import torch  # noqa: E402
 
 from beatheritage_b200 import MelSpectrogram  # noqa: E402
 from beatheritage_b200.segment import segment_plan  # noqa: E402
-from oracle import mel_oracle  # noqa: E402
-from oracle.torch_port import TorchPortMel  # noqa: E402
 
 WINDOW, SR, HOP, M = 524160, 16000, 128, 80
 P0 = ("torchaudio", True, SR, 1024, M, HOP, 20, 8000, "reflect")
@@ -79,8 +78,11 @@ def main():
     except Exception as e:   # torchaudio missing
         ta = None
         res["torchaudio_gpu"] = f"unavailable: {e}"
-    torch.set_num_threads(os.cpu_count() or 1)
-    port = TorchPortMel()
+
+    def materialise(song_t, plan):
+        """What Preprocessor.segment builds on the host: zero-pad to plan.padded_len, strided windows."""
+        sp = torch.nn.functional.pad(song_t, (0, plan.padded_len - song_t.numel()))
+        return sp.as_strided((plan.n_windows, plan.window_len), (plan.stride, 1)).contiguous()
 
     # ------------------------------------------------------------------ C1
     g = torch.Generator().manual_seed(0)
@@ -90,12 +92,6 @@ def main():
     if ta is not None:
         c1["torchaudio_gpu_us"] = 1e3 * timed(lambda: ta(x1d), 200)
         c1["max_abs_diff_vs_torchaudio_gpu"] = float((mel(x1d) - ta(x1d)).abs().max())
-    t0 = time.perf_counter()
-    for _ in range(20):
-        yc = port(x1)
-    c1["cpu_port_us"] = 1e6 * (time.perf_counter() - t0) / 20
-    c1["cpu_threads"] = torch.get_num_threads()
-    c1["max_abs_err_vs_cpu_port"] = float((mel(x1d).cpu() - yc).abs().max())
     res["C1_clip_10s"] = c1
 
     # ------------------------------------------------------------------ C2
@@ -106,8 +102,7 @@ def main():
     c2 = {}
     for name, parallel in (("sequential_46", False), ("parallel_6", True)):
         plan = segment_plan(len(song), parallel=parallel)
-        seq = torch.from_numpy(mel_oracle.segment(song, plan.window_len, plan.stride)).to(dev)
-        assert seq.shape[0] == plan.n_windows
+        seq = materialise(song_d, plan)
         ms_mod = timed(lambda: mel(seq), 50)
         ms_gat = timed(lambda: mel.forward_gather(song_d, 0, plan.stride, plan.n_windows, plan.window_len), 50)
         same = bool(torch.equal(mel(seq), mel.forward_gather(song_d, 0, plan.stride, plan.n_windows, plan.window_len)))
@@ -163,7 +158,7 @@ def main():
                                 num_mel_bins=M + 384, max_source_positions=2048)
             enc = WhisperEncoder(cfg).to(dev).to(torch.bfloat16).eval()
             plan = segment_plan(len(song))
-            seq_host = torch.from_numpy(mel_oracle.segment(song, plan.window_len, plan.stride)).pin_memory()
+            seq_host = materialise(song_d, plan).cpu().pin_memory()
             cond = torch.randn(1, 1, 384, device=dev, dtype=torch.bfloat16)
 
             def run(frontend, batch):
