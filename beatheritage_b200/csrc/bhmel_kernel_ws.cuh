@@ -219,6 +219,11 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
       t0 += gridDim.x;
       if (t0 < p.n_tiles) issue_span(p, t0, S.span[1], &S.span_full[1], &S.span_delta[1], mt);
     }
+    // tile -> (row, 32-frame block) is tracked incrementally: tile advances by gridDim.x per step
+    const int tpr = p.tiles_per_row;
+    const int step_r = static_cast<int>(gridDim.x / tpr), step_tb = static_cast<int>(gridDim.x % tpr);
+    int r = static_cast<int>(blockIdx.x / tpr);   // rows fit an int (checked by the host)
+    int tb = static_cast<int>(blockIdx.x % tpr);
     int it = 0;
 #pragma unroll 1
     for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
@@ -229,11 +234,10 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
       const long long tile2 = tile + 2 * static_cast<long long>(gridDim.x);
       if (tile2 < p.n_tiles) issue_span(p, tile2, S.span[b], &S.span_full[b], &S.span_delta[b], mt);
 
-      const long long r = tile / p.tiles_per_row;
-      const int t0 = static_cast<int>(tile - r * p.tiles_per_row) * kTileF;
+      const int t0 = tb * kTileF;
       const long long frames_left = p.T - t0;
       const int nf = frames_left < kTileF ? static_cast<int>(frames_left) : kTileF;
-      const long long ybase = r * p.y_row_pitch + static_cast<long long>(t0) * p.y_frame_pitch;
+      const long long ybase = static_cast<long long>(r) * p.y_row_pitch + static_cast<long long>(t0) * p.y_frame_pitch;
       const float4* prow = reinterpret_cast<const float4*>(S.P[b] + lane * kPPitchW);
       float* orow = S.out + lane * kOutPitch;
 #ifdef BHMEL_DEBUG_SKIP_MEL
@@ -258,19 +262,35 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
           for (int a = 0; a < kFr; ++a)
 #pragma unroll
             for (int bb = 0; bb < kCo; ++bb) vals[a][bb] = S.out[(mw + a * kMelWarps) * kOutPitch + lane + 32 * bb];
+          const long long fpitch = p.y_frame_pitch;
+          const long long y0 = ybase + static_cast<long long>(mw) * fpitch + mc + lane;
+          if (!p.y_bf16) {
+            float* yp = p.y + y0;
 #pragma unroll
-          for (int a = 0; a < kFr; ++a) {
-            const int fr = mw + a * kMelWarps;
-            const long long yrow = ybase + static_cast<long long>(fr) * p.y_frame_pitch + mc;
+            for (int a = 0; a < kFr; ++a, yp += kMelWarps * fpitch) {
+              if (mw + a * kMelWarps < nf) {
 #pragma unroll
-            for (int bb = 0; bb < kCo; ++bb) {
-              const int c2 = lane + 32 * bb;
-              if (fr < nf && c2 < mcount) store_out(p, yrow + c2, vals[a][bb]);
+                for (int bb = 0; bb < kCo; ++bb)
+                  if (lane + 32 * bb < mcount) yp[32 * bb] = vals[a][bb];
+              }
+            }
+          } else {
+            __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + y0;
+#pragma unroll
+            for (int a = 0; a < kFr; ++a, yp += kMelWarps * fpitch) {
+              if (mw + a * kMelWarps < nf) {
+#pragma unroll
+                for (int bb = 0; bb < kCo; ++bb)
+                  if (lane + 32 * bb < mcount) yp[32 * bb] = __float2bfloat16_rn(vals[a][bb]);
+              }
             }
           }
         }
         mel_group_sync();   // staging free again
       }
+      r += step_r;
+      tb += step_tb;
+      if (tb >= tpr) { tb -= tpr; ++r; }
     }
   }
 }
