@@ -234,28 +234,6 @@ __device__ __forceinline__ void mel_chunk(const float4* __restrict__ prow, const
     const float4* pa = prow + (d.x & 0xFFFF);
     const float4* pb = prow + (static_cast<unsigned>(d.x) >> 16);
     float va, vb;
-#ifdef BHMEL_MEL_COMPACT
-    // compact code (instruction-cache friendly): blocks of 4 groups in a loop, then a 0-3 remainder
-    {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
-      int ng = d.z;
-      auto step = [&](int g) {
-        const float4 wa = ldw<kSmemW>(wp + 2 * g), wb = ldw<kSmemW>(wp + 2 * g + 1);
-        const float4 xa = pa[g], xb = pb[g];
-        a0 = fmaf(xa.x, wa.x, a0); a1 = fmaf(xa.y, wa.y, a1); a2 = fmaf(xa.z, wa.z, a2); a3 = fmaf(xa.w, wa.w, a3);
-        b0 = fmaf(xb.x, wb.x, b0); b1 = fmaf(xb.y, wb.y, b1); b2 = fmaf(xb.z, wb.z, b2); b3 = fmaf(xb.w, wb.w, b3);
-      };
-      int g = 0;
-#pragma unroll 1
-      for (; g + 4 <= ng; g += 4) {
-        step(g); step(g + 1); step(g + 2); step(g + 3);
-      }
-      if (g + 2 <= ng) { step(g); step(g + 1); g += 2; }
-      if (g < ng) step(g);
-      va = (a0 + a1) + (a2 + a3);
-      vb = (b0 + b1) + (b2 + b3);
-    }
-#else
     if constexpr (!kSmemW) {   // rare path (huge / dense filterbanks): keep the code small
       band_dot2_n<kSmemW>(pa, pb, wp, d.z, va, vb);
     } else
@@ -273,7 +251,6 @@ __device__ __forceinline__ void mel_chunk(const float4* __restrict__ prow, const
       case 10: band_dot2<10, kSmemW>(pa, pb, wp, va, vb); break;
       default: band_dot2_n<kSmemW>(pa, pb, wp, d.z, va, vb); break;
     }
-#endif
     if constexpr (kLog) {
       va = fast_log1p(va);
       vb = fast_log1p(vb);

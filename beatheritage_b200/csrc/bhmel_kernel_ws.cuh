@@ -26,19 +26,24 @@ namespace ws {
 
 constexpr int kPPitchW = 532;                          // 532/4 odd -> LDS.128 conflict free; 2 rows >= 4224 B
 constexpr int kFftWarps = 8;
-constexpr int kMelWarps = 8;
+#ifndef BHMEL_MEL_WARPS
+#define BHMEL_MEL_WARPS 8
+#endif
+constexpr int kMelWarps = BHMEL_MEL_WARPS;                // 8 (2 warpgroups) or 4 (1 warpgroup)
 constexpr int kMelThreads = kMelWarps * 32;
 constexpr int kThreadsW = (kFftWarps + kMelWarps) * 32;   // 512
 constexpr int kPlanePitch = 33;                        // floats per row of a transposed plane
 // setmaxnreg budget: the CTA is launched with 128 registers/thread (65536 / 512); registers only
 // move between the warpgroups of the CTA, so 2 * kFftRegs + 2 * kMelRegs must not exceed 4 * 128.
-constexpr int kLaunchRegs = 128;
+constexpr int kLaunchRegs = (65536 / kThreadsW) / 8 * 8;   // 128 for 512 threads, 168 for 384
 #ifndef BHMEL_FFT_REGS
 #define BHMEL_FFT_REGS 184
 #endif
 constexpr int kFftRegs = BHMEL_FFT_REGS;                   // tunable at build time (A/B experiments)
-constexpr int kMelRegs = 4 * kLaunchRegs / 2 - kFftRegs;   // 72 for 184
-static_assert(2 * kFftRegs + 2 * kMelRegs <= 4 * kLaunchRegs, "setmaxnreg pool would deadlock");
+constexpr int kMelGroups = kMelWarps / 4;
+constexpr int kMelRegs = ((2 + kMelGroups) * kLaunchRegs - 2 * kFftRegs) / kMelGroups / 8 * 8;   // 72 for 184 / 8 warps
+static_assert(2 * kFftRegs + kMelGroups * kMelRegs <= (2 + kMelGroups) * kLaunchRegs, "setmaxnreg pool would deadlock");
+static_assert(kMelRegs >= 24 && kMelRegs <= 256 && kFftRegs <= 256, "setmaxnreg range");
 static_assert(2 * kPPitchW * 4 >= 32 * kPlanePitch * 4, "a pair's two P rows must hold one transposed plane");
 
 struct SmemWS {
