@@ -217,6 +217,23 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    # bind this rank to the CPUs next to its GPU so pinned host buffers are NUMA-local (matters
+    # for the host-buffer e2e leg when several ranks share the host); undone for the CPU baseline
+    numa_bound = False
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = local_rank
+        if visible:
+            ids = [v for v in visible.split(",") if v.strip() != ""]
+            if local_rank < len(ids) and ids[local_rank].strip().isdigit():
+                phys = int(ids[local_rank])
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
+        numa_bound = True
+    except Exception:
+        pass
+
     from beatheritage_b200 import MelSpectrogram
     mel = MelSpectrogram(*P0).to(dev)
 
@@ -354,6 +371,11 @@ def run_ours(args):
 
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------------
     cpu = None
+    if numa_bound:
+        try:
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))
+        except Exception:
+            pass
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         windows = 16
         mean_v, best_v, passes, threads = cpu_port_throughput(args.cpu_budget, windows)
@@ -384,7 +406,7 @@ def run_ours(args):
             "config": workload_config(world),
             "e2e": {"value": e2e_audio / e2e_t, "unit": UNIT, "h2d_bytes_per_step": BATCH * WINDOW * 4,
                     "d2h_bytes_per_step": BATCH * FRAMES * N_MELS * 4, "steps": n_e2e, "launches": e2e_launches,
-                    "api": "MelSpectrogram.forward_host -> bhmel_forward_host (pinned host buffers)",
+                    "api": "MelSpectrogram.forward_host -> bhmel_forward_host (pinned host buffers)", "numa_bound": numa_bound,
                     "finite": e2e_ok},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

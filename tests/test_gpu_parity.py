@@ -419,6 +419,24 @@ def test_c_abi_errors_on_device(dev):
     lib.bhmel_destroy(h)
 
 
+def test_plain_c_host_program(dev, tmp_path):
+    """examples/c_abi_demo.c: a C program (no Python, no torch) drives the library through the C ABI."""
+    import os
+    import shutil
+    import subprocess
+    from tests.conftest import ROOT
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available on this box")
+    exe = str(tmp_path / "c_abi_demo")
+    libdir = os.path.join(ROOT, "beatheritage_b200")
+    subprocess.run([nvcc, "-x", "cu", os.path.join(ROOT, "examples", "c_abi_demo.c"), "-I", os.path.join(ROOT, "include"),
+                    "-L", libdir, "-lbhmel", "-Xlinker", f"-rpath={libdir}", "-o", exe], check=True, capture_output=True)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "frames per window: 513" in res.stdout
+
+
 def test_torch_compile_does_not_graph_break(mods, dev):
     m = mods["P0"]
 
