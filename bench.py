@@ -406,9 +406,10 @@ def run_ours(args):
             peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
         except Exception:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        traffic = None
+        traffic, ncu_facts = None, {}
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["dram_bytes_per_launch"]
+            ncu_facts = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = ncu_facts["dram_bytes_per_launch"]
         except Exception:
             pass
         line = {
@@ -427,7 +428,9 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "bhmel_logmel_ws_kernel",
                          "algorithmic_bytes_per_launch": BATCH * ALGO_BYTES_PER_WINDOW,
-                         "note": "fp32 CUDA-core FFT: the FP32 issue rate, not HBM, bounds this kernel (DESIGN.md)"},
+                         "note": "fp32 CUDA-core FFT: the FP32 issue rate, not HBM, bounds this kernel (DESIGN.md)",
+                         "ncu_issue_slots_busy_pct": ncu_facts.get("issue_slots_busy_pct"),
+                         "ncu_warp_instructions_per_launch": ncu_facts.get("warp_instructions_per_launch")},
             "cpu_baseline": cpu,
             "clocks": clock_summary,
             "parity_max_abs_err_vs_cpu_port": parity,

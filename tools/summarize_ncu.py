@@ -87,6 +87,10 @@ if len(srows) > 2:
 open(out + "_summary.md", "w").write("\n".join(lines) + "\n")
 if "--traffic" in sys.argv:
     json.dump({"dram_bytes_per_launch": traffic, "source": os.path.basename(out) + "_raw.csv",
-               "kernel": d.get("Kernel Name", "?"), "duration_ms_under_ncu": f("gpu__time_duration.sum")},
+               "kernel": d.get("Kernel Name", "?"), "duration_ms_under_ncu": f("gpu__time_duration.sum"),
+               "issue_slots_busy_pct": f("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+               "fma_pipe_pct": f("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+               "lsu_pipe_pct": f("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+               "warp_instructions_per_launch": f("smsp__inst_executed.sum")},
               open(os.path.join(os.path.dirname(out), "traffic.json"), "w"), indent=1)
 print("\n".join(lines[:40]))
