@@ -419,6 +419,19 @@ def test_c_abi_errors_on_device(dev):
     lib.bhmel_destroy(h)
 
 
+def test_fuzz_three_schedules(dev):
+    """A few seconds of tools/fuzz_variants.py: random shapes / strides / pad modes / filterbanks,
+    module and gather mode; the three kernel schedules must agree bit for bit."""
+    import os
+    import subprocess
+    import sys
+    from tests.conftest import ROOT
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_variants.py"), "--seconds", "6", "--seed", "3"],
+                         capture_output=True, text=True, timeout=200)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "fuzz ok" in res.stdout
+
+
 def test_plain_c_host_program(dev, tmp_path):
     """examples/c_abi_demo.c: a C program (no Python, no torch) drives the library through the C ABI."""
     import os
