@@ -15,6 +15,8 @@ pass A fuses the (half-)Hann window into its first butterfly stage (3 instructio
 pair), pass B fuses the inter-pass twiddle W_1024^(k1*n2) into its first stage (10 per pair).
 
 Usage: python gen_fft32.py > fft32_gen.h   (build.py runs it; the output is not committed)
+       python gen_fft32.py --packed > ...   additionally emits fft32x2_pass_a/b, the same schedule on
+       packed (re, im) register pairs with Blackwell's FFMA2/FADD2/FMUL2 (experiment)
 """
 import math
 import sys
@@ -111,6 +113,120 @@ def gen_pass_b(em):
     return dit(em, list(range(N)), base2)
 
 
+# --------------------------------------------------------------------------------------------
+# Packed flavour: the same butterfly schedule emitted with Blackwell's packed fp32 instructions
+# (fma/add/mul.rn.f32x2 -> SASS FFMA2/FADD2/FMUL2).  A complex value lives in one 64-bit register
+# pair (re, im); ptxas folds the half swaps / per-half negations / scalar broadcasts that the
+# mov.b64 pack-unpack sequences below express into operand modifiers (.LO_HI, .NP, R.F32), so a
+# butterfly costs half the issue slots of the scalar form.  The arithmetic (operation order and
+# rounding points) is IDENTICAL to the scalar flavour, so both give the same bits.
+class EmitX2(Emit):
+    def tmp64(self, expr):
+        name = f"z{self.n}"
+        self.n += 1
+        self.count += 1
+        self.lines.append(f"    const unsigned long long {name} = {expr};")
+        return name
+
+
+def x2_swap_np(o):      # (o.im, -o.re)
+    return f"pk_im_nre({o})"
+
+
+def x2_swap_pn(o):      # (-o.im, o.re)
+    return f"pk_nim_re({o})"
+
+
+def butterfly_x2(em, E, O, k, n):
+    k %= n
+    if k == 0:
+        return em.tmp64(f"add2({E}, {O})"), em.tmp64(f"sub2({E}, {O})")
+    if 4 * k == n:       # W = -i : W*O = (Oi, -Or)
+        return em.tmp64(f"add2({E}, {x2_swap_np(O)})"), em.tmp64(f"add2({E}, {x2_swap_pn(O)})")
+    th = 2.0 * math.pi * k / n
+    c, s = math.cos(th), math.sin(th)
+    inner = em.tmp64(f"fma2({x2_swap_np(O)}, bc({flit(s)}), {E})")     # (s*Oi + Er, -s*Or + Ei)
+    x = em.tmp64(f"fma2({O}, bc({flit(c)}), {inner})")
+    y = em.tmp64(f"fma2({E}, bc(2.0f), neg2({x}))")
+    return x, y
+
+
+def dit_x2(em, vals, base2):
+    n = len(vals)
+    if n == 2:
+        return list(base2(vals[0], vals[1]))
+    E = dit_x2(em, vals[0::2], base2)
+    O = dit_x2(em, vals[1::2], base2)
+    out = [None] * n
+    for k in range(n // 2):
+        out[k], out[k + n // 2] = butterfly_x2(em, E[k], O[k], k, n)
+    return out
+
+
+def gen_pass_a_x2(em):
+    """in: v[36], w[32] (as in the scalar flavour).  out: z[k1] packed (re, im)."""
+    def base2(i0, i1):
+        p = em.tmp64(f"mul2(pk(v[{i0}], v[{i0 + 4}]), bc(w[{i0}]))")
+        z1 = f"pk(v[{i1}], v[{i1 + 4}])"
+        s = em.tmp64(f"fma2({z1}, bc(w[{i1}]), {p})")
+        d = em.tmp64(f"fma2({z1}, bc(-w[{i1}]), {p})")
+        return s, d
+    return dit_x2(em, list(range(N)), base2)
+
+
+def gen_pass_b_x2(em):
+    """in: u[n2] packed, tr/ti[n2].  out: z[k2] packed."""
+    def base2(i0, i1):
+        if i0 == 0:
+            a = "u[0]"
+        else:
+            m = em.tmp64(f"mul2(pk_swap(u[{i0}]), pk(-ti[{i0}], ti[{i0}]))")           # (-ti*ui, ti*ur)
+            a = em.tmp64(f"fma2(u[{i0}], bc(tr[{i0}]), {m})")
+        inner = em.tmp64(f"fma2(pk_swap(u[{i1}]), pk(-ti[{i1}], ti[{i1}]), {a})")
+        x = em.tmp64(f"fma2(u[{i1}], bc(tr[{i1}]), {inner})")
+        y = em.tmp64(f"fma2({a}, bc(2.0f), neg2({x}))")
+        return x, y
+    return dit_x2(em, list(range(N)), base2)
+
+
+X2_HELPERS = r"""
+// ---- packed fp32 pair helpers (device only; sm_100+) ----
+__device__ __forceinline__ unsigned long long pk(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long bc(float s) { return pk(s, s); }
+__device__ __forceinline__ unsigned long long pk_swap(unsigned long long v) { float a, b; upk(v, a, b); return pk(b, a); }
+__device__ __forceinline__ unsigned long long pk_im_nre(unsigned long long v) { float a, b; upk(v, a, b); return pk(b, -a); }
+__device__ __forceinline__ unsigned long long pk_nim_re(unsigned long long v) { float a, b; upk(v, a, b); return pk(-b, a); }
+__device__ __forceinline__ unsigned long long neg2(unsigned long long v) { float a, b; upk(v, a, b); return pk(-a, -b); }
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+"""
+
+
 def main():
     out = []
     out.append("// GENERATED by gen_fft32.py -- do not edit.  Straight-line 32-point FFT passes.")
@@ -134,6 +250,27 @@ def main():
         for k, (r, i) in enumerate(res):
             out.append(f"    re[{k}] = {r}; im[{k}] = {i};")
         out.append("}")
+    if "--packed" not in sys.argv:      # the packed flavour is an experiment, off by default
+        out.append("}  // namespace bhmel")
+        sys.stdout.write("\n".join(out) + "\n")
+        return
+    out.append("#ifdef __CUDACC__")
+    out.append(X2_HELPERS)
+    for name, gen, sig in (
+        ("fft32x2_pass_a", gen_pass_a_x2,
+         "const float (&v)[36], const float (&w)[32], unsigned long long (&z)[32]"),
+        ("fft32x2_pass_b", gen_pass_b_x2,
+         "const unsigned long long (&u)[32], const float (&tr)[32], const float (&ti)[32], unsigned long long (&z)[32]"),
+    ):
+        em = EmitX2()
+        res = gen(em)
+        out.append(f"// ~{em.count} packed instructions")
+        out.append(f"__device__ __forceinline__ void {name}({sig}) {{")
+        out.extend(em.lines)
+        for k, r in enumerate(res):
+            out.append(f"    z[{k}] = {r};")
+        out.append("}")
+    out.append("#endif  // __CUDACC__")
     out.append("}  // namespace bhmel")
     sys.stdout.write("\n".join(out) + "\n")
 
