@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("BHMEL_LIB") or os.path.join(_PKG, "libbhmel.so")   # 
 PAD_CONSTANT, PAD_REFLECT = 0, 1
 OPT_BULK_COPY = 1
 OPT_KERNEL = 2
+OPT_STATIC_MEL = 3
 KERNEL_BARRIER, KERNEL_INDEPENDENT_WARPS, KERNEL_WARP_SPECIALIZED = 0, 1, 2
 OK, EINVAL, ECUDA, ESHAPE, EDEVICE = 0, 1, 2, 3, 4
 

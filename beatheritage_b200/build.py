@@ -33,6 +33,10 @@ def generate() -> str:
         out = subprocess.run([sys.executable, gen_py], check=True, capture_output=True, text=True).stdout
         with open(GEN, "w") as f:
             f.write(out)
+    mel_py, mel_h = os.path.join(CSRC, "gen_mel_static.py"), os.path.join(CSRC, "mel_static_gen.h")
+    gen_args = os.environ.get("BHMEL_GEN_MEL_ARGS", "").split()   # A/B experiments only
+    if gen_args or not _newer(mel_h, [mel_py, os.path.join(CSRC, "bhmel_fb_baked.h")]):
+        subprocess.run([sys.executable, mel_py, "-o", mel_h, *gen_args], check=True)
     return GEN
 
 

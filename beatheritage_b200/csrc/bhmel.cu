@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include "bhmel_fb_baked.h"
 #include "bhmel_kernel_iw.cuh"
 #include "bhmel_kernel_ws.cuh"
 
@@ -58,6 +59,10 @@ struct bhmel_handle {
   float* d_weights = nullptr;
   int n_weights = 0;
   int n_pairs = 0;
+  bhmel::PairDesc* d_pairs_rem = nullptr;   // baked filterbank: generic tables of the filters the static stage leaves
+  float* d_weights_rem = nullptr;
+  int n_weights_rem = 0;
+  int n_pairs_rem = 0;
   bhmel::RoundDesc* d_rounds = nullptr;   // independent-warp kernel tables
   int* d_g0 = nullptr;
   float* d_wt = nullptr;
@@ -66,6 +71,8 @@ struct bhmel_handle {
   std::atomic<int64_t> launches{0};
   int use_bulk = 1;
   int kernel_variant = BHMEL_KERNEL_WARP_SPECIALIZED;
+  int baked_fb = 0;      // 1: the filterbank is bit-identical to the baked P0 table (bhmel_fb_baked.h)
+  int static_mel = 1;    // BHMEL_OPT_STATIC_MEL: use the statically scheduled mel stage when baked_fb != 0
   // bhmel_forward_host pipeline (lazily created)
   std::mutex host_mu;
   cudaStream_t hs[kHostSlots] = {nullptr, nullptr, nullptr};
@@ -78,7 +85,16 @@ struct bhmel_handle {
 
 namespace {
 
+// Which baked filterbank (bhmel_fb_baked.h) the host table equals bit for bit; 0 = none.
+int match_baked_fb(const std::vector<float>& fb, int n_mels) {
+  if (n_mels != kBakedP0Mels) return 0;
+  std::vector<uint32_t> want(static_cast<size_t>(bhmel::kBins) * n_mels, 0u);
+  for (int i = 0; i < kBakedP0Nnz; ++i) want[static_cast<size_t>(kBakedP0[i][0]) * n_mels + kBakedP0[i][1]] = kBakedP0[i][2];
+  return std::memcmp(want.data(), fb.data(), want.size() * sizeof(uint32_t)) == 0 ? 1 : 0;
+}
+
 int upload_filterbank(bhmel_handle* h) {
+  h->baked_fb = match_baked_fb(h->fb, h->prm.n_mels);
   bhmel::PairTables t = bhmel::make_pairs(h->fb.data(), h->prm.n_mels);
   if (t.pairs.size() > static_cast<size_t>(bhmel::kPairCap))
     return fail(BHMEL_EINVAL, "too many filter pairs for the kernel's descriptor table");
@@ -96,6 +112,23 @@ int upload_filterbank(bhmel_handle* h) {
                      cudaMemcpyHostToDevice));
   h->n_weights = static_cast<int>(t.weights.size());
   h->n_pairs = static_cast<int>(t.pairs.size());
+  if (h->d_pairs_rem) cudaFree(h->d_pairs_rem);
+  if (h->d_weights_rem) cudaFree(h->d_weights_rem);
+  h->d_pairs_rem = nullptr;
+  h->d_weights_rem = nullptr;
+  if (h->baked_fb == 1) {
+    bhmel::PairTables r = bhmel::make_pairs(h->fb.data(), h->prm.n_mels, bhmel::kStaticP0Filters);
+    if (r.weights.size() > static_cast<size_t>(bhmel::kFwCap) || r.pairs.size() > static_cast<size_t>(bhmel::kPairCap)) {
+      h->baked_fb = 0;   // cannot happen for the baked table; keep the generic stage if it ever does
+    } else {
+      BH_CUDA(cudaMalloc(&h->d_pairs_rem, r.pairs.size() * sizeof(bhmel::PairDesc)));
+      BH_CUDA(cudaMalloc(&h->d_weights_rem, r.weights.size() * sizeof(float)));
+      BH_CUDA(cudaMemcpy(h->d_pairs_rem, r.pairs.data(), r.pairs.size() * sizeof(bhmel::PairDesc), cudaMemcpyHostToDevice));
+      BH_CUDA(cudaMemcpy(h->d_weights_rem, r.weights.data(), r.weights.size() * sizeof(float), cudaMemcpyHostToDevice));
+      h->n_weights_rem = static_cast<int>(r.weights.size());
+      h->n_pairs_rem = static_cast<int>(r.pairs.size());
+    }
+  }
 
   bhmel::RoundTables rt = bhmel::make_rounds(h->fb.data(), h->prm.n_mels);
   if (rt.rounds.size() > static_cast<size_t>(bhmel::iw::kRoundCap))
@@ -202,10 +235,21 @@ int launch(bhmel_handle* h, const float* x, long long row_stride, long long row0
       bhmel::iw::bhmel_logmel_iw_kernel<false><<<grid, bhmel::iw::kIwThreads, sizeof(bhmel::iw::SmemIW), stream>>>(q);
   } else if (ws) {
     const unsigned grid = static_cast<unsigned>(p.n_tiles < h->num_sms ? p.n_tiles : h->num_sms);
-    if (p.log_scale)
-      bhmel::ws::bhmel_logmel_ws_kernel<true><<<grid, bhmel::ws::kThreadsW, sizeof(bhmel::ws::SmemWS), stream>>>(p);
-    else
-      bhmel::ws::bhmel_logmel_ws_kernel<false><<<grid, bhmel::ws::kThreadsW, sizeof(bhmel::ws::SmemWS), stream>>>(p);
+    const bool st = h->static_mel && h->baked_fb == 1;
+    constexpr size_t smem = sizeof(bhmel::ws::SmemWS);
+    if (st) {   // the generic stage only sees the filters the generated code leaves
+      p.pairs = h->d_pairs_rem;
+      p.weights = h->d_weights_rem;
+      p.n_pairs = h->n_pairs_rem;
+      p.n_weights = h->n_weights_rem;
+    }
+    if (p.log_scale) {
+      if (st) bhmel::ws::bhmel_logmel_ws_kernel<true, 1><<<grid, bhmel::ws::kThreadsW, smem, stream>>>(p);
+      else bhmel::ws::bhmel_logmel_ws_kernel<true, 0><<<grid, bhmel::ws::kThreadsW, smem, stream>>>(p);
+    } else {
+      if (st) bhmel::ws::bhmel_logmel_ws_kernel<false, 1><<<grid, bhmel::ws::kThreadsW, smem, stream>>>(p);
+      else bhmel::ws::bhmel_logmel_ws_kernel<false, 0><<<grid, bhmel::ws::kThreadsW, smem, stream>>>(p);
+    }
   } else {
     const unsigned grid = static_cast<unsigned>(p.n_tiles < h->num_sms ? p.n_tiles : h->num_sms);
     if (p.log_scale)
@@ -223,6 +267,15 @@ int launch(bhmel_handle* h, const float* x, long long row_stride, long long row0
 extern "C" {
 
 int bhmel_version(void) { return BHMEL_VERSION; }
+
+#ifdef BHMEL_TRACE   // debug builds only: fetch the phase timeline recorded by block 0 of the ws kernel
+int bhmel_debug_trace(long long* out, int n) {
+  const size_t bytes = sizeof(long long) * static_cast<size_t>(n);
+  if (bytes > sizeof(bhmel::ws::g_trace)) return BHMEL_EINVAL;
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out, bhmel::ws::g_trace, bytes) == cudaSuccess ? BHMEL_OK : BHMEL_ECUDA;
+}
+#endif
 
 const char* bhmel_last_error(void) { return g_err.c_str(); }
 
@@ -257,9 +310,13 @@ int bhmel_create(const bhmel_params* prm, bhmel_handle** out) {
                                static_cast<int>(sizeof(bhmel::SmemLayout))));
   BH_CUDA(cudaFuncSetAttribute(bhmel::bhmel_logmel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(sizeof(bhmel::SmemLayout))));
-  BH_CUDA(cudaFuncSetAttribute(bhmel::ws::bhmel_logmel_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  BH_CUDA(cudaFuncSetAttribute(bhmel::ws::bhmel_logmel_ws_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(sizeof(bhmel::ws::SmemWS))));
-  BH_CUDA(cudaFuncSetAttribute(bhmel::ws::bhmel_logmel_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  BH_CUDA(cudaFuncSetAttribute(bhmel::ws::bhmel_logmel_ws_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(sizeof(bhmel::ws::SmemWS))));
+  BH_CUDA(cudaFuncSetAttribute(bhmel::ws::bhmel_logmel_ws_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(sizeof(bhmel::ws::SmemWS))));
+  BH_CUDA(cudaFuncSetAttribute(bhmel::ws::bhmel_logmel_ws_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(sizeof(bhmel::ws::SmemWS))));
   BH_CUDA(cudaFuncSetAttribute(bhmel::iw::bhmel_logmel_iw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(sizeof(bhmel::iw::SmemIW))));
@@ -311,6 +368,8 @@ void bhmel_destroy(bhmel_handle* h) {
   if (h->d_tw) cudaFree(h->d_tw);
   if (h->d_pairs) cudaFree(h->d_pairs);
   if (h->d_weights) cudaFree(h->d_weights);
+  if (h->d_pairs_rem) cudaFree(h->d_pairs_rem);
+  if (h->d_weights_rem) cudaFree(h->d_weights_rem);
   if (h->d_rounds) cudaFree(h->d_rounds);
   if (h->d_g0) cudaFree(h->d_g0);
   if (h->d_wt) cudaFree(h->d_wt);
@@ -360,6 +419,9 @@ int bhmel_set_option(bhmel_handle* h, int32_t option, int64_t value) {
           value != BHMEL_KERNEL_WARP_SPECIALIZED)
         return fail(BHMEL_EINVAL, "unknown kernel variant");
       h->kernel_variant = static_cast<int>(value);
+      return BHMEL_OK;
+    case BHMEL_OPT_STATIC_MEL:
+      h->static_mel = value != 0;
       return BHMEL_OK;
     default:
       return fail(BHMEL_EINVAL, "unknown option " + std::to_string(option));

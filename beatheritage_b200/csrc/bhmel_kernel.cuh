@@ -220,6 +220,46 @@ __device__ __forceinline__ void band_dot2_n(const float4* __restrict__ pa, const
   vb = (b0 + b1) + (b2 + b3);
 }
 
+// Fall-through form of the pair dot product: one copy of the group body per possible remaining
+// count, entered at `ng` and run to the end, so the hot mel code is ~10 group bodies instead of
+// 1 + 2 + ... + 10 (the kernel's hot loop has to fit the 32 KB instruction cache next to the FFT
+// role's ~24 KB; DESIGN.md "instruction footprint").  Groups are addressed back from the END of
+// the band, which keeps the accumulation order ascending -- bit-identical to band_dot2<NG>.
+template <bool kSmemW>
+__device__ __forceinline__ void band_dot2_ft(const float4* __restrict__ pa, const float4* __restrict__ pb,
+                                             const float4* __restrict__ wp, int ng, float& va, float& vb) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+  const float4* pae = pa + ng;
+  const float4* pbe = pb + ng;
+  const float4* wpe = wp + 2 * ng;
+#define BHMEL_GROUP(L)                                                                                   \
+  {                                                                                                      \
+    const float4 wa = ldw<kSmemW>(wpe - 2 * (L)), wb = ldw<kSmemW>(wpe - 2 * (L) + 1);                   \
+    const float4 xa = pae[-(L)], xb = pbe[-(L)];                                                         \
+    a0 = fmaf(xa.x, wa.x, a0); a1 = fmaf(xa.y, wa.y, a1); a2 = fmaf(xa.z, wa.z, a2); a3 = fmaf(xa.w, wa.w, a3); \
+    b0 = fmaf(xb.x, wb.x, b0); b1 = fmaf(xb.y, wb.y, b1); b2 = fmaf(xb.z, wb.z, b2); b3 = fmaf(xb.w, wb.w, b3); \
+  }
+  switch (ng) {
+    default:
+      for (int L = ng; L > 10; --L) BHMEL_GROUP(L)
+      [[fallthrough]];
+    case 10: BHMEL_GROUP(10) [[fallthrough]];
+    case 9: BHMEL_GROUP(9) [[fallthrough]];
+    case 8: BHMEL_GROUP(8) [[fallthrough]];
+    case 7: BHMEL_GROUP(7) [[fallthrough]];
+    case 6: BHMEL_GROUP(6) [[fallthrough]];
+    case 5: BHMEL_GROUP(5) [[fallthrough]];
+    case 4: BHMEL_GROUP(4) [[fallthrough]];
+    case 3: BHMEL_GROUP(3) [[fallthrough]];
+    case 2: BHMEL_GROUP(2) [[fallthrough]];
+    case 1: BHMEL_GROUP(1) [[fallthrough]];
+    case 0: break;
+  }
+#undef BHMEL_GROUP
+  va = (a0 + a1) + (a2 + a3);
+  vb = (b0 + b1) + (b2 + b3);
+}
+
 // One chunk (<= kMChunk output columns) of the mel projection for the 32 frames of the tile:
 // warp w takes pairs w, w + kWarps, ...; results go to the staging buffer [frame][column].
 template <bool kSmemW, bool kLog, int kStride = kWarps>
@@ -234,9 +274,18 @@ __device__ __forceinline__ void mel_chunk(const float4* __restrict__ prow, const
     const float4* pa = prow + (d.x & 0xFFFF);
     const float4* pb = prow + (static_cast<unsigned>(d.x) >> 16);
     float va, vb;
-    if constexpr (!kSmemW) {   // rare path (huge / dense filterbanks): keep the code small
+#if defined(BHMEL_MEL_COMPACT)
+    constexpr int kForm = 1;
+#elif defined(BHMEL_MEL_UNROLLED)
+    constexpr int kForm = kSmemW ? 2 : 1;   // rare path (huge / dense filterbanks): keep the code small
+#else
+    constexpr int kForm = kSmemW ? 0 : 1;
+#endif
+    if constexpr (kForm == 0) {
+      band_dot2_ft<kSmemW>(pa, pb, wp, d.z, va, vb);
+    } else if constexpr (kForm == 1) {
       band_dot2_n<kSmemW>(pa, pb, wp, d.z, va, vb);
-    } else
+    } else {
     switch (d.z) {
       case 0: va = 0.f; vb = 0.f; break;
       case 1: band_dot2<1, kSmemW>(pa, pb, wp, va, vb); break;
@@ -250,6 +299,7 @@ __device__ __forceinline__ void mel_chunk(const float4* __restrict__ prow, const
       case 9: band_dot2<9, kSmemW>(pa, pb, wp, va, vb); break;
       case 10: band_dot2<10, kSmemW>(pa, pb, wp, va, vb); break;
       default: band_dot2_n<kSmemW>(pa, pb, wp, d.z, va, vb); break;
+    }
     }
     if constexpr (kLog) {
       va = fast_log1p(va);

@@ -20,6 +20,7 @@
 //             256-thread role group (named barrier 1).
 #pragma once
 #include "bhmel_kernel.cuh"
+#include "mel_static_gen.h"
 
 namespace bhmel {
 namespace ws {
@@ -57,6 +58,18 @@ struct SmemWS {
   unsigned long long p_empty[2];
   int span_delta[2];                          // element offset of the tile's first sample inside span[b]
 };
+
+#ifdef BHMEL_TRACE   // phase timeline of block 0 (tools/trace_phases.py); never defined in the shipped build
+constexpr int kTraceIt0 = 64, kTraceIts = 4, kTraceEv = 16;
+__device__ long long g_trace[16 * kTraceIts * kTraceEv];
+#define BHMEL_TR(ev)                                                                                  \
+  do {                                                                                                \
+    if (blockIdx.x == 0 && lane == 0 && it >= kTraceIt0 && it < kTraceIt0 + kTraceIts)                \
+      g_trace[(warp * kTraceIts + (it - kTraceIt0)) * kTraceEv + (ev)] = clock64();                   \
+  } while (0)
+#else
+#define BHMEL_TR(ev) do {} while (0)
+#endif
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
@@ -115,7 +128,12 @@ __device__ __forceinline__ void issue_span(const KParams& p, long long tile, flo
   cp_async_arrive_noinc(bar);
 }
 
-template <bool kLog>
+// kStatic selects the mel stage: 0 = generic (pair descriptors + weight table, any filterbank);
+// 1 = the baked P0 filterbank: mel warps 0..kStaticP0Warps-1 run generated straight-line code
+// (mel_static_gen.h: weights as FFMA immediates, every power block read once) for filters
+// 0..kStaticP0Filters-1, the other mel warps run the generic stage on the pair tables of the
+// remaining filters.  Results are bit-identical to kStatic = 0.
+template <bool kLog, int kStatic = 0>
 __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemWS& S = *reinterpret_cast<SmemWS*>(smem_raw);
@@ -123,7 +141,8 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
   const int warp = tid >> 5;
   const int lane = tid & 31;
 
-  const bool fw_in_smem = p.n_weights <= kFwCap;
+  static_assert(kStatic == 0 || (kMelWarps == 8 && kStaticP0Warps < kMelWarps), "static mel stage: 8 mel warps");
+  const bool fw_in_smem = p.n_weights <= kFwCap;   // the host guarantees this for kStatic != 0
   if (fw_in_smem)
     for (int i = tid; i < p.n_weights; i += kThreadsW) S.fw[i] = p.weights[i];
   for (int i = tid; i < p.n_pairs; i += kThreadsW) S.pairs[i] = reinterpret_cast<const int4*>(p.pairs)[i];
@@ -156,6 +175,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
       const uint32_t ph = (it >> 1) & 1;
       mbar_wait(&S.span_full[b], ph);
       mbar_wait(&S.p_empty[b], ph ^ 1);   // the mel role has released this P buffer (tile it-2)
+      BHMEL_TR(0);
       const float* span_b = S.span[b] + S.span_delta[b];
 #ifdef BHMEL_DEBUG_SKIP_FFT
       if (tile < 0)
@@ -171,6 +191,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
           for (int m = 0; m < 36; ++m) v[m] = sp[32 * m];
           fft32_pass_a(v, wreg, ar, ai);
         }
+        BHMEL_TR(1 + 5 * (j / kFftWarps));
         // transpose the real plane, then the imaginary plane, through the pair's own rows
         float ur[32], ui[32];
 #pragma unroll
@@ -185,8 +206,10 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
 #pragma unroll
         for (int n = 0; n < 32; ++n) ui[n] = rows[lane * kPlanePitch + n];
         __syncwarp();
+        BHMEL_TR(2 + 5 * (j / kFftWarps));
         float br[32], bi[32];
         fft32_pass_b(ur, ui, twr, twi, br, bi);
+        BHMEL_TR(3 + 5 * (j / kFftWarps));
         float* Pa = rows + lane;
         float* Pb = Pa + kPPitchW;
 #pragma unroll
@@ -209,6 +232,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
           Pb[512] = zi * zi;
         }
         if (lane < 6) rows[(lane / 3) * kPPitchW + kBins + lane % 3] = 0.f;   // bins 513..515 read as zero weights' partners
+        BHMEL_TR(4 + 5 * (j / kFftWarps));
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.p_full[b]);
@@ -234,7 +258,9 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
     for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int b = it & 1;
       const uint32_t ph = (it >> 1) & 1;
+      BHMEL_TR(0);
       mbar_wait(&S.p_full[b], ph);
+      BHMEL_TR(1);
       // every FFT warp is done with tile `it`, so span[b] is free: fetch the tile two steps ahead
       const long long tile2 = tile + 2 * static_cast<long long>(gridDim.x);
       if (tile2 < p.n_tiles) issue_span(p, tile2, S.span[b], &S.span_full[b], &S.span_delta[b], mt);
@@ -253,13 +279,22 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
       for (int mc = 0, c = 0; mc < p.n_mels; mc += kMChunk, ++c) {
         const int mcount = (p.n_mels - mc) < kMChunk ? (p.n_mels - mc) : kMChunk;
         const int4* pd = S.pairs + c * (kMChunk / 2);
-        if (fw_in_smem) mel_chunk<true, kLog, kMelWarps>(prow, pd, (mcount + 1) >> 1, S.fw, orow, mw);
+#ifdef BHMEL_DEBUG_SKIP_DOTS
+        if (tile < 0)
+#endif
+        if constexpr (kStatic == 1) {
+          if (mw < kStaticP0Warps) mel_static_P0<kLog>(prow, orow, mw);
+          else mel_chunk<true, kLog, kMelWarps - kStaticP0Warps>(prow, pd, p.n_pairs, S.fw, orow, mw - kStaticP0Warps);
+        }
+        else if (fw_in_smem) mel_chunk<true, kLog, kMelWarps>(prow, pd, (mcount + 1) >> 1, S.fw, orow, mw);
         else mel_chunk<false, kLog, kMelWarps>(prow, pd, (mcount + 1) >> 1, p.weights, orow, mw);
+        BHMEL_TR(2);
         if (mc + kMChunk >= p.n_mels) {   // last chunk: this warp no longer reads P[b]
           __syncwarp();
           if (lane == 0) mbar_arrive(&S.p_empty[b]);
         }
         mel_group_sync();   // staging complete
+        BHMEL_TR(3);
         {
           constexpr int kFr = kTileF / kMelWarps, kCo = kMChunk / 32;   // 4 frames x 3 column steps
           float vals[kFr][kCo];
@@ -291,7 +326,9 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
             }
           }
         }
+        BHMEL_TR(4);
         mel_group_sync();   // staging free again
+        BHMEL_TR(5);
       }
       r += step_r;
       tb += step_tb;

@@ -124,20 +124,24 @@ struct PairTables {
   int max_groups = 0;
 };
 
-inline PairTables make_pairs(const float* fb, int n_mels) {
+// first_filter > 0 builds the tables for filters [first_filter, n_mels) only (the remainder the
+// generic stage handles next to a statically scheduled mel stage); output columns stay absolute.
+inline PairTables make_pairs(const float* fb, int n_mels, int first_filter = 0) {
   const BandTables bt = make_bands(fb, n_mels);
   constexpr int kGroups = (kBins + 3) / 4;   // 129 groups cover bins 0..515
   PairTables t;
   t.chunk_start.push_back(0);
   for (int mc = 0; mc < n_mels; mc += kMelChunk) {
     const int cnt = (n_mels - mc) < kMelChunk ? (n_mels - mc) : kMelChunk;
-    std::vector<int> order(cnt);
-    for (int i = 0; i < cnt; ++i) order[i] = mc + i;
+    std::vector<int> order;
+    for (int i = 0; i < cnt; ++i)
+      if (mc + i >= first_filter) order.push_back(mc + i);
     // longest bands first (stable -> deterministic)
-    for (int i = 1; i < cnt; ++i)
+    const int cnt_sel = static_cast<int>(order.size());
+    for (int i = 1; i < cnt_sel; ++i)
       for (int j = i; j > 0 && bt.bands[order[j]].ng > bt.bands[order[j - 1]].ng; --j) std::swap(order[j], order[j - 1]);
-    for (int i = 0; i < cnt; i += 2) {
-      const int ma = order[i], mb = (i + 1 < cnt) ? order[i + 1] : -1;
+    for (int i = 0; i < cnt_sel; i += 2) {
+      const int ma = order[i], mb = (i + 1 < cnt_sel) ? order[i + 1] : -1;
       const FilterBand a = bt.bands[ma];
       const FilterBand b = mb >= 0 ? bt.bands[mb] : FilterBand{0, 0, 0, 0};
       const int ng = a.ng > b.ng ? a.ng : b.ng;

@@ -146,6 +146,7 @@ class MelSpectrogram(nn.Module):
         self._stamp: dict[int, tuple] = {}        # device index -> buffer versions the handle was built from
         self._bulk = True
         self._variant = _lib.KERNEL_WARP_SPECIALIZED
+        self._static_mel = True
         self._register()
 
     def _register(self) -> None:
@@ -196,6 +197,8 @@ class MelSpectrogram(nn.Module):
                     if not self._bulk:
                         _lib.check(lib.bhmel_set_option(h, _lib.OPT_BULK_COPY, 0))
                     _lib.check(lib.bhmel_set_option(h, _lib.OPT_KERNEL, self._variant))
+                    if not getattr(self, "_static_mel", True):
+                        _lib.check(lib.bhmel_set_option(h, _lib.OPT_STATIC_MEL, 0))
                 else:   # buffers were reloaded / edited: refresh the device tables
                     _lib.check(lib.bhmel_set_fb(h, ctypes.cast(fb.data_ptr(), fp)))
                     _lib.check(lib.bhmel_set_window(h, ctypes.cast(win.data_ptr(), fp)))
@@ -228,6 +231,13 @@ class MelSpectrogram(nn.Module):
                          "ws": _lib.KERNEL_WARP_SPECIALIZED}[variant]
         for h in self._handles.values():
             _lib.check(_lib.lib().bhmel_set_option(h, _lib.OPT_KERNEL, self._variant))
+
+    def set_static_mel(self, enabled: bool) -> None:
+        """Debug / A-B switch: False forces the generic mel stage even for the baked default
+        filterbank (results are bit-identical; see BHMEL_OPT_STATIC_MEL in include/bhmel.h)."""
+        self._static_mel = bool(enabled)
+        for h in self._handles.values():
+            _lib.check(_lib.lib().bhmel_set_option(h, _lib.OPT_STATIC_MEL, int(self._static_mel)))
 
     # -- forward -----------------------------------------------------------------------
     def _check_input(self, samples: torch.Tensor) -> torch.Tensor:

@@ -135,6 +135,13 @@ int bhmel_forward_host(bhmel_handle* h, const float* x_host, int64_t B, int64_t 
 #define BHMEL_KERNEL_BARRIER 0
 #define BHMEL_KERNEL_INDEPENDENT_WARPS 1
 #define BHMEL_KERNEL_WARP_SPECIALIZED 2
+/* BHMEL_OPT_STATIC_MEL: 1 (default) lets the warp-specialised kernel run the mel stage as generated
+ * straight-line code (weights as instruction immediates, every power-spectrum block read once)
+ * whenever the handle's filterbank equals, bit for bit, a table baked into the library -- the
+ * reference's default front end (P0: 80 htk mels, 20..8000 Hz at 16 kHz; ref:
+ * configs/model/whisper_small_v2.yaml:16-21).  0 forces the generic descriptor-driven stage.
+ * Results are bit-identical either way; any other filterbank always takes the generic stage. */
+#define BHMEL_OPT_STATIC_MEL 3
 int bhmel_set_option(bhmel_handle* h, int32_t option, int64_t value);
 
 /* Host-buffer entry with typed input / output (next rows N1 + N2 of SURVEY.md 8f).

@@ -89,7 +89,9 @@ def emu_lib():
     from beatheritage_b200 import build as bbuild
     gen = bbuild.generate()
     src = os.path.join(ROOT, "tests", "emu", "emu.cpp")
-    deps = [src, gen, os.path.join(ROOT, "beatheritage_b200", "csrc", "bhmel_tables.h")]
+    csrc = os.path.join(ROOT, "beatheritage_b200", "csrc")
+    deps = [src, gen, os.path.join(csrc, "bhmel_tables.h"), os.path.join(csrc, "mel_static_gen.h"),
+            os.path.join(csrc, "bhmel_fb_baked.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, src],
                        check=True)
@@ -101,8 +103,9 @@ def emu_lib():
     lib.bhmel_emu_forward.restype = ctypes.c_int
 
     def run(x, n_mels, fb=None, window=None, f_min=20.0, f_max=8000.0, reflect=True, log=True,
-            gather=None, rounds=False):
-        """gather = (first_offset, stride, W, window_len) treats x as a 1-D song."""
+            gather=None, rounds=False, static_mel=False):
+        """gather = (first_offset, stride, W, window_len) treats x as a 1-D song.  rounds / static_mel pick
+        the mel stage of the independent-warp kernel / the hybrid generated-code stage (baked P0 table)."""
         x = np.ascontiguousarray(x, np.float32)
         if gather is None:
             B, N = x.shape
@@ -114,7 +117,8 @@ def emu_lib():
         fbp = fb.ctypes.data_as(fp) if fb is not None else None
         wp = window.ctypes.data_as(fp) if window is not None else None
         rc = lib.bhmel_emu_forward(x.ctypes.data_as(fp), B, N, stride, row0, n_total, n_mels, fbp, wp,
-                                   float(f_min), float(f_max), 16000, int(reflect), int(log), 2 if rounds else 0,
+                                   float(f_min), float(f_max), 16000, int(reflect), int(log),
+                                   (2 if rounds else 0) | (4 if static_mel else 0),
                                    y.ctypes.data_as(fp))
         assert rc == 0
         return y

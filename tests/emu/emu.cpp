@@ -12,6 +12,16 @@
 #define BHMEL_HD static inline
 #include "../../beatheritage_b200/csrc/fft32_gen.h"
 #include "../../beatheritage_b200/csrc/bhmel_tables.h"
+#include "../../beatheritage_b200/csrc/bhmel_fb_baked.h"
+
+// host shims for the generated static mel stage (mel_static_gen.h is device code)
+struct float4 { float x, y, z, w; };
+#define __device__
+#define __forceinline__ inline
+static inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline float __fmul_rn(float a, float b) { return a * b; }   // built with -ffp-contract=off
+namespace bhmel { static inline float fast_log1p(float v) { return logf(1.0f + v); } }
+#include "../../beatheritage_b200/csrc/mel_static_gen.h"
 
 namespace {
 constexpr int kTileF = 32, kSpan = (kTileF - 1) * bhmel::kHop + bhmel::kNfft, kPPitch = 516, kScrPitch = 33;
@@ -31,7 +41,18 @@ extern "C" int bhmel_emu_forward(const float* x, long long B, long long N, long 
   PairTables pt = make_pairs(fb.data(), n_mels);
   RoundTables rt = make_rounds(fb.data(), n_mels);
   const bool use_rounds = (exact_log1p & 2) != 0;   // bit 1: independent-warp kernel's round tables
+  // bit 2: the warp-specialised kernel's hybrid mel stage for the baked P0 filterbank -- generated
+  // code for filters < kStaticP0Filters, pair tables of the remaining filters for the rest
+  const bool use_static = (exact_log1p & 4) != 0;
   exact_log1p &= 1;
+  PairTables pt_rem;
+  if (use_static) {
+    if (n_mels != kBakedP0Mels) return 2;
+    std::vector<uint32_t> want((size_t)kBins * n_mels, 0u);
+    for (int i = 0; i < kBakedP0Nnz; ++i) want[(size_t)kBakedP0[i][0] * n_mels + kBakedP0[i][1]] = kBakedP0[i][2];
+    if (std::memcmp(want.data(), fb.data(), want.size() * 4) != 0) return 2;   // not the baked table
+    pt_rem = make_pairs(fb.data(), n_mels, kStaticP0Filters);
+  }
 
   const long long T = N / kHop + 1;
   const int tiles_per_row = (int)((T + kTileF - 1) / kTileF);
@@ -103,7 +124,35 @@ extern "C" int bhmel_emu_forward(const float* x, long long B, long long N, long 
       for (int f = 0; f < nf; ++f) {
         const float* prow = P.data() + (size_t)f * kPPitch;
         float* yrow = y + ((r * T + t0 + f) * (long long)n_mels);
-        if (use_rounds) {
+        if (use_static) {
+          float orow[96];
+          for (int mw = 0; mw < kStaticP0Warps; ++mw)
+            mel_static_P0<false>(reinterpret_cast<const float4*>(prow), orow, mw);
+          for (int m = 0; m < kStaticP0Filters; ++m) {
+            float v = orow[m];
+            if (log_scale) v = exact_log1p ? log1pf(v) : logf(1.0f + v);
+            yrow[m] = v;
+          }
+          for (const PairDesc& d : pt_rem.pairs) {
+            const float* pa = prow + 4 * (d.g0 & 0xFFFF);
+            const float* pb = prow + 4 * ((unsigned)d.g0 >> 16);
+            const float* w = pt_rem.weights.data() + d.woff;
+            float a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+            for (int g = 0; g < d.ng; ++g)
+              for (int e = 0; e < 4; ++e) {
+                a[e] = fmaf(pa[4 * g + e], w[8 * g + e], a[e]);
+                b[e] = fmaf(pb[4 * g + e], w[8 * g + 4 + e], b[e]);
+              }
+            float va = (a[0] + a[1]) + (a[2] + a[3]), vb = (b[0] + b[1]) + (b[2] + b[3]);
+            if (log_scale) {
+              va = exact_log1p ? log1pf(va) : logf(1.0f + va);
+              vb = exact_log1p ? log1pf(vb) : logf(1.0f + vb);
+            }
+            const int ca = d.mcol & 0xFFFF, cb = (unsigned)d.mcol >> 16;
+            yrow[ca] = va;
+            if (cb != 0xFFFF) yrow[cb] = vb;
+          }
+        } else if (use_rounds) {
           for (size_t r = 0; r < rt.rounds.size(); ++r)
             for (int li = 0; li < 16; ++li) {
               const int m = (int)r * 16 + li;

@@ -109,3 +109,16 @@ def test_round_tables_dense_and_odd_filter_counts(emu_lib):
         ref = mel_oracle.mel_forward(x, fb=fb, window=window, log_scale=False, dtype=np.float64)
         assert np.array_equal(a, b)
         assert np.abs(b - ref).max() / ref.max() < 1e-5
+
+
+@pytest.mark.parametrize("log", [True, False])
+def test_static_mel_stage_is_bit_identical_to_the_generic_one(emu_lib, log):
+    """The generated straight-line mel code for the baked P0 filterbank (mel_static_gen.h, filters
+    below kStaticP0Filters) plus the pair tables of the remaining filters reproduce the generic
+    pair-table stage bit for bit -- same chains, same order, zero weights dropped."""
+    window, fb = load_params("P0")
+    for x in (signals.noise(2, 9000, 11), signals.music(6000, seed=3)[None, :], 40.0 * signals.noise(1, 3000, 5),
+              np.zeros((1, 2000), np.float32)):
+        y_gen = emu_lib(x, 80, fb=fb, window=window, log=log)
+        y_st = emu_lib(x, 80, fb=fb, window=window, log=log, static_mel=True)
+        assert np.array_equal(y_st.view(np.uint32), y_gen.view(np.uint32))

@@ -91,6 +91,33 @@ def test_kernel_variants_are_bit_identical(mods, dev, pset, shape):
     assert parity_error(y_ws, ref, log) < TARGET
 
 
+@pytest.mark.parametrize("log", [True, False])
+@pytest.mark.parametrize("shape", [(1, 513), (3, 40000), (2, 524160), (7, 4097)])
+def test_static_mel_stage_is_bit_identical_to_generic(dev, log, shape):
+    """P0's filterbank is recognised as the baked table and takes the generated mel stage
+    (BHMEL_OPT_STATIC_MEL, default on); forcing the generic stage must not change a single bit.
+    A filterbank that differs in one weight must fall back to the generic stage by itself."""
+    from beatheritage_b200 import MelSpectrogram
+    m = MelSpectrogram("torchaudio", log, 16000, 1024, 80, 128, 20, 8000, "reflect").to(dev)
+    x = signals.noise(shape[0], shape[1], 5 + shape[1])
+    y_static = run(m, x, dev)
+    m.set_static_mel(False)
+    y_generic = run(m, x, dev)
+    m.set_static_mel(True)
+    assert np.array_equal(y_static.view(np.uint32), y_generic.view(np.uint32))
+    window, fb = load_params("P0")
+    ref = mel_oracle.mel_forward(x, fb=fb, window=window, pad_mode="reflect", log_scale=log, dtype=np.float64)
+    assert parity_error(y_static, ref, log) < TARGET
+    # perturb one weight: no longer the baked table -> generic stage, result follows the new weight
+    fb2 = fb.copy()
+    fb2[100, 36] *= 1.5
+    with torch.no_grad():
+        m.transform.mel_scale.fb.copy_(torch.from_numpy(fb2))
+    y2 = run(m, x, dev)
+    ref2 = mel_oracle.mel_forward(x, fb=fb2, window=window, pad_mode="reflect", log_scale=log, dtype=np.float64)
+    assert parity_error(y2, ref2, log) < TARGET
+
+
 @pytest.mark.parametrize("offset", [0, 1, 2, 3])
 def test_unaligned_rows_use_aligned_down_tma(mods, dev, offset):
     """Rows starting 0..3 elements off a 16-byte boundary: interior tiles stay on the TMA path via

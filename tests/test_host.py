@@ -134,3 +134,40 @@ def test_shard_range_partitions_everything_once():
         assert seen == list(range(n))
     with pytest.raises(ValueError):
         seg.shard_range(10, 4, 4)
+
+
+def test_baked_filterbank_header_is_the_reference_p0_table():
+    """csrc/bhmel_fb_baked.h (committed; selects the statically scheduled mel stage at run time and feeds
+    its code generator) holds exactly the non-zeros of the reference's P0 `mel_scale.fb` buffer."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    txt = open(os.path.join(root, "beatheritage_b200", "csrc", "bhmel_fb_baked.h")).read()
+    t = np.zeros((513, 80), np.uint32)
+    ent = re.findall(r"\{(\d+), (\d+), 0x([0-9a-f]+)u\}", txt)
+    assert len(ent) == int(re.search(r"kBakedP0Nnz = (\d+)", txt).group(1)) == 1003
+    for k, m, bits in ent:
+        t[int(k), int(m)] = int(bits, 16)
+    _, fb = load_params("P0")
+    assert np.array_equal(t, fb.view(np.uint32))
+    assert np.array_equal(t, melscale_fbanks_htk(513, 20.0, 8000.0, 80, 16000).numpy().view(np.uint32))
+
+
+def test_static_mel_generator_covers_each_weight_once(tmp_path):
+    import os
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "mel_static_gen.h"
+    subprocess.run([sys.executable, os.path.join(root, "beatheritage_b200", "csrc", "gen_mel_static.py"), "-o", str(out)],
+                   check=True)
+    txt = out.read_text()
+    n_static = int(re.search(r"kStaticP0Filters = (\d+)", txt).group(1))
+    n_warps = int(re.search(r"kStaticP0Warps = (\d+)", txt).group(1))
+    assert 0 < n_static < 80 and 0 < n_warps < 8
+    _, fb = load_params("P0")
+    want = sorted(int(b) for b in fb[:, :n_static].view(np.uint32)[fb[:, :n_static] != 0])
+    got = sorted(int(h, 16) for h in re.findall(r"__uint_as_float\(0x([0-9a-f]+)u\)", txt))
+    assert got == want                                    # every non-zero weight of the static filters, once
+    assert sorted(int(f) for f in re.findall(r"orow\[(\d+)\] = ", txt)) == list(range(n_static))

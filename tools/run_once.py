@@ -14,11 +14,14 @@ ap.add_argument("--reps", type=int, default=4)
 ap.add_argument("--samples", type=int, default=524160)
 ap.add_argument("--mels", type=int, default=80)
 ap.add_argument("--variant", default=None)
+ap.add_argument("--no-static-mel", action="store_true")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 mel = MelSpectrogram("torchaudio", True, 16000, 1024, a.mels, 128, 20, 8000, "reflect").to(dev)
 if a.variant:
     mel.set_kernel_variant(a.variant)
+if a.no_static_mel:
+    mel.set_static_mel(False)
 g = torch.Generator(device=dev).manual_seed(1234)
 x = torch.rand(a.batch, a.samples, device=dev, generator=g).mul_(2).sub_(1)
 torch.cuda.synchronize()
@@ -28,4 +31,6 @@ for i in range(a.reps):
     y = mel(x)
     ev[i + 1].record()
 torch.cuda.synchronize()
-print("ms per launch:", [round(ev[i].elapsed_time(ev[i + 1]), 4) for i in range(a.reps)], "sum", float(y.sum()))
+import hashlib  # noqa: E402
+digest = hashlib.sha1(y.cpu().numpy().tobytes()).hexdigest()[:16]
+print("ms per launch:", [round(ev[i].elapsed_time(ev[i + 1]), 4) for i in range(a.reps)], "sum", float(y.sum()), "sha1", digest)
