@@ -72,6 +72,8 @@ SIGNATURES = {
     "bhmel_forward": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "bhmel_forward_ex": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, ctypes.POINTER(BhmelOutDesc), _vp]),
     "bhmel_forward_gather": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "bhmel_peak_scale_pcm16": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "bhmel_forward_gather_pcm16": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp]),
     "bhmel_forward_host": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _vp]),
     "bhmel_forward_host_ex": (ctypes.c_int, [_vp, ctypes.POINTER(BhmelHostIO), _i64, _i64, _i64]),
     "bhmel_set_option": (ctypes.c_int, [_vp, _i32, _i64]),

@@ -47,6 +47,44 @@ __global__ void bhmel_pcm16_to_f32_kernel(const int16_t* __restrict__ in, float*
   }
 }
 
+// max |pcm| over a device-resident int16 song (grid-stride, 8 samples per 128-bit load where the
+// pointer allows), then scale = 1.0f / max in float32 -- ref: data_utils.py:94-96.
+__global__ void bhmel_absmax_pcm16_kernel(const int16_t* __restrict__ in, long long n, unsigned* __restrict__ out_max) {
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+  unsigned m = 0;
+  auto upd = [&m](int v) {
+    const unsigned a = static_cast<unsigned>(v < 0 ? -v : v);   // |-32768| = 32768 fits
+    m = a > m ? a : m;
+  };
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(in);
+  long long head = ((16 - (addr & 15)) & 15) / 2;               // samples before the first 16-byte boundary
+  if (head > n) head = n;
+  for (long long i = tid; i < head; i += nthreads) upd(in[i]);
+  const long long nvec = (n - head) / 8;
+  const int4* v = reinterpret_cast<const int4*>(in + head);
+  for (long long i = tid; i < nvec; i += nthreads) {
+    const int4 q = v[i];
+    const int w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      upd(static_cast<int16_t>(w[k] & 0xFFFF));
+      upd(static_cast<int16_t>(static_cast<unsigned>(w[k]) >> 16));
+    }
+  }
+  for (long long i = head + nvec * 8 + tid; i < n; i += nthreads) upd(in[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned other = __shfl_xor_sync(0xffffffffu, m, o);
+    m = other > m ? other : m;
+  }
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out_max, m);
+}
+
+__global__ void bhmel_peak_to_scale_kernel(const unsigned* __restrict__ max_abs, float* __restrict__ scale) {
+  *scale = 1.0f / static_cast<float>(*max_abs);   // 1/0 -> +inf, like the reference's division by zero
+}
+
 struct bhmel_handle {
   int device = 0;
   int num_sms = 0;
@@ -81,6 +119,10 @@ struct bhmel_handle {
   int16_t* d_pcm[kHostSlots] = {nullptr, nullptr, nullptr};
   float* d_scales = nullptr;
   size_t cap_in = 0, cap_out = 0, cap_pcm = 0, cap_scales = 0;
+  // bhmel_peak_scale_pcm16 / bhmel_forward_gather_pcm16 (lazily created)
+  unsigned* d_peak = nullptr;
+  float* d_song = nullptr;     // float32 copy of the int16 song the gather kernel reads
+  size_t cap_song = 0;
 };
 
 namespace {
@@ -364,6 +406,8 @@ void bhmel_destroy(bhmel_handle* h) {
     if (h->d_pcm[i]) cudaFree(h->d_pcm[i]);
   }
   if (h->d_scales) cudaFree(h->d_scales);
+  if (h->d_peak) cudaFree(h->d_peak);
+  if (h->d_song) cudaFree(h->d_song);
   if (h->d_win) cudaFree(h->d_win);
   if (h->d_tw) cudaFree(h->d_tw);
   if (h->d_pairs) cudaFree(h->d_pairs);
@@ -452,6 +496,55 @@ int bhmel_forward_gather(bhmel_handle* h, const float* song, int64_t n_song, int
     return fail(BHMEL_EINVAL, "need n_song >= 0, first_offset >= 0, stride > 0");
   return launch(h, song, stride, first_offset, n_song, W, window_len, OutSpec{y, 0, 0, 0},
                 static_cast<cudaStream_t>(stream));
+}
+
+int bhmel_peak_scale_pcm16(bhmel_handle* h, const int16_t* pcm_dev, int64_t n, float* scale_dev, void* stream) {
+  if (!h) return fail(BHMEL_EINVAL, "null handle");
+  if (!pcm_dev || !scale_dev) return fail(BHMEL_EINVAL, "null data pointer");
+  if (n <= 0) return fail(BHMEL_ESHAPE, "sample count must be positive");
+  if (reinterpret_cast<uintptr_t>(pcm_dev) & 1) return fail(BHMEL_EINVAL, "pcm_dev must be 2-byte aligned");
+  if (int rc = check_device(h)) return rc;
+  std::lock_guard<std::mutex> lock(h->host_mu);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!h->d_peak) BH_CUDA(cudaMalloc(&h->d_peak, sizeof(unsigned)));
+  BH_CUDA(cudaMemsetAsync(h->d_peak, 0, sizeof(unsigned), s));
+  const long long work = (n + 8 * 256 - 1) / (8 * 256);
+  const unsigned blocks = static_cast<unsigned>(work < h->num_sms * 8 ? (work < 1 ? 1 : work) : h->num_sms * 8);
+  bhmel_absmax_pcm16_kernel<<<blocks, 256, 0, s>>>(pcm_dev, n, h->d_peak);
+  bhmel_peak_to_scale_kernel<<<1, 1, 0, s>>>(h->d_peak, scale_dev);
+  BH_CUDA(cudaGetLastError());
+  h->launches.fetch_add(2, std::memory_order_relaxed);
+  return BHMEL_OK;
+}
+
+int bhmel_forward_gather_pcm16(bhmel_handle* h, const int16_t* song_dev, int64_t n_song, const float* scale_dev,
+                               int64_t first_offset, int64_t stride, int64_t W, int64_t window_len,
+                               float* y, void* stream) {
+  if (!h) return fail(BHMEL_EINVAL, "null handle");
+  if (!song_dev) return fail(BHMEL_EINVAL, "null data pointer");
+  if (n_song <= 0 || first_offset < 0 || stride <= 0)
+    return fail(BHMEL_EINVAL, "need n_song > 0, first_offset >= 0, stride > 0");
+  if (int rc = check_device(h)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  {
+    std::lock_guard<std::mutex> lock(h->host_mu);
+    const size_t need = static_cast<size_t>(n_song) * sizeof(float);
+    if (need > h->cap_song) {
+      BH_CUDA(cudaDeviceSynchronize());   // the old scratch may still be read by a kernel in flight
+      if (h->d_song) cudaFree(h->d_song);
+      h->d_song = nullptr;
+      h->cap_song = 0;
+      BH_CUDA(cudaMalloc(&h->d_song, need));
+      h->cap_song = need;
+    }
+  }
+  const long long work = (n_song + 255) / 256;
+  const unsigned blocks = static_cast<unsigned>(work < h->num_sms * 8 ? work : h->num_sms * 8);
+  // one "row" of n_song samples: the per-row scale pointer is the song's scale (or none)
+  bhmel_pcm16_to_f32_kernel<<<blocks, 256, 0, s>>>(song_dev, h->d_song, scale_dev, n_song, n_song);
+  BH_CUDA(cudaGetLastError());
+  h->launches.fetch_add(1, std::memory_order_relaxed);
+  return launch(h, h->d_song, stride, first_offset, n_song, W, window_len, OutSpec{y, 0, 0, 0}, s);
 }
 
 int bhmel_forward_host_ex(bhmel_handle* h, const bhmel_host_io* io, int64_t B, int64_t N, int64_t x_row_stride) {

@@ -351,19 +351,56 @@ class MelSpectrogram(nn.Module):
         return out
 
     @torch.no_grad()
+    def peak_scale(self, pcm: torch.Tensor) -> torch.Tensor:
+        """`1.0 / max|pcm|` of a device-resident int16 song as a float32 CUDA scalar tensor [1] -- the
+        factor of the reference's `samples *= 1.0 / np.max(np.abs(samples))`
+        (osuT5/osuT5/dataset/data_utils.py:94-96), reduced on the device."""
+        if pcm.dim() != 1 or not pcm.is_cuda or pcm.dtype != torch.int16:
+            raise RuntimeError("peak_scale expects a 1-D int16 CUDA tensor")
+        pcm = pcm.contiguous()
+        scale = torch.empty(1, dtype=torch.float32, device=pcm.device)
+        h = self._handle_for(pcm.device)
+        with torch.cuda.device(pcm.device):
+            stream = torch.cuda.current_stream(pcm.device).cuda_stream
+            _lib.check(_lib.lib().bhmel_peak_scale_pcm16(h, pcm.data_ptr(), pcm.numel(), scale.data_ptr(), stream))
+        return scale
+
     def forward_gather(self, song: torch.Tensor, first_offset: int, stride: int, n_windows: int,
-                       window_len: int) -> torch.Tensor:
+                       window_len: int, normalize=False) -> torch.Tensor:
         """Fused segmentation + forward: window w covers song[first_offset + w*stride : ... + window_len]
         with zeros past the end of `song` -- what Preprocessor.segment materialises on the host
         (reference osuT5/osuT5/inference/preprocessor.py:58-71, 94-102) -- without ever building
-        the [W, window_len] batch.  `song` float32 CUDA [n_song]."""
+        the [W, window_len] batch.
+
+        `song`: 1-D CUDA tensor, float32, or int16 PCM kept resident at 2 bytes per sample.  For int16,
+        `normalize` selects the reference loader's peak normalisation (data_utils.py:94-96): True
+        reduces the peak on the device, a float32 CUDA tensor [1] supplies the scale, False uses 1.0;
+        sample i enters the transform as float32(pcm[i]) * scale."""
         if song.dim() != 1 or not song.is_cuda:
             raise RuntimeError("forward_gather expects a 1-D CUDA tensor")
         if self.pad_mode == "reflect" and window_len <= self.n_fft // 2:
             raise RuntimeError("window_len too short for reflect padding")
+        T = window_len // self.hop_length + 1
+        if song.dtype == torch.int16:
+            x = song.contiguous()
+            if isinstance(normalize, torch.Tensor):
+                if normalize.dtype != torch.float32 or normalize.device != x.device or normalize.numel() != 1:
+                    raise RuntimeError("normalize must be a float32 tensor with one element on the song's device")
+                scale = normalize.contiguous()
+            else:
+                scale = self.peak_scale(x) if normalize else None
+            y = torch.empty((n_windows, T, self.n_mels), dtype=torch.float32, device=x.device)
+            h = self._handle_for(x.device)
+            with torch.cuda.device(x.device):
+                stream = torch.cuda.current_stream(x.device).cuda_stream
+                _lib.check(_lib.lib().bhmel_forward_gather_pcm16(
+                    h, x.data_ptr(), x.numel(), scale.data_ptr() if scale is not None else None, first_offset,
+                    stride, n_windows, window_len, y.data_ptr(), stream))
+            return y
+        if normalize is not False:
+            raise RuntimeError("normalize applies to int16 songs only")
         x = song if song.dtype == torch.float32 else song.to(torch.float32)
         x = x.contiguous()
-        T = window_len // self.hop_length + 1
         y = torch.empty((n_windows, T, self.n_mels), dtype=torch.float32, device=x.device)
         h = self._handle_for(x.device)
         with torch.cuda.device(x.device):

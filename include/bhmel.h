@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define BHMEL_VERSION 100          /* 0.1.0 */
+#define BHMEL_VERSION 101          /* 0.1.1 */
 
 #define BHMEL_OK 0
 #define BHMEL_EINVAL 1             /* bad argument / unsupported parameter combination */
@@ -111,6 +111,26 @@ int bhmel_forward_ex(bhmel_handle* h, const float* x, int64_t B, int64_t N, int6
  * forward does.   song DEVICE float32 [n_song];  y DEVICE float32 [W][window_len/hop+1][n_mels]. */
 int bhmel_forward_gather(bhmel_handle* h, const float* song, int64_t n_song, int64_t first_offset,
                          int64_t stride, int64_t W, int64_t window_len, float* y, void* stream);
+
+/* Peak normalisation scalar of an int16 PCM song that is resident on the DEVICE (next-row N2 of
+ * SURVEY.md 8f).  Writes  scale = 1.0f / max|pcm[i]|  (float32 division, i < n) to *scale_dev --
+ * the factor of the reference's `samples *= 1.0 / np.max(np.abs(samples))` after its
+ * `.astype(np.float32)` (ref: osuT5/osuT5/dataset/data_utils.py:94-96).  An all-zero song gives
+ * +inf exactly like the reference's division by zero (its samples then become NaN).
+ * pcm_dev DEVICE int16 [n];  scale_dev DEVICE float32 [1].  Asynchronous on `stream`. */
+int bhmel_peak_scale_pcm16(bhmel_handle* h, const int16_t* pcm_dev, int64_t n, float* scale_dev, void* stream);
+
+/* bhmel_forward_gather for a song kept on the device as int16 PCM (2 bytes per sample resident
+ * instead of 4): sample i is used as  float32(pcm[i]) * *scale_dev  (scale_dev == NULL: 1.0), i.e.
+ * the reference's int16 -> float32 cast + peak normalisation (data_utils.py:94-96) followed by
+ * Preprocessor.segment/window + forward (preprocessor.py:58-71, 94-102).  The conversion runs as a
+ * bandwidth-bound pre-pass into a handle-owned float32 scratch of n_song samples (grown on demand,
+ * the only allocation this entry may make), then the fused kernel gathers the windows from it;
+ * results are bit-identical to bhmel_forward_gather on the converted song.
+ * Not re-entrant per handle (the scratch is shared); calls on one stream are ordered. */
+int bhmel_forward_gather_pcm16(bhmel_handle* h, const int16_t* song_dev, int64_t n_song, const float* scale_dev,
+                               int64_t first_offset, int64_t stride, int64_t W, int64_t window_len,
+                               float* y, void* stream);
 
 /* Same contract as bhmel_forward with HOST buffers (pinned memory recommended): chunks the
  * batch, and overlaps host->device copy, the kernel and device->host copy on private streams.

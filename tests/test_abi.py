@@ -21,7 +21,7 @@ def lib():
 def declared_functions():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(bhmel_[a-z_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(bhmel_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_header_declares_what_the_binding_binds():
@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_version_and_kernel_info(lib):
-    assert lib.bhmel_version() == 100
+    assert lib.bhmel_version() == 101
     smem, threads, tile = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
     lib.bhmel_kernel_info(ctypes.byref(smem), ctypes.byref(threads), ctypes.byref(tile))
     assert threads.value == 512 and tile.value == 32

@@ -53,7 +53,7 @@ def test_native_library_is_loaded_and_kernel_launches(mods, dev):
     assert torch.all(y == 0)                     # zero input -> exactly 0.0 (log1p(0)), SURVEY.md 0.1
     maps = open("/proc/self/maps").read()
     assert "libbhmel.so" in maps
-    assert _lib.lib().bhmel_version() == 100
+    assert _lib.lib().bhmel_version() == 101
 
 
 @pytest.mark.parametrize("name", golden_case_names())
@@ -153,6 +153,44 @@ def test_kernel_variants_gather_unaligned(mods, dev):
     seq = np.stack([np.pad(song[1:].cpu().numpy(), (0, 600000))[3 + w * 52415: 3 + w * 52415 + 262144] for w in range(9)])
     ref = mel_oracle.mel_forward(seq, fb=fb, window=window, dtype=np.float64)
     assert parity_error(outs["warp"], ref, True) < TARGET
+
+
+@pytest.mark.parametrize("n,offset", [(700001, 0), (700001, 1), (12345, 3), (7, 0), (524160 * 3, 5)])
+def test_peak_scale_of_a_resident_int16_song(mods, dev, n, offset):
+    """bhmel_peak_scale_pcm16 == float32(1) / max|pcm| as NumPy computes the reference's factor
+    (data_utils.py:94-96), for aligned and unaligned device pointers, including -32768."""
+    m = mods["P0"]
+    rng = np.random.default_rng(n + offset)
+    pcm = rng.integers(-20000, 20000, size=n + offset, dtype=np.int16)
+    pcm[offset + int(rng.integers(n))] = -32768 if n % 2 else 23456
+    t = torch.from_numpy(pcm).to(dev)[offset:]
+    scale = m.peak_scale(t).cpu().numpy()
+    want = np.float32(1.0) / np.max(np.abs(pcm[offset:].astype(np.float32)))
+    assert scale.dtype == np.float32 and scale[0] == want
+    zeros = torch.zeros(1000, dtype=torch.int16, device=dev)
+    assert np.isinf(m.peak_scale(zeros).cpu().numpy()[0])          # the reference divides by zero here too
+
+
+def test_gather_from_a_resident_int16_song_matches_the_reference_loader(mods, dev):
+    """int16 song on the device -> on-device peak -> fused convert + gather  ==  the reference's host
+    path: astype(float32), samples *= 1/max|samples| (data_utils.py:94-96), segment, forward."""
+    m = mods["P0"]
+    rng = np.random.default_rng(11)
+    pcm = (signals.music(700001, seed=4) * 9000).astype(np.int16)
+    pcm[1234] = 30000
+    samples = pcm.astype(np.float32)
+    samples *= np.float32(1.0) / np.max(np.abs(samples))
+    song_i16 = torch.from_numpy(pcm).to(dev)
+    song_f32 = torch.from_numpy(samples).to(dev)
+    for first, stride, W, wlen in ((0, 52415, 9, 262144), (3, 131040, 5, 524160), (17, 999, 40, 4000)):
+        y_ref = m.forward_gather(song_f32, first, stride, W, wlen)
+        y_auto = m.forward_gather(song_i16, first, stride, W, wlen, normalize=True)
+        y_given = m.forward_gather(song_i16, first, stride, W, wlen, normalize=m.peak_scale(song_i16))
+        assert torch.equal(y_auto, y_ref) and torch.equal(y_given, y_ref)
+    y_raw = m.forward_gather(song_i16, 0, 52415, 3, 262144)                  # normalize=False: scale 1.0
+    assert torch.equal(y_raw, m.forward_gather(song_i16.to(torch.float32), 0, 52415, 3, 262144))
+    with pytest.raises(RuntimeError):
+        m.forward_gather(song_f32, 0, 52415, 3, 262144, normalize=True)      # float songs carry no PCM scale
 
 
 @pytest.mark.parametrize("bulk", [True, False])
