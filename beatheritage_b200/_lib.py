@@ -40,6 +40,12 @@ class BhmelOutDesc(ctypes.Structure):
 
 
 OUT_F32, OUT_BF16 = 0, 1
+LAYOUT_BTC, LAYOUT_BCT = 0, 1
+
+
+class BhmelEncoderInputDesc(ctypes.Structure):
+    _fields_ = [("y", ctypes.c_void_p), ("dtype", ctypes.c_int32), ("layout", ctypes.c_int32),
+                ("cond", ctypes.c_void_p), ("n_cond", ctypes.c_int64)]
 IN_F32, IN_PCM16 = 0, 1
 
 
@@ -71,6 +77,7 @@ SIGNATURES = {
     "bhmel_num_frames": (_i64, [_vp, _i64]),
     "bhmel_forward": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "bhmel_forward_ex": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, ctypes.POINTER(BhmelOutDesc), _vp]),
+    "bhmel_forward_encoder_input": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, ctypes.POINTER(BhmelEncoderInputDesc), _vp]),
     "bhmel_forward_gather": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
     "bhmel_peak_scale_pcm16": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "bhmel_forward_gather_pcm16": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp]),

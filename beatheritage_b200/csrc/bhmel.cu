@@ -85,6 +85,63 @@ __global__ void bhmel_peak_to_scale_kernel(const unsigned* __restrict__ max_abs,
   *scale = 1.0f / static_cast<float>(*max_abs);   // 1/0 -> +inf, like the reference's division by zero
 }
 
+// ---- encoder-input assembly helpers (bhmel_forward_encoder_input); T = float or __nv_bfloat16 ----
+// BTC: y[(b*Tn + t)*C + n_mels + c] = cond[b*n_cond + c].  One thread per 16-byte chunk of a frame's
+// conditioning slice when everything is 16-byte aligned (the reference shapes: 80 + 384 channels),
+// else one thread per element.
+template <typename T, bool kVec>
+__global__ void bhmel_cond_fill_btc_kernel(T* __restrict__ y, const T* __restrict__ cond, long long rows /* B*Tn */,
+                                           long long Tn, int C, int n_mels, int n_cond) {
+  constexpr int kPer = kVec ? 16 / static_cast<int>(sizeof(T)) : 1;
+  const int per_row = n_cond / kPer;
+  const long long total = rows * per_row;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long row = i / per_row;
+    const int k = static_cast<int>(i - row * per_row);
+    const long long b = row / Tn;
+    if constexpr (kVec) {
+      const int4 v = *reinterpret_cast<const int4*>(cond + b * n_cond + k * kPer);
+      *reinterpret_cast<int4*>(y + row * C + n_mels + k * kPer) = v;
+    } else {
+      y[row * C + n_mels + k] = cond[b * n_cond + k];
+    }
+  }
+}
+
+// BCT: y[b][c][t] = mel[b][t][c] for c < n_mels (32 x 32 tile transpose through shared memory),
+// cond[b][c - n_mels] for the rest.  Grid: (tiles of 32 frames, tiles of 32 channels, B).
+template <typename T>
+__global__ void bhmel_assemble_bct_kernel(T* __restrict__ y, const T* __restrict__ mel, const T* __restrict__ cond,
+                                          long long Tn, int C, int n_mels, int n_cond) {
+  __shared__ T tile[32][33];
+  const long long b = blockIdx.z;
+  const long long t0 = static_cast<long long>(blockIdx.x) * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+  T* yb = y + b * C * Tn;
+  if (c0 < n_mels) {   // a tile that holds mel channels (n_mels need not be a multiple of 32)
+    const T* mb = mel + b * Tn * n_mels;
+    for (int j = ty; j < 32; j += 8) {
+      const long long t = t0 + j;
+      const int c = c0 + tx;
+      if (t < Tn && c < n_mels) tile[j][tx] = mb[t * n_mels + c];
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+      const int c = c0 + j;
+      const long long t = t0 + tx;
+      if (t < Tn && c < C) yb[static_cast<long long>(c) * Tn + t] = c < n_mels ? tile[tx][j] : cond[b * n_cond + (c - n_mels)];
+    }
+  } else {
+    for (int j = ty; j < 32; j += 8) {
+      const int c = c0 + j;
+      const long long t = t0 + tx;
+      if (t < Tn && c < C) yb[static_cast<long long>(c) * Tn + t] = cond[b * n_cond + (c - n_mels)];
+    }
+  }
+}
+
 struct bhmel_handle {
   int device = 0;
   int num_sms = 0;
@@ -120,6 +177,8 @@ struct bhmel_handle {
   float* d_scales = nullptr;
   size_t cap_in = 0, cap_out = 0, cap_pcm = 0, cap_scales = 0;
   // bhmel_peak_scale_pcm16 / bhmel_forward_gather_pcm16 (lazily created)
+  void* d_stage = nullptr;     // bhmel_forward_encoder_input, BCT layout: [B][T][n_mels] of the output dtype
+  size_t cap_stage = 0;
   unsigned* d_peak = nullptr;
   float* d_song = nullptr;     // float32 copy of the int16 song the gather kernel reads
   size_t cap_song = 0;
@@ -304,6 +363,31 @@ int launch(bhmel_handle* h, const float* x, long long row_stride, long long row0
   return BHMEL_OK;
 }
 
+template <typename T>
+int encoder_input_tail(bhmel_handle* h, const bhmel_encoder_input_desc* d, const T* staged, long long B, long long Tn,
+                       cudaStream_t s) {
+  const int n_mels = h->prm.n_mels, n_cond = static_cast<int>(d->n_cond), C = n_mels + n_cond;
+  T* y = static_cast<T*>(d->y);
+  const T* cond = static_cast<const T*>(d->cond);
+  if (d->layout == BHMEL_LAYOUT_BTC) {
+    if (n_cond == 0) return BHMEL_OK;
+    constexpr int kPer = 16 / static_cast<int>(sizeof(T));
+    const bool vec = n_cond % kPer == 0 && n_mels % kPer == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(cond) & 15) == 0;
+    const long long total = B * Tn * (vec ? n_cond / kPer : n_cond);
+    const long long want = (total + 255) / 256;
+    const unsigned blocks = static_cast<unsigned>(want < h->num_sms * 16 ? want : h->num_sms * 16);
+    if (vec) bhmel_cond_fill_btc_kernel<T, true><<<blocks, 256, 0, s>>>(y, cond, B * Tn, Tn, C, n_mels, n_cond);
+    else bhmel_cond_fill_btc_kernel<T, false><<<blocks, 256, 0, s>>>(y, cond, B * Tn, Tn, C, n_mels, n_cond);
+  } else {
+    const dim3 grid(static_cast<unsigned>((Tn + 31) / 32), static_cast<unsigned>((C + 31) / 32), static_cast<unsigned>(B));
+    bhmel_assemble_bct_kernel<T><<<grid, dim3(32, 8), 0, s>>>(y, staged, cond, Tn, C, n_mels, n_cond);
+  }
+  BH_CUDA(cudaGetLastError());
+  h->launches.fetch_add(1, std::memory_order_relaxed);
+  return BHMEL_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -406,6 +490,7 @@ void bhmel_destroy(bhmel_handle* h) {
     if (h->d_pcm[i]) cudaFree(h->d_pcm[i]);
   }
   if (h->d_scales) cudaFree(h->d_scales);
+  if (h->d_stage) cudaFree(h->d_stage);
   if (h->d_peak) cudaFree(h->d_peak);
   if (h->d_song) cudaFree(h->d_song);
   if (h->d_win) cudaFree(h->d_win);
@@ -488,6 +573,45 @@ int bhmel_forward_ex(bhmel_handle* h, const float* x, int64_t B, int64_t N, int6
   return launch(h, x, x_row_stride, 0, LLONG_MAX, B, N,
                 OutSpec{out->y, out->dtype == BHMEL_OUT_BF16, out->frame_pitch, out->row_pitch},
                 static_cast<cudaStream_t>(stream));
+}
+
+int bhmel_forward_encoder_input(bhmel_handle* h, const float* x, int64_t B, int64_t N, int64_t x_row_stride,
+                                const bhmel_encoder_input_desc* d, void* stream) {
+  if (!h) return fail(BHMEL_EINVAL, "null handle");
+  if (!d || !d->y) return fail(BHMEL_EINVAL, "null output descriptor / pointer");
+  if (x_row_stride < N) return fail(BHMEL_EINVAL, "x_row_stride must be >= N");
+  if (d->dtype != BHMEL_OUT_F32 && d->dtype != BHMEL_OUT_BF16) return fail(BHMEL_EINVAL, "unknown output dtype");
+  if (d->layout != BHMEL_LAYOUT_BTC && d->layout != BHMEL_LAYOUT_BCT) return fail(BHMEL_EINVAL, "unknown layout");
+  if (d->n_cond < 0 || d->n_cond > 65536) return fail(BHMEL_EINVAL, "n_cond out of range");
+  if (d->n_cond > 0 && !d->cond) return fail(BHMEL_EINVAL, "null conditioning pointer");
+  if (B > 65535 && d->layout == BHMEL_LAYOUT_BCT) return fail(BHMEL_ESHAPE, "batch too large for the BCT layout");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool bf16 = d->dtype == BHMEL_OUT_BF16;
+  const long long Tn = N / bhmel::kHop + 1;
+  const long long C = h->prm.n_mels + d->n_cond;
+  const void* staged = nullptr;
+  if (d->layout == BHMEL_LAYOUT_BTC) {
+    if (int rc = launch(h, x, x_row_stride, 0, LLONG_MAX, B, N, OutSpec{d->y, bf16 ? 1 : 0, C, Tn * C}, s)) return rc;
+  } else {
+    if (B <= 0 || N <= 0) return fail(BHMEL_ESHAPE, "batch and sample count must be positive");
+    if (int rc = check_device(h)) return rc;
+    {
+      std::lock_guard<std::mutex> lock(h->host_mu);
+      const size_t need = static_cast<size_t>(B) * Tn * h->prm.n_mels * (bf16 ? 2 : 4);
+      if (need > h->cap_stage) {
+        BH_CUDA(cudaDeviceSynchronize());   // the old scratch may still be in use by kernels in flight
+        if (h->d_stage) cudaFree(h->d_stage);
+        h->d_stage = nullptr;
+        h->cap_stage = 0;
+        BH_CUDA(cudaMalloc(&h->d_stage, need));
+        h->cap_stage = need;
+      }
+    }
+    if (int rc = launch(h, x, x_row_stride, 0, LLONG_MAX, B, N, OutSpec{h->d_stage, bf16 ? 1 : 0, 0, 0}, s)) return rc;
+    staged = h->d_stage;
+  }
+  if (bf16) return encoder_input_tail<__nv_bfloat16>(h, d, static_cast<const __nv_bfloat16*>(staged), B, Tn, s);
+  return encoder_input_tail<float>(h, d, static_cast<const float*>(staged), B, Tn, s);
 }
 
 int bhmel_forward_gather(bhmel_handle* h, const float* song, int64_t n_song, int64_t first_offset,

@@ -311,6 +311,47 @@ class MelSpectrogram(nn.Module):
         return out
 
     @torch.no_grad()
+    def forward_encoder_input(self, samples: torch.Tensor, conds=(), dtype: torch.dtype = torch.bfloat16,
+                              channels_first: bool = False) -> torch.Tensor:
+        """The encoder input the reference assembles after the frontend
+        (modeling_mapperatorinator.py:351-352, 368-376), in one go:
+
+            frames = self(samples).to(dtype)
+            x = torch.concatenate([frames] + [c.unsqueeze(1).expand(-1, T, -1) for c in conds], dim=-1)
+            x = torch.swapaxes(x, 1, 2).contiguous()          # only if channels_first
+
+        `conds`: the conditioning embeddings, each [B, D_i] (any float dtype; converted to `dtype`
+        like torch.concatenate would require them to be).  Returns [B, T, C] or [B, C, T] with
+        C = n_mels + sum(D_i); bit-identical to the torch ops above."""
+        self._check_input(samples)
+        if not samples.is_cuda:
+            raise RuntimeError("forward_encoder_input expects a CUDA tensor")
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise RuntimeError("dtype must be float32 or bfloat16")
+        B, N = samples.shape
+        T = N // self.hop_length + 1
+        conds = [conds] if isinstance(conds, torch.Tensor) else list(conds)
+        for c in conds:
+            if c.dim() != 2 or c.shape[0] != B or c.device != samples.device:
+                raise RuntimeError("every conditioning tensor must be [B, D] on the samples' device")
+        cond = torch.cat([c.to(dtype) for c in conds], dim=1).contiguous() if conds else None
+        n_cond = cond.shape[1] if cond is not None else 0
+        C = self.n_mels + n_cond
+        out = torch.empty((B, C, T) if channels_first else (B, T, C), dtype=dtype, device=samples.device)
+        x = samples if samples.dtype == torch.float32 else samples.to(torch.float32)
+        if x.stride(1) != 1 or (B > 1 and x.stride(0) < N):
+            x = x.contiguous()
+        h = self._handle_for(x.device)
+        desc = _lib.BhmelEncoderInputDesc(out.data_ptr(), _lib.OUT_BF16 if dtype == torch.bfloat16 else _lib.OUT_F32,
+                                          _lib.LAYOUT_BCT if channels_first else _lib.LAYOUT_BTC,
+                                          cond.data_ptr() if cond is not None else None, n_cond)
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            _lib.check(_lib.lib().bhmel_forward_encoder_input(h, x.data_ptr(), B, N, x.stride(0) if B > 1 else N,
+                                                              ctypes.byref(desc), stream))
+        return out
+
+    @torch.no_grad()
     def forward_host(self, samples: torch.Tensor, out: torch.Tensor | None = None, device: int | None = None,
                      scales: torch.Tensor | None = None, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
         """End-to-end call for HOST batches (reference osuT5/dataloading.py:128-130 calls the module

@@ -104,6 +104,31 @@ typedef struct bhmel_out_desc {
 int bhmel_forward_ex(bhmel_handle* h, const float* x, int64_t B, int64_t N, int64_t x_row_stride,
                      const bhmel_out_desc* out, void* stream);
 
+/* Encoder-input assembly (next-row N1 of SURVEY.md 8f).  Replaces, after MelSpectrogram.forward,
+ *   frames = frames.to(dtype); conds_expanded = [c.unsqueeze(1).expand(-1, T, -1) ...];
+ *   inputs_embeds = torch.concatenate([frames] + conds_expanded, dim=-1)       -> layout BTC
+ *   inputs_embeds = torch.swapaxes(inputs_embeds, 1, 2)                        -> layout BCT
+ * (ref: osuT5/osuT5/model/modeling_mapperatorinator.py:351-352, 368-376): the mel channels are
+ * written once, already converted, into channels 0..n_mels-1 of the [B][T][C] / [B][C][T] buffer
+ * (C = n_mels + n_cond) and the conditioning vector of each batch row is broadcast over its T
+ * frames into channels n_mels..C-1, so the dtype cast, expand, concatenate and transpose passes
+ * over the encoder input disappear.  Bit-identical to those torch ops. */
+#define BHMEL_LAYOUT_BTC 0   /* [B][T][C] channels last  (what torch.concatenate builds)              */
+#define BHMEL_LAYOUT_BCT 1   /* [B][C][T] channels first (contiguous form of the swapaxes view)      */
+typedef struct bhmel_encoder_input_desc {
+  void* y;            /* DEVICE, contiguous B*T*C elements of dtype in `layout`                      */
+  int32_t dtype;      /* BHMEL_OUT_F32 or BHMEL_OUT_BF16                                              */
+  int32_t layout;     /* BHMEL_LAYOUT_BTC or BHMEL_LAYOUT_BCT                                         */
+  const void* cond;   /* DEVICE [B][n_cond] of dtype: the concatenated conditioning embeddings; NULL
+                         only if n_cond == 0                                                          */
+  int64_t n_cond;     /* >= 0                                                                          */
+} bhmel_encoder_input_desc;
+/* BTC: the fused kernel stores straight into y (pitched), one broadcast-fill kernel follows.
+ * BCT: the fused kernel stores [B][T][n_mels] of dtype into a handle-owned scratch (grown on demand;
+ * not re-entrant per handle), one assembly kernel transposes it and fills the conditioning rows. */
+int bhmel_forward_encoder_input(bhmel_handle* h, const float* x, int64_t B, int64_t N, int64_t x_row_stride,
+                                const bhmel_encoder_input_desc* out, void* stream);
+
 /* Fused segmentation + forward.  Replaces Preprocessor.segment/window followed by forward
  * (ref: osuT5/osuT5/inference/preprocessor.py:58-71, 94-102): window w (0 <= w < W) covers
  * song[first_offset + w*stride ... + window_len), samples at or beyond n_song read as zero

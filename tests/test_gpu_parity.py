@@ -364,6 +364,28 @@ def test_forward_into_typed_pitched_output(mods, dev, variant):
         m.forward_into(x, torch.empty(3, T, 60, device=dev))
 
 
+@pytest.mark.parametrize("channels_first", [False, True])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("pset,shape,dims", [("P0", (3, 40000), (128, 128, 64, 64)), ("P0", (2, 524160), (384,)),
+                                             ("P128", (2, 9999), (5, 3)), ("P0", (1, 4097), ())])
+def test_encoder_input_assembly_matches_the_reference_ops(mods, dev, pset, shape, dims, dtype, channels_first):
+    """bhmel_forward_encoder_input == frames.to(dtype) + expand + concatenate (+ swapaxes) of
+    modeling_mapperatorinator.py:351-352, 368-376, bit for bit, for both layouts and dtypes,
+    vectorisable (80 + 384) and odd (128 + 5 + 3) channel counts, and no conditioning at all."""
+    m = mods[pset]
+    x = torch.from_numpy(signals.noise(shape[0], shape[1], 3 + shape[1])).to(dev)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    conds = [torch.randn(shape[0], d, generator=g).to(dev) for d in dims]
+    frames = m(x).to(dtype)
+    T = frames.shape[1]
+    want = torch.concatenate([frames] + [c.to(dtype).unsqueeze(1).expand(-1, T, -1) for c in conds], dim=-1)
+    if channels_first:
+        want = torch.swapaxes(want, 1, 2).contiguous()
+    got = m.forward_encoder_input(x, conds, dtype=dtype, channels_first=channels_first)
+    assert got.shape == want.shape and got.dtype == dtype and got.is_contiguous()
+    assert torch.equal(got, want)
+
+
 def test_state_dict_reload_rebuilds_device_tables(dev):
     from beatheritage_b200 import MelSpectrogram
     m = MelSpectrogram("torchaudio", False, 16000, 1024, 80, 128, 20, 8000, "reflect").to(dev)
