@@ -45,7 +45,7 @@ LAYOUT_BTC, LAYOUT_BCT = 0, 1
 
 class BhmelEncoderInputDesc(ctypes.Structure):
     _fields_ = [("y", ctypes.c_void_p), ("dtype", ctypes.c_int32), ("layout", ctypes.c_int32),
-                ("cond", ctypes.c_void_p), ("n_cond", ctypes.c_int64)]
+                ("cond", ctypes.c_void_p), ("n_cond", ctypes.c_int64), ("scratch", ctypes.c_void_p)]
 IN_F32, IN_PCM16 = 0, 1
 
 
@@ -80,7 +80,7 @@ SIGNATURES = {
     "bhmel_forward_encoder_input": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, ctypes.POINTER(BhmelEncoderInputDesc), _vp]),
     "bhmel_forward_gather": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
     "bhmel_peak_scale_pcm16": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),
-    "bhmel_forward_gather_pcm16": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "bhmel_forward_gather_pcm16": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
     "bhmel_forward_host": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _vp]),
     "bhmel_forward_host_ex": (ctypes.c_int, [_vp, ctypes.POINTER(BhmelHostIO), _i64, _i64, _i64]),
     "bhmel_set_option": (ctypes.c_int, [_vp, _i32, _i64]),

@@ -595,7 +595,8 @@ int bhmel_forward_encoder_input(bhmel_handle* h, const float* x, int64_t B, int6
   } else {
     if (B <= 0 || N <= 0) return fail(BHMEL_ESHAPE, "batch and sample count must be positive");
     if (int rc = check_device(h)) return rc;
-    {
+    void* stage = d->scratch;
+    if (!stage) {
       std::lock_guard<std::mutex> lock(h->host_mu);
       const size_t need = static_cast<size_t>(B) * Tn * h->prm.n_mels * (bf16 ? 2 : 4);
       if (need > h->cap_stage) {
@@ -606,9 +607,10 @@ int bhmel_forward_encoder_input(bhmel_handle* h, const float* x, int64_t B, int6
         BH_CUDA(cudaMalloc(&h->d_stage, need));
         h->cap_stage = need;
       }
+      stage = h->d_stage;
     }
-    if (int rc = launch(h, x, x_row_stride, 0, LLONG_MAX, B, N, OutSpec{h->d_stage, bf16 ? 1 : 0, 0, 0}, s)) return rc;
-    staged = h->d_stage;
+    if (int rc = launch(h, x, x_row_stride, 0, LLONG_MAX, B, N, OutSpec{stage, bf16 ? 1 : 0, 0, 0}, s)) return rc;
+    staged = stage;
   }
   if (bf16) return encoder_input_tail<__nv_bfloat16>(h, d, static_cast<const __nv_bfloat16*>(staged), B, Tn, s);
   return encoder_input_tail<float>(h, d, static_cast<const float*>(staged), B, Tn, s);
@@ -643,14 +645,14 @@ int bhmel_peak_scale_pcm16(bhmel_handle* h, const int16_t* pcm_dev, int64_t n, f
 
 int bhmel_forward_gather_pcm16(bhmel_handle* h, const int16_t* song_dev, int64_t n_song, const float* scale_dev,
                                int64_t first_offset, int64_t stride, int64_t W, int64_t window_len,
-                               float* y, void* stream) {
+                               float* y, float* scratch, void* stream) {
   if (!h) return fail(BHMEL_EINVAL, "null handle");
   if (!song_dev) return fail(BHMEL_EINVAL, "null data pointer");
   if (n_song <= 0 || first_offset < 0 || stride <= 0)
     return fail(BHMEL_EINVAL, "need n_song > 0, first_offset >= 0, stride > 0");
   if (int rc = check_device(h)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  {
+  if (!scratch) {
     std::lock_guard<std::mutex> lock(h->host_mu);
     const size_t need = static_cast<size_t>(n_song) * sizeof(float);
     if (need > h->cap_song) {
@@ -661,14 +663,15 @@ int bhmel_forward_gather_pcm16(bhmel_handle* h, const int16_t* song_dev, int64_t
       BH_CUDA(cudaMalloc(&h->d_song, need));
       h->cap_song = need;
     }
+    scratch = h->d_song;
   }
   const long long work = (n_song + 255) / 256;
   const unsigned blocks = static_cast<unsigned>(work < h->num_sms * 8 ? work : h->num_sms * 8);
   // one "row" of n_song samples: the per-row scale pointer is the song's scale (or none)
-  bhmel_pcm16_to_f32_kernel<<<blocks, 256, 0, s>>>(song_dev, h->d_song, scale_dev, n_song, n_song);
+  bhmel_pcm16_to_f32_kernel<<<blocks, 256, 0, s>>>(song_dev, scratch, scale_dev, n_song, n_song);
   BH_CUDA(cudaGetLastError());
   h->launches.fetch_add(1, std::memory_order_relaxed);
-  return launch(h, h->d_song, stride, first_offset, n_song, W, window_len, OutSpec{y, 0, 0, 0}, s);
+  return launch(h, scratch, stride, first_offset, n_song, W, window_len, OutSpec{y, 0, 0, 0}, s);
 }
 
 int bhmel_forward_host_ex(bhmel_handle* h, const bhmel_host_io* io, int64_t B, int64_t N, int64_t x_row_stride) {

@@ -342,9 +342,12 @@ class MelSpectrogram(nn.Module):
         if x.stride(1) != 1 or (B > 1 and x.stride(0) < N):
             x = x.contiguous()
         h = self._handle_for(x.device)
+        # channels first stages [B, T, n_mels] first; the torch allocator keeps that stream-ordered / thread-safe
+        scratch = torch.empty((B, T, self.n_mels), dtype=dtype, device=x.device) if channels_first else None
         desc = _lib.BhmelEncoderInputDesc(out.data_ptr(), _lib.OUT_BF16 if dtype == torch.bfloat16 else _lib.OUT_F32,
                                           _lib.LAYOUT_BCT if channels_first else _lib.LAYOUT_BTC,
-                                          cond.data_ptr() if cond is not None else None, n_cond)
+                                          cond.data_ptr() if cond is not None else None, n_cond,
+                                          scratch.data_ptr() if scratch is not None else None)
         with torch.cuda.device(x.device):
             stream = torch.cuda.current_stream(x.device).cuda_stream
             _lib.check(_lib.lib().bhmel_forward_encoder_input(h, x.data_ptr(), B, N, x.stride(0) if B > 1 else N,
@@ -431,12 +434,13 @@ class MelSpectrogram(nn.Module):
             else:
                 scale = self.peak_scale(x) if normalize else None
             y = torch.empty((n_windows, T, self.n_mels), dtype=torch.float32, device=x.device)
+            scratch = torch.empty(x.numel(), dtype=torch.float32, device=x.device)   # stream-ordered, thread-safe
             h = self._handle_for(x.device)
             with torch.cuda.device(x.device):
                 stream = torch.cuda.current_stream(x.device).cuda_stream
                 _lib.check(_lib.lib().bhmel_forward_gather_pcm16(
                     h, x.data_ptr(), x.numel(), scale.data_ptr() if scale is not None else None, first_offset,
-                    stride, n_windows, window_len, y.data_ptr(), stream))
+                    stride, n_windows, window_len, y.data_ptr(), scratch.data_ptr(), stream))
             return y
         if normalize is not False:
             raise RuntimeError("normalize applies to int16 songs only")

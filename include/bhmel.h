@@ -122,10 +122,12 @@ typedef struct bhmel_encoder_input_desc {
   const void* cond;   /* DEVICE [B][n_cond] of dtype: the concatenated conditioning embeddings; NULL
                          only if n_cond == 0                                                          */
   int64_t n_cond;     /* >= 0                                                                          */
+  void* scratch;      /* BCT only: DEVICE B*T*n_mels elements of dtype owned by the caller, or NULL to
+                         use a handle-owned buffer (grown on demand; then not re-entrant per handle)   */
 } bhmel_encoder_input_desc;
 /* BTC: the fused kernel stores straight into y (pitched), one broadcast-fill kernel follows.
- * BCT: the fused kernel stores [B][T][n_mels] of dtype into a handle-owned scratch (grown on demand;
- * not re-entrant per handle), one assembly kernel transposes it and fills the conditioning rows. */
+ * BCT: the fused kernel stores [B][T][n_mels] of dtype into the scratch, one assembly kernel
+ * transposes it and fills the conditioning rows. */
 int bhmel_forward_encoder_input(bhmel_handle* h, const float* x, int64_t B, int64_t N, int64_t x_row_stride,
                                 const bhmel_encoder_input_desc* out, void* stream);
 
@@ -149,13 +151,13 @@ int bhmel_peak_scale_pcm16(bhmel_handle* h, const int16_t* pcm_dev, int64_t n, f
  * instead of 4): sample i is used as  float32(pcm[i]) * *scale_dev  (scale_dev == NULL: 1.0), i.e.
  * the reference's int16 -> float32 cast + peak normalisation (data_utils.py:94-96) followed by
  * Preprocessor.segment/window + forward (preprocessor.py:58-71, 94-102).  The conversion runs as a
- * bandwidth-bound pre-pass into a handle-owned float32 scratch of n_song samples (grown on demand,
- * the only allocation this entry may make), then the fused kernel gathers the windows from it;
- * results are bit-identical to bhmel_forward_gather on the converted song.
- * Not re-entrant per handle (the scratch is shared); calls on one stream are ordered. */
+ * bandwidth-bound pre-pass into a float32 scratch of n_song samples, then the fused kernel gathers
+ * the windows from it; results are bit-identical to bhmel_forward_gather on the converted song.
+ * scratch: DEVICE float32 [n_song] owned by the caller, or NULL to use a handle-owned buffer (grown
+ * on demand -- the only allocation this entry may make -- and then not re-entrant per handle). */
 int bhmel_forward_gather_pcm16(bhmel_handle* h, const int16_t* song_dev, int64_t n_song, const float* scale_dev,
                                int64_t first_offset, int64_t stride, int64_t W, int64_t window_len,
-                               float* y, void* stream);
+                               float* y, float* scratch, void* stream);
 
 /* Same contract as bhmel_forward with HOST buffers (pinned memory recommended): chunks the
  * batch, and overlaps host->device copy, the kernel and device->host copy on private streams.

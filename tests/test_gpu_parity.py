@@ -386,6 +386,33 @@ def test_encoder_input_assembly_matches_the_reference_ops(mods, dev, pset, shape
     assert torch.equal(got, want)
 
 
+def test_handle_owned_scratch_paths_of_the_c_abi(mods, dev):
+    """The Python mirror hands the library caller-owned scratch buffers; the C entries also work with
+    scratch = NULL (handle-owned, grown on demand) and give the same bits."""
+    import ctypes
+    from beatheritage_b200 import _lib
+    m = mods["P0"]
+    lib = _lib.lib()
+    x = torch.from_numpy(signals.noise(2, 30000, 8)).to(dev)
+    cond = torch.randn(2, 24, device=dev).to(torch.bfloat16)
+    want = m.forward_encoder_input(x, [cond], channels_first=True)
+    h = m._handle_for(dev)
+    for _ in range(2):                                              # second call reuses the grown buffer
+        got = torch.empty_like(want)
+        desc = _lib.BhmelEncoderInputDesc(got.data_ptr(), _lib.OUT_BF16, _lib.LAYOUT_BCT, cond.data_ptr(), 24, None)
+        _lib.check(lib.bhmel_forward_encoder_input(h, x.data_ptr(), 2, 30000, 30000, ctypes.byref(desc),
+                                                   torch.cuda.current_stream(dev).cuda_stream))
+        assert torch.equal(got, want)
+    pcm = (signals.music(200001, seed=2) * 8000).astype(np.int16)
+    song = torch.from_numpy(pcm).to(dev)
+    want_g = m.forward_gather(song, 5, 20011, 7, 65536, normalize=True)
+    scale = m.peak_scale(song)
+    got_g = torch.empty_like(want_g)
+    _lib.check(lib.bhmel_forward_gather_pcm16(h, song.data_ptr(), song.numel(), scale.data_ptr(), 5, 20011, 7, 65536,
+                                              got_g.data_ptr(), None, torch.cuda.current_stream(dev).cuda_stream))
+    assert torch.equal(got_g, want_g)
+
+
 def test_state_dict_reload_rebuilds_device_tables(dev):
     from beatheritage_b200 import MelSpectrogram
     m = MelSpectrogram("torchaudio", False, 16000, 1024, 80, 128, 20, 8000, "reflect").to(dev)
