@@ -47,6 +47,30 @@ def melscale_fbanks_htk(n_freqs: int, f_min: float, f_max: float, n_mels: int, s
     return torch.max(torch.zeros(1), torch.min(rising, falling))
 
 
+def melscale_fbanks_slaney(n_freqs: int, f_min: float, f_max: float, n_mels: int, sample_rate: int) -> torch.Tensor:
+    """Slaney mel scale, area-normalised triangular filterbank [n_freqs, n_mels] float32 -- the
+    transpose of the `mel_basis` nnAudio's MelSpectrogram builds with its defaults `htk=False,
+    norm=1` (reference spectrogram.py:52-61 passes neither).  UNPINNED against nnAudio itself (not
+    vendored, not installable here: SURVEY.md 8c / N4); restated from the published definition
+    (linear 200/3 Hz per mel below 1 kHz, 27 mels per factor 6.4 above; each triangle scaled by
+    2 / band width in Hz; fp64 arithmetic rounded once to fp32) and held against torchaudio's
+    independent implementation of it in tests/test_host.py."""
+    f_sp, min_log_hz, logstep = 200.0 / 3, 1000.0, math.log(6.4) / 27.0
+    min_log_mel = min_log_hz / f_sp
+
+    def to_mel(f: float) -> float:
+        return min_log_mel + math.log(f / min_log_hz) / logstep if f >= min_log_hz else f / f_sp
+
+    mels = torch.linspace(to_mel(f_min), to_mel(f_max), n_mels + 2, dtype=torch.float64)
+    f_pts = torch.where(mels >= min_log_mel, min_log_hz * torch.exp(logstep * (mels - min_log_mel)), f_sp * mels)
+    all_freqs = torch.linspace(0, sample_rate / 2, n_freqs, dtype=torch.float64)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    tri = torch.clamp(torch.minimum(-slopes[:, :-2] / f_diff[:-1], slopes[:, 2:] / f_diff[1:]), min=0.0)
+    tri = tri.to(torch.float32).to(torch.float64)                 # the triangles are stored in fp32 first
+    return (tri * (2.0 / (f_pts[2:] - f_pts[:-2])).unsqueeze(0)).to(torch.float32)
+
+
 class _WindowHolder(nn.Module):
     """Carries the `window` buffer under the name torchaudio's Spectrogram uses."""
 
@@ -96,10 +120,77 @@ def _(samples, module_key, n_mels):
 
 
 # ----------------------------------------------------------------------------------------
+# State dict in nnAudio's layout (implementation="nnAudio", nnaudio_arithmetic="published").
+# nnAudio 0.3.x registers (names restated from its published source, UNPINNED like the rest of N4):
+#   transform.mel_basis         [n_mels, n_fft/2+1]     the filterbank, mel-major
+#   transform.stft.wsin / wcos  [n_fft/2+1, 1, n_fft]   sin / cos DFT kernels times the window
+#   transform.stft.window_mask  [1, n_fft, 1]           the window
+# The kernel keeps working from `fb` [n_fft/2+1, n_mels] and `window` [n_fft]; the hooks translate.
+# ----------------------------------------------------------------------------------------
+def _dft_kernels(window: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    n_fft = window.numel()
+    ang = 2 * math.pi * torch.arange(n_fft // 2 + 1, dtype=torch.float64).unsqueeze(1) \
+        * torch.arange(n_fft, dtype=torch.float64) / n_fft
+    w = window.detach().to("cpu", torch.float32)
+    return ((torch.sin(ang).to(torch.float32) * w).unsqueeze(1), (torch.cos(ang).to(torch.float32) * w).unsqueeze(1))
+
+
+def _nnaudio_save_hook(module, state_dict, prefix, local_metadata):
+    fb = state_dict.pop(prefix + "transform.mel_scale.fb")
+    window = state_dict.pop(prefix + "transform.spectrogram.window")
+    wsin, wcos = _dft_kernels(window)
+    state_dict[prefix + "transform.mel_basis"] = fb.t().contiguous()
+    state_dict[prefix + "transform.stft.wsin"] = wsin.to(window.device)
+    state_dict[prefix + "transform.stft.wcos"] = wcos.to(window.device)
+    state_dict[prefix + "transform.stft.window_mask"] = window.reshape(1, -1, 1)
+
+
+def _nnaudio_load_hook(module, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+    """Accept nnAudio's buffers: `mel_basis` becomes `fb`, the window is read back from the k = 0 row
+    of `wcos` (cos 0 = 1) or from `window_mask`, and every other `transform.*` key nnAudio may carry
+    (wsin, inverse kernels) is consumed after checking that the kernels are the plain windowed DFT
+    -- a *trained* STFT (nnAudio trainable_STFT) is not what the FFT kernel computes."""
+    tp = prefix + "transform."
+    ours = {tp + "spectrogram.window", tp + "mel_scale.fb"}
+    theirs = [k for k in state_dict if k.startswith(tp) and k not in ours]
+    if not theirs:
+        return
+    got = {k[len(tp):]: state_dict.pop(k) for k in theirs}
+    n_fft, n_bins = module.n_fft, module.n_fft // 2 + 1
+    if "mel_basis" in got:
+        mb = got["mel_basis"]
+        if tuple(mb.shape) != (module.n_mels, n_bins):
+            error_msgs.append(f"{tp}mel_basis: expected shape {(module.n_mels, n_bins)}, got {tuple(mb.shape)}")
+            return
+        state_dict[tp + "mel_scale.fb"] = mb.detach().to(torch.float32).t().contiguous()
+    window = None
+    if "stft.wcos" in got and tuple(got["stft.wcos"].shape) == (n_bins, 1, n_fft):
+        window = got["stft.wcos"][0, 0, :].detach().to(torch.float32).clone()
+    elif "stft.window_mask" in got and got["stft.window_mask"].numel() == n_fft:
+        window = got["stft.window_mask"].detach().to(torch.float32).reshape(n_fft).clone()
+    if window is not None:
+        if "stft.wcos" in got and "stft.wsin" in got:
+            wsin, wcos = _dft_kernels(window)
+            dev = max(float((got["stft.wsin"].detach().cpu().float() - wsin).abs().max()),
+                      float((got["stft.wcos"].detach().cpu().float() - wcos).abs().max()))
+            if dev > 1e-4:
+                error_msgs.append(f"{tp}stft.wsin/wcos are not window * sin/cos(2 pi k n / n_fft) (max deviation "
+                                  f"{dev:.3g}): a trained STFT is not supported by the FFT kernel")
+                return
+        state_dict[tp + "spectrogram.window"] = window
+
+
+# ----------------------------------------------------------------------------------------
 class MelSpectrogram(nn.Module):
     #: nnAudio arithmetic cannot be pinned (the package is neither vendored in the reference nor
-    #: installed here); set True to map implementation="nnAudio" onto the
-    #: torchaudio arithmetic instead of raising.
+    #: installed here, SURVEY.md 8c), so implementation="nnAudio" raises unless the integrator opts in:
+    #:   nnaudio_arithmetic = "published"   nnAudio's published defaults (Slaney scale, area-normalised
+    #:       filterbank `melscale_fbanks_slaney`, periodic Hann conv-STFT == windowed DFT), state dict
+    #:       under nnAudio's buffer names; buffers loaded from a checkpoint replace the restated tables,
+    #:       so a checkpoint that carries `mel_basis` / `wcos` pins the arithmetic by itself;
+    #:   nnaudio_arithmetic = "torchaudio"  (or the older allow_nnaudio_as_torchaudio = True) the
+    #:       torchaudio arithmetic (htk, no normalisation) with these parameters.
+    nnaudio_arithmetic: str | None = None
     allow_nnaudio_as_torchaudio = False
 
     def __init__(
@@ -120,11 +211,15 @@ class MelSpectrogram(nn.Module):
         sample_rate, n_ftt (STFT size), n_mels, hop_length, f_min, f_max, pad_mode."""
         super().__init__()
         assert implementation in ["torchaudio", "nnAudio"], f"Unsupported implementation: {implementation}"
-        if implementation == "nnAudio" and not self.allow_nnaudio_as_torchaudio:
-            raise NotImplementedError(
-                "implementation='nnAudio': nnAudio's arithmetic is unpinned (not vendored by the reference, "
-                "not installable offline); set MelSpectrogram.allow_nnaudio_as_torchaudio = True to use the "
-                "torchaudio arithmetic with these parameters instead")
+        mode = None
+        if implementation == "nnAudio":
+            mode = self.nnaudio_arithmetic or ("torchaudio" if self.allow_nnaudio_as_torchaudio else None)
+            if mode not in ("published", "torchaudio"):
+                raise NotImplementedError(
+                    "implementation='nnAudio': nnAudio's arithmetic is unpinned (not vendored by the reference, "
+                    "not installable offline); set MelSpectrogram.nnaudio_arithmetic = 'published' for nnAudio's "
+                    "published defaults (Slaney filterbank; buffers from a checkpoint take precedence) or "
+                    "'torchaudio' for the torchaudio arithmetic with these parameters")
         if n_ftt != N_FFT or hop_length != HOP:
             raise ValueError(
                 f"the sm_100a kernel is compiled for n_ftt={N_FFT}, hop_length={HOP} (constant in every reference "
@@ -140,8 +235,17 @@ class MelSpectrogram(nn.Module):
         self.f_min = f_min
         self.f_max = f_max
         self.pad_mode = pad_mode
-        fb = melscale_fbanks_htk(n_ftt // 2 + 1, float(f_min), float(f_max), n_mels, sample_rate)
+        self._nnaudio_layout = mode == "published"
+        make_fb = melscale_fbanks_slaney if self._nnaudio_layout else melscale_fbanks_htk
+        fb = make_fb(n_ftt // 2 + 1, float(f_min), float(f_max), n_mels, sample_rate)
         self.transform = _Transform(n_ftt, fb)
+        if self._nnaudio_layout:
+            # scipy.signal.get_window("hann", n_fft, fftbins=True).astype(float32): fp64 arithmetic rounded
+            # once, a few 1e-9 away from torch.hann_window's fp32 evaluation
+            n = torch.arange(n_ftt, dtype=torch.float64)
+            self.transform.spectrogram.window.copy_((0.5 - 0.5 * torch.cos(2 * math.pi * n / n_ftt)).to(torch.float32))
+            self.register_load_state_dict_pre_hook(_nnaudio_load_hook)
+            self.register_state_dict_post_hook(_nnaudio_save_hook)
         self._handles: dict[int, int] = {}        # device index -> bhmel_handle*
         self._stamp: dict[int, tuple] = {}        # device index -> buffer versions the handle was built from
         self._bulk = True

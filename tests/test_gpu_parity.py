@@ -441,6 +441,41 @@ def test_dense_filterbank_from_state_dict(dev):
     assert np.abs(y - ref).max() / ref.max() < 1e-5
 
 
+@pytest.mark.parametrize("args,shape", [
+    (("nnAudio", False, 16000, 1024, 388, 128, 0, 8000, "constant"), (2, 40000)),    # configs/model/default.yaml:19-27
+    (("nnAudio", True, 16000, 1024, 128, 128, 20, 8000, "reflect"), (3, 9999)),
+    (("nnAudio", False, 16000, 1024, 512, 128, 0, 8000, "constant"), (1, 524160)),   # 47 all-zero filters
+])
+def test_nnaudio_published_arithmetic(dev, monkeypatch, args, shape):
+    """N4, parity UNPINNED against nnAudio itself: the module in nnAudio mode against
+    the restatement of nnAudio's published conv-STFT + Slaney basis (oracle/nnaudio_oracle.py), and a
+    state-dict round trip in nnAudio's buffer layout."""
+    from beatheritage_b200 import MelSpectrogram
+    from oracle import nnaudio_oracle
+    monkeypatch.setattr(MelSpectrogram, "nnaudio_arithmetic", "published")
+    _, log, _, _, n_mels, _, f_min, f_max, pad = args
+    m = MelSpectrogram(*args).to(dev)
+    x = signals.noise(shape[0], shape[1], 31 + n_mels)
+    y = run(m, x, dev)
+    x_ref, y_cmp = (x, y) if shape[1] < 100000 else (x[:, :40000], y[:, :300])    # conv form is O(T * 513 * 1024)
+    ref = nnaudio_oracle.mel_forward(x_ref, n_mels=n_mels, f_min=f_min, f_max=f_max, pad_mode=pad, log_scale=log)
+    ref = ref[:, :y_cmp.shape[1]]
+    assert y.shape == (shape[0], shape[1] // 128 + 1, n_mels)
+    assert parity_error(y_cmp, ref, log) < TARGET
+    assert np.abs(y_cmp - ref).max() <= 1e-4 * np.abs(ref).max()                # SURVEY.md 8c bar for non-log sets
+    dead = ~nnaudio_oracle.mel_basis(16000, 1024, n_mels, f_min, f_max).any(axis=1)
+    assert np.all(y[..., dead] == 0)
+    m2 = MelSpectrogram(*args).to(dev)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    sd["transform.mel_basis"] *= 2.0
+    m2.load_state_dict(sd, strict=True)
+    y2 = run(m2, x, dev)
+    if log:
+        assert np.allclose(np.expm1(y2.astype(np.float64)), 2.0 * np.expm1(y.astype(np.float64)), rtol=5e-5, atol=5e-5)
+    else:
+        assert np.array_equal(y2, 2.0 * y)
+
+
 def test_runs_on_a_side_stream_and_under_autocast(mods, dev):
     m = mods["P0"]
     x = torch.from_numpy(signals.noise(2, 30000, 8)).to(dev)

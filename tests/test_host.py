@@ -71,7 +71,7 @@ def test_errors_mirror_the_reference():
     with pytest.raises(AssertionError):
         MelSpectrogram("librosa")                             # spectrogram.py:35
     with pytest.raises(NotImplementedError):
-        MelSpectrogram()                                      # nnAudio arithmetic is unpinned
+        MelSpectrogram()                                      # nnAudio arithmetic is unpinned: opt-in only
     with pytest.raises(ValueError):
         MelSpectrogram("torchaudio", True, 16000, 2048)
     m = MelSpectrogram(*P0)
@@ -171,3 +171,87 @@ def test_static_mel_generator_covers_each_weight_once(tmp_path):
     got = sorted(int(h, 16) for h in re.findall(r"__uint_as_float\(0x([0-9a-f]+)u\)", txt))
     assert got == want                                    # every non-zero weight of the static filters, once
     assert sorted(int(f) for f in re.findall(r"orow\[(\d+)\] = ", txt)) == list(range(n_static))
+
+
+# ---------------------------------------------------------------------------------------------
+# N4: implementation="nnAudio" (reference spectrogram.py:50-61), opt-in, parity unpinned
+# ---------------------------------------------------------------------------------------------
+NNAUDIO_P1 = ("nnAudio", False, 16000, 1024, 388, 128, 0, 8000, "constant")   # configs/model/default.yaml:19-27
+
+
+@pytest.fixture
+def nnaudio_published(monkeypatch):
+    monkeypatch.setattr(MelSpectrogram, "nnaudio_arithmetic", "published")
+
+
+def test_nnaudio_is_opt_in_and_the_older_flag_still_maps_to_torchaudio(monkeypatch):
+    with pytest.raises(NotImplementedError, match="nnaudio_arithmetic"):
+        MelSpectrogram(*NNAUDIO_P1)
+    monkeypatch.setattr(MelSpectrogram, "allow_nnaudio_as_torchaudio", True)
+    m = MelSpectrogram(*NNAUDIO_P1)
+    assert list(m.state_dict()) == ["transform.spectrogram.window", "transform.mel_scale.fb"]
+    _, fb = load_params("P1")
+    assert torch.equal(m.transform.mel_scale.fb, torch.from_numpy(fb))
+
+
+def test_nnaudio_published_filterbank_and_state_dict_layout(nnaudio_published):
+    from beatheritage_b200.spectrogram import melscale_fbanks_slaney
+    from oracle import nnaudio_oracle
+    m = MelSpectrogram(*NNAUDIO_P1)
+    basis = nnaudio_oracle.mel_basis(16000, 1024, 388, 0.0, 8000.0)
+    assert np.array_equal(m.transform.mel_scale.fb.numpy(), basis.T)             # two independent codings agree
+    assert np.array_equal(melscale_fbanks_slaney(513, 20.0, 8000.0, 80, 16000).numpy(),
+                          nnaudio_oracle.mel_basis(16000, 1024, 80, 20.0, 8000.0).T)
+    sd = m.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == {
+        "transform.mel_basis": (388, 513), "transform.stft.wsin": (513, 1, 1024),
+        "transform.stft.wcos": (513, 1, 1024), "transform.stft.window_mask": (1, 1024, 1)}
+    wsin, wcos, window = nnaudio_oracle.fourier_kernels()
+    assert np.array_equal(sd["transform.mel_basis"].numpy(), basis)
+    assert np.abs(sd["transform.stft.wsin"].numpy() - wsin).max() < 1e-6
+    assert np.abs(sd["transform.stft.wcos"].numpy() - wcos).max() < 1e-6
+    assert np.array_equal(sd["transform.stft.window_mask"].numpy().reshape(-1), window)
+
+
+def test_nnaudio_checkpoint_buffers_load_strictly_and_take_precedence(nnaudio_published):
+    class Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.spectrogram = MelSpectrogram(*NNAUDIO_P1)
+    src = Model()
+    sd = src.state_dict()
+    assert list(sd) == ["spectrogram.transform.mel_basis", "spectrogram.transform.stft.wsin",
+                        "spectrogram.transform.stft.wcos", "spectrogram.transform.stft.window_mask"]
+    # a checkpoint with its own tables: scaled basis, a different (still plain-DFT) window, inverse kernels
+    win = torch.hamming_window(1024)
+    ang = 2 * np.pi * torch.arange(513, dtype=torch.float64)[:, None] * torch.arange(1024, dtype=torch.float64) / 1024
+    sd["spectrogram.transform.mel_basis"] = sd["spectrogram.transform.mel_basis"] * 3
+    sd["spectrogram.transform.stft.wcos"] = (torch.cos(ang).float() * win)[:, None]
+    sd["spectrogram.transform.stft.wsin"] = (torch.sin(ang).float() * win)[:, None]
+    sd["spectrogram.transform.stft.window_mask"] = win.reshape(1, -1, 1)
+    sd["spectrogram.transform.stft.kernel_sin_inv"] = torch.zeros(513, 1024, 1)
+    dst = Model()
+    stamp = dst.spectrogram._buffer_stamp()
+    res = dst.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert torch.equal(dst.spectrogram.transform.mel_scale.fb, src.spectrogram.transform.mel_scale.fb * 3)
+    assert torch.equal(dst.spectrogram.transform.spectrogram.window, win)
+    assert dst.spectrogram._buffer_stamp() != stamp                       # device tables will be rebuilt
+    # our own layout still loads (e.g. a state dict saved before switching the module to nnAudio names)
+    dst.load_state_dict({"spectrogram.transform.spectrogram.window": torch.hann_window(1024),
+                         "spectrogram.transform.mel_scale.fb": src.spectrogram.transform.mel_scale.fb}, strict=True)
+    assert torch.equal(dst.spectrogram.transform.spectrogram.window, torch.hann_window(1024))
+    # a trained STFT (kernels that are not window * sin/cos) is refused, not silently approximated
+    bad = dict(sd)
+    bad["spectrogram.transform.stft.wsin"] = bad["spectrogram.transform.stft.wsin"] + 0.01
+    with pytest.raises(RuntimeError, match="trained STFT"):
+        Model().load_state_dict(bad, strict=True)
+    with pytest.raises(RuntimeError, match="mel_basis"):
+        Model().load_state_dict({"spectrogram.transform.mel_basis": torch.zeros(80, 513)}, strict=False)
+
+
+def test_nnaudio_module_copies_and_pickles(nnaudio_published):
+    m = MelSpectrogram(*NNAUDIO_P1)
+    for c in (copy.deepcopy(m), pickle.loads(pickle.dumps(m))):
+        assert list(c.state_dict()) == list(m.state_dict())
+        c.load_state_dict(m.state_dict(), strict=True)

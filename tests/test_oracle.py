@@ -113,3 +113,40 @@ def test_live_reference_agrees_with_oracle_and_fixtures():
     y_ref = ref(torch.from_numpy(x)).numpy()
     y = mel_oracle.mel_forward(x, fb=fb, window=window, dtype=np.float64)
     assert parity_error(y_ref, y, True) < 2e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# N4: the nnAudio-arithmetic restatement.  Parity UNPINNED against nnAudio itself
+# (see oracle/nnaudio_oracle.py); these tests hold it to the two things that can be checked here.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_mels,f_min", [(80, 0.0), (128, 20.0), (388, 0.0), (512, 0.0)])
+def test_nnaudio_mel_basis_matches_torchaudios_slaney_filterbank(n_mels, f_min):
+    import warnings
+
+    import torchaudio
+    from oracle import nnaudio_oracle
+    mb = nnaudio_oracle.mel_basis(16000, 1024, n_mels, f_min, 8000.0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                # torchaudio warns about all-zero filters (388 / 512 mels)
+        ta = torchaudio.functional.melscale_fbanks(513, f_min, 8000.0, n_mels, 16000, norm="slaney",
+                                                   mel_scale="slaney").numpy()
+    assert mb.shape == (n_mels, 513) and mb.dtype == np.float32
+    # torchaudio does the same construction in fp32 tensor arithmetic: a few fp32 ulps of the peak apart
+    assert np.abs(mb.T - ta).max() <= 4e-5 * ta.max()
+    assert np.array_equal(mb.T > 0, ta > 0) or np.abs(mb.T - ta)[(mb.T > 0) != (ta > 0)].max() < 1e-6
+
+
+def test_nnaudio_conv_stft_equals_the_pinned_fft_form():
+    from oracle import nnaudio_oracle
+    from tests.golden import signals
+    x = signals.noise(2, 6000, 5)
+    mb = nnaudio_oracle.mel_basis(16000, 1024, 388, 0.0, 8000.0)
+    for pad, log in (("constant", False), ("reflect", True)):
+        conv = nnaudio_oracle.mel_forward(x, pad_mode=pad, log_scale=log)
+        fft = mel_oracle.mel_forward(x, fb=mb.T, pad_mode=pad, log_scale=log, dtype=np.float64)
+        assert conv.shape == fft.shape == (2, 47, 388)
+        # fp32-rounded sin/cos kernels vs the exact DFT: ~1e-7 relative
+        assert np.abs(conv - fft).max() <= 1e-6 * np.abs(fft).max()
+    wsin, wcos, window = nnaudio_oracle.fourier_kernels()
+    assert wsin.shape == wcos.shape == (513, 1, 1024)
+    assert np.array_equal(wcos[0, 0], window) and not wsin[0].any()
