@@ -11,6 +11,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libbhmel.so")
+LIB_STEM = os.path.join(PKG, "libbhstem.so")      # conv stem: its own library, its own header
 GEN = os.path.join(CSRC, "fft32_gen.h")
 
 NVCC_FLAGS = [
@@ -40,19 +41,31 @@ def generate() -> str:
     return GEN
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    generate()
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".py"))]
-    srcs.append(os.path.join(os.path.dirname(PKG), "include", "bhmel.h"))
-    if not force and _newer(LIB, srcs):
-        return LIB
+def _nvcc(out: str, src: str, verbose: bool) -> None:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, os.path.join(CSRC, "bhmel.cu")]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    res = subprocess.run([nvcc, *NVCC_FLAGS, "-o", out, src], capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libbhmel.so")
+        raise RuntimeError(f"nvcc failed building {os.path.basename(out)}")
+
+
+def build_stem(force: bool = False, verbose: bool = False) -> str:
+    src = os.path.join(CSRC, "bhstem.cu")
+    if force or not _newer(LIB_STEM, [src, os.path.join(os.path.dirname(PKG), "include", "bhstem.h")]):
+        _nvcc(LIB_STEM, src, verbose)
+    return LIB_STEM
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    generate()
+    build_stem(force, verbose)
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)
+            if f.endswith((".cu", ".cuh", ".h", ".py")) and f != "bhstem.cu"]
+    srcs.append(os.path.join(os.path.dirname(PKG), "include", "bhmel.h"))
+    if not force and _newer(LIB, srcs):
+        return LIB
+    _nvcc(LIB, os.path.join(CSRC, "bhmel.cu"), verbose)
     return LIB
 
 

@@ -1,0 +1,134 @@
+"""Host-side mirror of the encoder's convolutional stem.
+
+The reference encoder (osuT5/osuT5/model/custom_transformers/modeling_ropewhisper.py:1135-1136,
+1206-1209; the stock HF WhisperEncoder is identical here) starts with
+
+    inputs_embeds = gelu(conv1(input_features))        # Conv1d(C_in, D, 3, padding=1) on [B, C_in, T]
+    inputs_embeds = gelu(conv2(inputs_embeds))         # Conv1d(D, D, 3, stride=2, padding=1)
+    inputs_embeds = inputs_embeds.permute(0, 2, 1)     # [B, T/2, D]
+
+`ConvStem` keeps the parameter names (`conv1.weight`, `conv1.bias`, `conv2.weight`, `conv2.bias`)
+so it loads from the encoder's state dict, and computes the three lines with two tcgen05 implicit
+GEMM launches behind the C ABI in include/bhstem.h.  It consumes the CHANNELS-LAST encoder input
+[B, T, C_in] bf16 -- what `MelSpectrogram.forward_encoder_input(..., channels_first=False)` returns,
+i.e. the tensor the reference has *before* its `swapaxes(1, 2)` (modeling_mapperatorinator.py:
+368-376) -- so that swapaxes and the permute above both disappear.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+
+import torch
+import torch.nn as nn
+
+from . import _stem_lib
+
+_handle_lock = threading.Lock()
+
+
+class ConvStem(nn.Module):
+    def __init__(self, num_mel_bins: int, d_model: int):
+        """num_mel_bins = encoder input channels (config.num_mel_bins: mel + conditioning channels),
+        d_model = config.d_model (reference modeling_ropewhisper.py:1129-1136)."""
+        super().__init__()
+        if num_mel_bins % 8 or d_model % 128:
+            raise ValueError("the sm_100a stem needs num_mel_bins % 8 == 0 and d_model % 128 == 0")
+        self.conv1 = nn.Conv1d(num_mel_bins, d_model, kernel_size=3, padding=1)
+        self.conv2 = nn.Conv1d(d_model, d_model, kernel_size=3, stride=2, padding=1)
+        self._handles: dict[int, int] = {}
+        self._stamp: dict[int, tuple] = {}
+
+    @classmethod
+    def from_encoder(cls, encoder: nn.Module) -> "ConvStem":
+        """Build from any module that carries `conv1` / `conv2` like the reference encoder."""
+        stem = cls(encoder.conv1.in_channels, encoder.conv1.out_channels)
+        stem.load_state_dict({k: v for k, v in encoder.state_dict().items() if k.startswith(("conv1.", "conv2."))})
+        return stem.to(encoder.conv1.weight.device)
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_handles"], state["_stamp"] = {}, {}
+        return state
+
+    def _param_stamp(self) -> tuple:
+        ps = (self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias)
+        return tuple((p.data_ptr(), p._version) for p in ps)
+
+    def _handle_for(self, device: torch.device) -> int:
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        stamp = self._param_stamp()
+        with _handle_lock:
+            h = self._handles.get(idx)
+            if h is not None and self._stamp.get(idx) == stamp:
+                return h
+            lib = _stem_lib.lib()
+            if h is not None:                       # parameters were reloaded / edited: repack
+                lib.bhstem_destroy(h)
+                del self._handles[idx]
+            host = [p.detach().to("cpu", torch.float32).contiguous()
+                    for p in (self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias)]
+            fp = ctypes.POINTER(ctypes.c_float)
+            out = ctypes.c_void_p()
+            with torch.cuda.device(idx):
+                _stem_lib.check(lib.bhstem_create(self.conv1.in_channels, self.conv1.out_channels,
+                                                  *[ctypes.cast(t.data_ptr(), fp) for t in host], ctypes.byref(out)))
+            self._handles[idx] = out.value
+            self._stamp[idx] = stamp
+            return out.value
+
+    def __del__(self):
+        try:
+            lib = _stem_lib.lib()
+            for h in self._handles.values():
+                lib.bhstem_destroy(h)
+        except Exception:
+            pass
+
+    def launch_count(self) -> int:
+        lib = _stem_lib.lib()
+        return sum(int(lib.bhstem_launch_count(h)) for h in self._handles.values())
+
+    def _check(self, x: torch.Tensor) -> None:
+        if x.dim() != 3 or x.shape[2] != self.conv1.in_channels:
+            raise RuntimeError(f"expected channels-last input [B, T, {self.conv1.in_channels}], got {tuple(x.shape)}")
+        if not x.is_cuda:
+            raise RuntimeError("beatheritage_b200.ConvStem has no CPU path: move the batch to a CUDA (sm_100) device")
+        if x.dtype != torch.bfloat16:
+            raise RuntimeError("ConvStem computes in bfloat16 (the reference model's inference dtype): pass a bfloat16 tensor")
+        if x.shape[1] < 2 or x.shape[1] % 2:
+            raise RuntimeError("the number of frames T must be even")
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x [B, T, C_in] bf16 channels last -> [B, T/2, D] bf16
+        == gelu(conv2(gelu(conv1(x.swapaxes(1, 2))))).permute(0, 2, 1)."""
+        self._check(x)
+        x = x.contiguous()
+        B, T, _ = x.shape
+        D = self.conv1.out_channels
+        hidden = torch.empty((B, T, D), dtype=torch.bfloat16, device=x.device)
+        y = torch.empty((B, T // 2, D), dtype=torch.bfloat16, device=x.device)
+        h = self._handle_for(x.device)
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            _stem_lib.check(_stem_lib.lib().bhstem_forward(h, x.data_ptr(), B, T, hidden.data_ptr(), y.data_ptr(), stream))
+        return y
+
+    @torch.no_grad()
+    def forward_stage(self, stage: int, x: torch.Tensor) -> torch.Tensor:
+        """conv1 + GELU (stage 1: [B, T, C_in] -> [B, T, D]) or conv2 + GELU (stage 2: [B, T, D] ->
+        [B, T/2, D]) alone, channels last; for tests and profiling."""
+        D = self.conv1.out_channels
+        if stage == 1:
+            self._check(x)
+        elif not (x.dim() == 3 and x.shape[2] == D and x.is_cuda and x.dtype == torch.bfloat16 and x.shape[1] % 2 == 0):
+            raise RuntimeError(f"stage 2 expects a bfloat16 CUDA tensor [B, even T, {D}]")
+        x = x.contiguous()
+        B, T, _ = x.shape
+        out = torch.empty((B, T if stage == 1 else T // 2, D), dtype=torch.bfloat16, device=x.device)
+        h = self._handle_for(x.device)
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            _stem_lib.check(_stem_lib.lib().bhstem_forward_stage(h, stage, x.data_ptr(), B, T, out.data_ptr(), stream))
+        return out

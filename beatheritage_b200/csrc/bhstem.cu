@@ -1,0 +1,478 @@
+// libbhstem.so -- the encoder's convolutional stem as two tcgen05 implicit GEMMs (include/bhstem.h).
+//
+// Reference: osuT5/osuT5/model/custom_transformers/modeling_ropewhisper.py:1135-1136 (conv1 / conv2),
+// :1206-1209 (gelu(conv1), gelu(conv2), permute).  SURVEY.md 8f row N3.
+//
+// A 1-D convolution with kernel 3 over channels-last activations X[b][t][c] is
+//     Y[b][t][n] = bias[n] + sum_tap sum_c X[b][s*t + tap - 1][c] * W[tap][n][c]
+// i.e. three GEMMs accumulated into the same tile, whose A operands are the SAME matrix shifted by
+// one row.  Nothing is materialised: every (tap, 64-channel block) of A is one TMA box load from a
+// 3-D tensor map [batch][row][channel] at row offset tap-1 -- rows -1 and T fall outside the map and
+// come back as zeros, which IS the convolution's zero padding.  The stride-2 convolution reads the
+// activations through a [batch][T/2][2*D] view (two time steps per row): tap 0 is the odd half of
+// the previous row, taps 1 and 2 the even and odd halves of the current one.
+//
+// One persistent CTA per SM, 192 threads, warp-specialised:
+//   warp 0      TMA producer    A box 128 rows x 64 ch + W box BN rows x 64 ch per stage, 128-byte
+//                                swizzle, 4-stage mbarrier ring
+//   warp 1      MMA issuer      one thread issues tcgen05.mma.kind::f16 (128 x BN x 16, bf16 -> fp32)
+//                                into one of two TMEM accumulator stages; tcgen05.commit frees the
+//                                shared-memory stage / publishes the accumulator
+//   warps 2-5   epilogue        tcgen05.ld 32 lanes x 32 columns -> + bias -> round to bf16 (the conv
+//                                output) -> erf GELU in fp32 -> bf16 -> 64-byte row segments to HBM;
+//                                overlaps the next tile's MMAs through the second accumulator stage
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/bhstem.h"
+
+namespace {
+
+constexpr int BLOCK_M = 128;      // output rows (time steps) per tile = TMEM lanes
+constexpr int BLOCK_K = 64;       // channels per stage: 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;        // K of one tcgen05.mma.kind::f16
+constexpr int STAGES = 4;
+constexpr int THREADS = 192;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr long long SPIN_LIMIT_CYCLES = 4000000000LL;   // ~2 s: a protocol bug traps instead of hanging the GPU
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;   // + slack to align the ring to 1024 B
+  static constexpr int TMEM_COLS = 2 * BN;                         // two fp32 accumulator stages
+};
+
+struct StemProblem {
+  int32_t batches, m_tiles, n_tiles;
+  int32_t rows_out;        // valid output rows per batch
+  int32_t n_out;           // output channels (row pitch of the output, elements)
+  int32_t k_blocks;        // ceil(C / 64) per tap
+  int32_t c_in;            // channels per tap
+  int32_t tap_col[3];      // column offset of each tap inside a row of the A view
+  int32_t tap_row[3];      // row offset of each tap
+};
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > SPIN_LIMIT_CYCLES) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+
+// Shared-memory matrix descriptor, K-major operand with 128-byte swizzle: rows of 128 bytes, groups of
+// 8 rows 1024 bytes apart (SBO); LBO is ignored for swizzled K-major layouts; version 1 = sm_100.
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// conv output rounded to bf16, exact GELU in fp32 on that value (torch: gelu(conv(x)) under bf16)
+__device__ __forceinline__ float conv_gelu(float acc_plus_bias) {
+  const float x = __bfloat162float(__float2bfloat16_rn(acc_plus_bias));
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+template <int BN>
+__global__ void __launch_bounds__(THREADS, 1)
+bhstem_conv_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, const StemProblem p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) unsigned long long bars[2 * STAGES + 4];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
+  const uint32_t tfull0 = smem_u32(&bars[2 * STAGES]), tempty0 = smem_u32(&bars[2 * STAGES + 2]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, 4);          // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "n"(C::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int tiles_per_batch = p.m_tiles * p.n_tiles;
+  const int num_tiles = p.batches * tiles_per_batch;
+  const int k_iters = 3 * p.k_blocks;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_batch, rem = tile % tiles_per_batch;
+        const int mt = rem / p.n_tiles, nt = rem % p.n_tiles;
+        for (int it = 0; it < k_iters; ++it) {
+          const int tap = it / p.k_blocks, kb = it % p.k_blocks;
+          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          const uint32_t sa = ring + stage * C::STAGE_BYTES, sb = sa + A_BYTES;
+          mbar_expect_tx(full0 + 8 * stage, C::STAGE_BYTES);
+          tma_load_3d(&map_a, full0 + 8 * stage, sa, p.tap_col[tap] + kb * BLOCK_K, mt * BLOCK_M + p.tap_row[tap], b);
+          tma_load_3d(&map_w, full0 + 8 * stage, sb, kb * BLOCK_K, nt * BN, tap);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      // D = F32, A = B = BF16, both K-major, N >> 3, M >> 4
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
+                                 (static_cast<uint32_t>(BLOCK_M >> 4) << 24);
+      uint32_t stage = 0, phase = 0, local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const uint32_t as = local & 1, aphase = (local >> 1) & 1;
+        mbar_wait(tempty0 + 8 * as, aphase ^ 1);          // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int it = 0; it < k_iters; ++it) {
+          const int kb = it % p.k_blocks;
+          const int rem_c = p.c_in - kb * BLOCK_K;
+          const int ksteps = rem_c >= BLOCK_K ? BLOCK_K / UMMA_K : (rem_c + UMMA_K - 1) / UMMA_K;   // zero-filled tail skipped
+          mbar_wait(full0 + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = ring + stage * C::STAGE_BYTES, sb = sa + A_BYTES;
+          const uint64_t adesc = sw128_desc(sa), bdesc = sw128_desc(sb);
+          for (int k = 0; k < ksteps; ++k)                 // 16 bf16 = 32 bytes along K: +2 in the (addr >> 4) field
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+          umma_commit(empty0 + 8 * stage);                 // frees the stage when these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull0 + 8 * as);                      // accumulator complete
+      }
+    }
+  } else {
+    // ===================================== epilogue =========================================
+    const int quarter = warp & 3;                          // TMEM lanes this warp may touch: 32 * (warp % 4) ...
+    const int row_in_tile = quarter * 32 + lane;
+    uint32_t local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int b = tile / tiles_per_batch, rem = tile % tiles_per_batch;
+      const int mt = rem / p.n_tiles, nt = rem % p.n_tiles;
+      const uint32_t as = local & 1, aphase = (local >> 1) & 1;
+      const int row = mt * BLOCK_M + row_in_tile;
+      const bool valid = row < p.rows_out;
+      __nv_bfloat16* orow = out + (static_cast<size_t>(b) * p.rows_out + (valid ? row : 0)) * p.n_out + nt * BN;
+      const float* brow = bias + nt * BN;
+      mbar_wait(tfull0 + 8 * as, aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        __syncwarp();                                      // tcgen05.ld is warp-collective (.sync.aligned)
+        tmem_ld32(taddr + c * 32, r);
+        if (c == BN / 32 - 1) {                            // everything is in registers: hand the stage back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+        }
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(brow + c * 32 + j));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(brow + c * 32 + j + 4));
+            uint4 v;
+            v.x = pack_bf16(conv_gelu(__uint_as_float(r[j + 0]) + b0.x), conv_gelu(__uint_as_float(r[j + 1]) + b0.y));
+            v.y = pack_bf16(conv_gelu(__uint_as_float(r[j + 2]) + b0.z), conv_gelu(__uint_as_float(r[j + 3]) + b0.w));
+            v.z = pack_bf16(conv_gelu(__uint_as_float(r[j + 4]) + b1.x), conv_gelu(__uint_as_float(r[j + 5]) + b1.y));
+            v.w = pack_bf16(conv_gelu(__uint_as_float(r[j + 6]) + b1.z), conv_gelu(__uint_as_float(r[j + 7]) + b1.w));
+            *reinterpret_cast<uint4*>(orow + c * 32 + j) = v;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS));
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(BHSTEM_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  return reinterpret_cast<EncodeTiledFn>(fn);
+}
+
+// bf16 tensor map [d2][d1][d0] (d0 contiguous), box [1][box1][64], 128-byte swizzle, zero fill outside
+int make_map(EncodeTiledFn enc, CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+             uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box1) {
+  const cuuint64_t dims[3] = {d0, d1, d2};
+  const cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  const cuuint32_t box[3] = {BLOCK_K, box1, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(BHSTEM_ECUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
+  return BHSTEM_OK;
+}
+
+}  // namespace
+
+struct bhstem_handle {
+  int device = 0, sms = 0;
+  int32_t c_in = 0, d = 0, bn = 0;
+  __nv_bfloat16 *w1 = nullptr, *w2 = nullptr;   // [3][D][C] tap-major, bf16
+  float *b1 = nullptr, *b2 = nullptr;
+  CUtensorMap map_w1, map_w2;
+  EncodeTiledFn enc = nullptr;
+  long long launches = 0;
+};
+
+namespace {
+
+// torch Conv1d weight [D][C][3] f32 -> [3][D][C] bf16 (round to nearest even, like .to(bfloat16))
+std::vector<__nv_bfloat16> pack_weight(const float* w, int d, int c) {
+  std::vector<__nv_bfloat16> out(static_cast<size_t>(3) * d * c);
+  for (int n = 0; n < d; ++n)
+    for (int ci = 0; ci < c; ++ci)
+      for (int tap = 0; tap < 3; ++tap)
+        out[(static_cast<size_t>(tap) * d + n) * c + ci] = __float2bfloat16_rn(w[(static_cast<size_t>(n) * c + ci) * 3 + tap]);
+  return out;
+}
+
+template <int BN>
+int launch_stage(bhstem_handle* h, int stage, const void* in, int64_t B, int64_t T, void* out, cudaStream_t stream) {
+  const int c = stage == 1 ? h->c_in : h->d;
+  StemProblem p{};
+  CUtensorMap map_a;
+  int rc;
+  if (stage == 1) {
+    p.rows_out = static_cast<int32_t>(T);
+    rc = make_map(h->enc, &map_a, in, c, T, B, static_cast<uint64_t>(c) * 2, static_cast<uint64_t>(T) * c * 2, BLOCK_M);
+    for (int t = 0; t < 3; ++t) { p.tap_col[t] = 0; p.tap_row[t] = t - 1; }
+  } else {
+    // two time steps per row: tap 0 = x[2t-1] (odd half of row t-1), tap 1 = x[2t], tap 2 = x[2t+1]
+    p.rows_out = static_cast<int32_t>(T / 2);
+    rc = make_map(h->enc, &map_a, in, 2 * static_cast<uint64_t>(c), T / 2, B, static_cast<uint64_t>(c) * 4,
+                  static_cast<uint64_t>(T) * c * 2, BLOCK_M);
+    p.tap_col[0] = c; p.tap_row[0] = -1;
+    p.tap_col[1] = 0; p.tap_row[1] = 0;
+    p.tap_col[2] = c; p.tap_row[2] = 0;
+  }
+  if (rc != BHSTEM_OK) return rc;
+  p.batches = static_cast<int32_t>(B);
+  p.m_tiles = (p.rows_out + BLOCK_M - 1) / BLOCK_M;
+  p.n_tiles = h->d / BN;
+  p.n_out = h->d;
+  p.c_in = c;
+  p.k_blocks = (c + BLOCK_K - 1) / BLOCK_K;
+  const long long tiles = static_cast<long long>(p.batches) * p.m_tiles * p.n_tiles;
+  const int grid = static_cast<int>(tiles < h->sms ? tiles : h->sms);
+  auto kernel = bhstem_conv_gelu_kernel<BN>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+  kernel<<<grid, THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(map_a, stage == 1 ? h->map_w1 : h->map_w2,
+                                                         stage == 1 ? h->b1 : h->b2, static_cast<__nv_bfloat16*>(out), p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+  ++h->launches;
+  return BHSTEM_OK;
+}
+
+int check_call(bhstem_handle* h, const void* in, int64_t B, int64_t T, void* out) {
+  if (!h || !in || !out) return fail(BHSTEM_EINVAL, "null argument");
+  if (B < 1 || T < 2 || (T & 1)) return fail(BHSTEM_EINVAL, "need B >= 1 and an even T >= 2");
+  if (B > 65535 || T > (1 << 24)) return fail(BHSTEM_EINVAL, "B or T too large");
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
+    return fail(BHSTEM_EINVAL, "buffers must be 16-byte aligned");
+  int dev = -1;
+  cudaGetDevice(&dev);
+  if (dev != h->device) return fail(BHSTEM_EDEVICE, "handle was created on another device than the current one");
+  return BHSTEM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bhstem_version(void) { return BHSTEM_VERSION; }
+const char* bhstem_last_error(void) { return g_err.c_str(); }
+int64_t bhstem_launch_count(const bhstem_handle* h) { return h ? h->launches : 0; }
+
+int bhstem_create(int32_t c_in, int32_t d_model, const float* conv1_weight, const float* conv1_bias,
+                  const float* conv2_weight, const float* conv2_bias, bhstem_handle** out) {
+  if (!out) return fail(BHSTEM_EINVAL, "out is null");
+  *out = nullptr;
+  if (!conv1_weight || !conv1_bias || !conv2_weight || !conv2_bias) return fail(BHSTEM_EINVAL, "null parameter array");
+  if (c_in < 8 || c_in % 8 || c_in > 65536) return fail(BHSTEM_EINVAL, "c_in must be a positive multiple of 8");
+  if (d_model < 128 || d_model % 128 || d_model > 8192) return fail(BHSTEM_EINVAL, "d_model must be a multiple of 128");
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+  if (prop.major != 10) return fail(BHSTEM_EDEVICE, "libbhstem needs an sm_100 device (tcgen05 / TMEM)");
+  bhstem_handle* h = new (std::nothrow) bhstem_handle();
+  if (!h) return fail(BHSTEM_EINVAL, "out of host memory");
+  h->device = dev;
+  h->sms = prop.multiProcessorCount;
+  h->c_in = c_in;
+  h->d = d_model;
+  h->bn = d_model % 256 == 0 ? 256 : 128;
+  h->enc = encode_tiled_fn();
+  if (!h->enc) { delete h; return fail(BHSTEM_ECUDA, "cuTensorMapEncodeTiled is not available from this driver"); }
+  const std::vector<__nv_bfloat16> w1 = pack_weight(conv1_weight, d_model, c_in), w2 = pack_weight(conv2_weight, d_model, d_model);
+  std::vector<float> b1(d_model), b2(d_model);          // biases are bf16 in the bf16 model too
+  for (int i = 0; i < d_model; ++i) {
+    b1[i] = __bfloat162float(__float2bfloat16_rn(conv1_bias[i]));
+    b2[i] = __bfloat162float(__float2bfloat16_rn(conv2_bias[i]));
+  }
+  auto up = [&](void** dst, const void* src, size_t bytes) {
+    cudaError_t er = cudaMalloc(dst, bytes);
+    if (er == cudaSuccess) er = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+    return er;
+  };
+  if ((e = up(reinterpret_cast<void**>(&h->w1), w1.data(), w1.size() * 2)) != cudaSuccess ||
+      (e = up(reinterpret_cast<void**>(&h->w2), w2.data(), w2.size() * 2)) != cudaSuccess ||
+      (e = up(reinterpret_cast<void**>(&h->b1), b1.data(), static_cast<size_t>(d_model) * 4)) != cudaSuccess ||
+      (e = up(reinterpret_cast<void**>(&h->b2), b2.data(), static_cast<size_t>(d_model) * 4)) != cudaSuccess) {
+    bhstem_destroy(h);
+    return cuda_fail(e, "uploading the stem parameters");
+  }
+  int rc = make_map(h->enc, &h->map_w1, h->w1, c_in, d_model, 3, static_cast<uint64_t>(c_in) * 2,
+                    static_cast<uint64_t>(d_model) * c_in * 2, h->bn);
+  if (rc == BHSTEM_OK)
+    rc = make_map(h->enc, &h->map_w2, h->w2, d_model, d_model, 3, static_cast<uint64_t>(d_model) * 2,
+                  static_cast<uint64_t>(d_model) * d_model * 2, h->bn);
+  if (rc != BHSTEM_OK) { bhstem_destroy(h); return rc; }
+  *out = h;
+  return BHSTEM_OK;
+}
+
+void bhstem_destroy(bhstem_handle* h) {
+  if (!h) return;
+  cudaFree(h->w1);
+  cudaFree(h->w2);
+  cudaFree(h->b1);
+  cudaFree(h->b2);
+  delete h;
+}
+
+int bhstem_forward_stage(bhstem_handle* h, int32_t stage, const void* in, int64_t B, int64_t T, void* out, void* stream) {
+  const int rc = check_call(h, in, B, T, out);
+  if (rc != BHSTEM_OK) return rc;
+  if (stage != 1 && stage != 2) return fail(BHSTEM_EINVAL, "stage must be 1 or 2");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return h->bn == 256 ? launch_stage<256>(h, stage, in, B, T, out, s) : launch_stage<128>(h, stage, in, B, T, out, s);
+}
+
+int bhstem_forward(bhstem_handle* h, const void* x, int64_t B, int64_t T, void* hidden, void* y, void* stream) {
+  if (!hidden) return fail(BHSTEM_EINVAL, "null argument");
+  int rc = bhstem_forward_stage(h, 1, x, B, T, hidden, stream);
+  if (rc == BHSTEM_OK) rc = bhstem_forward_stage(h, 2, hidden, B, T, y, stream);
+  return rc;
+}
+
+}  // extern "C"

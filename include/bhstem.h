@@ -1,0 +1,75 @@
+/* bhstem.h -- C ABI of libbhstem.so: the encoder's convolutional stem on B200 (sm_100a), the
+ * consumer of the log-mel frames libbhmel.so produces.
+ *
+ * Replaces, in the reference encoder (ref: osuT5/osuT5/model/custom_transformers/
+ * modeling_ropewhisper.py:1135-1136 construction, :1206-1209 forward; the stock HF WhisperEncoder
+ * has the same stem):
+ *
+ *     inputs_embeds = gelu(conv1(input_features))      conv1 = Conv1d(C_in, D, kernel 3, padding 1)
+ *     inputs_embeds = gelu(conv2(inputs_embeds))       conv2 = Conv1d(D, D, kernel 3, stride 2, padding 1)
+ *     inputs_embeds = inputs_embeds.permute(0, 2, 1)   -> [B, T/2, D]
+ *
+ * as two implicit GEMMs on the tcgen05 tensor cores (bf16 operands, fp32 accumulation in tensor
+ * memory), operands staged by TMA straight from the channels-last activations -- the three taps
+ * are three shifted views of the same matrix, the zero padding is TMA's out-of-bounds fill -- with
+ * bias, GELU and the bf16 conversion fused into the epilogue.  The input is the channels-last
+ * encoder input [B][T][C_in] that bhmel_forward_encoder_input (BHMEL_LAYOUT_BTC) writes, so the
+ * reference's swapaxes before the stem and permute after it both disappear.
+ *
+ * Arithmetic contract (what the reference computes under bf16): per output element, fp32
+ * accumulation of bf16 products plus the fp32 bias, rounded to bf16 (the convolution's output),
+ * then exact (erf) GELU evaluated in fp32 on that bf16 value, rounded to bf16.
+ *
+ * Plain C: pointers, sizes, a CUDA stream.  The caller owns every device buffer; the handle owns
+ * the packed weights.  Launches on the caller's stream, never synchronises, allocates nothing in
+ * bhstem_forward.  Every int-returning function returns 0 on success, a BHSTEM_E* code otherwise;
+ * message through bhstem_last_error() (thread-local).
+ */
+#ifndef BHSTEM_H_
+#define BHSTEM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BHSTEM_VERSION 1
+
+#define BHSTEM_OK 0
+#define BHSTEM_EINVAL 1
+#define BHSTEM_ECUDA 2
+#define BHSTEM_EDEVICE 3
+
+typedef struct bhstem_handle bhstem_handle;
+
+/* Builds a stem for C_in input channels and D model channels on the CURRENT device from HOST
+ * float32 parameters in torch's Conv1d layout (state-dict keys conv1.weight [D][C_in][3],
+ * conv1.bias [D], conv2.weight [D][D][3], conv2.bias [D]; ref: modeling_ropewhisper.py:1135-1136).
+ * Weights and biases are rounded to bf16 (what `.to(bfloat16)` of the model does, ref:
+ * inference.py:486-489); the weights are repacked tap-major [3][D][C].  Requires C_in % 8 == 0 and D % 128 == 0. */
+int bhstem_create(int32_t c_in, int32_t d_model, const float* conv1_weight, const float* conv1_bias,
+                  const float* conv2_weight, const float* conv2_bias, bhstem_handle** out);
+void bhstem_destroy(bhstem_handle* h);
+
+/* x       DEVICE bf16 [B][T][C_in], channels last, contiguous (T even, T >= 2)
+ * hidden  DEVICE bf16 [B][T][D] scratch for gelu(conv1) (caller-owned; stays L2-resident for
+ *         inference-sized batches)
+ * y       DEVICE bf16 [B][T/2][D] = gelu(conv2(gelu(conv1(x^T))))^T
+ * Two kernel launches on `stream`. */
+int bhstem_forward(bhstem_handle* h, const void* x, int64_t B, int64_t T, void* hidden, void* y, void* stream);
+
+/* conv1 or conv2 alone (stage 1 / 2): for tests and profiling.  Stage 1: in [B][T][C_in] ->
+ * out [B][T][D]; stage 2: in [B][T][D] -> out [B][T/2][D]. */
+int bhstem_forward_stage(bhstem_handle* h, int32_t stage, const void* in, int64_t B, int64_t T, void* out,
+                         void* stream);
+
+int bhstem_version(void);
+const char* bhstem_last_error(void);
+/* Kernel launches issued through this handle so far. */
+int64_t bhstem_launch_count(const bhstem_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BHSTEM_H_ */

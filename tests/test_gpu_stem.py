@@ -1,0 +1,125 @@
+"""GPU (-m gpu): the tcgen05 conv stem (include/bhstem.h) against the CPU oracle and
+against the reference's own torch modules in bf16 on the GPU.
+
+Tolerance: both sides round to bf16 at the same points (twice per stage: the convolution's output and
+GELU's), so results agree except where the fp32 summation order flips one of those roundings -- a
+flipped pre-activation (1 ulp of x) moves gelu(x) by up to 1.13 ulp(x), which is 2-3 ulps of the
+smaller gelu(x), before that is rounded itself: |diff| <= 2^-6 |want| + 4e-3 everywhere.  One stage on
+identical inputs: fewer than 2 % of the elements differ at all; the two-stage stem, where conv2 sees
+the flipped hidden values: fewer than 10 %."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import conv_stem_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda", 0)
+
+
+def make_stem(c_in, d, dev, seed=0):
+    from beatheritage_b200.conv_stem import ConvStem
+    torch.manual_seed(seed)
+    stem = ConvStem(c_in, d)
+    with torch.no_grad():                        # bf16-representable parameters, like a model cast with .to(bfloat16)
+        for p in stem.parameters():
+            p.copy_(p.to(torch.bfloat16).float())
+    return stem.to(dev)
+
+
+def make_input(B, T, c_in, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, T, c_in, generator=g) * 1.5       # log-mel + embeddings are O(1)
+    return x.to(torch.bfloat16)
+
+
+def assert_close(got, want, what, max_frac=0.02):
+    got, want = got.float().cpu(), want.float().cpu()
+    assert got.shape == want.shape, what
+    diff = (got - want).abs()
+    bound = want.abs() * 2.0 ** -6 + 4e-3
+    worst = float((diff - bound).max())
+    assert worst <= 0, f"{what}: exceeds 2^-6 |want| + 4e-3 by {worst} (max diff {float(diff.max())})"
+    frac = float((diff > 0).float().mean())
+    assert frac < max_frac, f"{what}: {frac:.4f} of the elements differ"
+
+
+@pytest.mark.parametrize("B,T,c_in,d", [
+    (2, 256, 464, 768),        # whisper-small dims (C5): 29 channel blocks of 16, BN = 256
+    (1, 200, 464, 768),        # ragged: partial row tile, TMA zero fill below the last row
+    (3, 64, 80, 384),          # whisper-tiny width: BN = 128, 80 channels = 1 full + 1 quarter block
+    (1, 2, 8, 128),            # smallest legal problem
+])
+def test_each_stage_matches_the_oracle(dev, B, T, c_in, d):
+    stem = make_stem(c_in, d, dev, seed=c_in + d)
+    x = make_input(B, T, c_in, seed=T)
+    want_y, want_h = conv_stem_oracle.conv_stem(x, stem.conv1.weight, stem.conv1.bias, stem.conv2.weight,
+                                                stem.conv2.bias, return_hidden=True)
+    before = stem.launch_count()
+    h = stem.forward_stage(1, x.to(dev))
+    torch.cuda.synchronize()
+    assert stem.launch_count() == before + 1
+    assert h.shape == (B, T, d) and h.dtype == torch.bfloat16
+    assert_close(h, want_h, "gelu(conv1)")
+    y2 = stem.forward_stage(2, want_h.to(torch.bfloat16).to(dev))      # stage 2 on the oracle's hidden: isolates conv2
+    assert_close(y2, want_y, "gelu(conv2) on the oracle's hidden")
+    y = stem(x.to(dev))
+    torch.cuda.synchronize()
+    assert y.shape == (B, T // 2, d) and y.is_contiguous()
+    assert_close(y, want_y, "stem", 0.10)
+    assert "libbhstem.so" in open("/proc/self/maps").read()
+
+
+def test_full_context_matches_the_reference_modules_on_the_gpu(dev):
+    """B = 6 windows x 4096 frames x 464 channels (C2 parallel batch, C5 dims): against torch's own
+    Conv1d + gelu in bf16 on the GPU (the modules the reference runs), and the oracle on one window."""
+    stem = make_stem(464, 768, dev, seed=7)
+    x = make_input(6, 4096, 464, seed=11).to(dev)
+    y = stem(x)
+    ref = stem.to(torch.bfloat16)
+    with torch.no_grad():
+        r = torch.nn.functional.gelu(ref.conv1(x.swapaxes(1, 2)))
+        r = torch.nn.functional.gelu(ref.conv2(r)).permute(0, 2, 1)
+    torch.cuda.synchronize()
+    assert_close(y, r, "stem vs torch bf16 modules on the GPU", 0.10)
+    want = conv_stem_oracle.conv_stem(x[4:5].cpu(), ref.conv1.weight, ref.conv1.bias, ref.conv2.weight, ref.conv2.bias)
+    assert_close(y[4:5], want, "stem vs oracle, window 4", 0.10)
+    assert_close(r[4:5], want, "torch bf16 modules vs oracle (pins the oracle)", 0.10)
+
+
+def test_linearity_free_properties(dev):
+    """Size-independent properties: zero input gives gelu(bias) rows; windows are independent of their
+    batch neighbours; an all-zero stem gives exactly 0."""
+    stem = make_stem(464, 768, dev, seed=3)
+    x = make_input(3, 512, 464, seed=5).to(dev)
+    y = stem(x)
+    y1 = stem(x[1:2])
+    assert torch.equal(y[1:2], y1)
+    z = stem.forward_stage(1, torch.zeros(1, 128, 464, dtype=torch.bfloat16, device=dev))
+    want = torch.nn.functional.gelu(stem.conv1.bias.to(torch.bfloat16).float()).to(torch.bfloat16)
+    assert torch.equal(z[0, 5], want) and torch.equal(z[0, 0], want) and torch.equal(z[0, 127], want)
+    with torch.no_grad():
+        for p in stem.parameters():
+            p.zero_()
+    assert torch.count_nonzero(stem(x)) == 0      # parameters edited in place: the handle repacks
+
+
+def test_errors(dev):
+    from beatheritage_b200.conv_stem import ConvStem
+    with pytest.raises(ValueError):
+        ConvStem(465, 768)
+    stem = make_stem(80, 128, dev)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        stem(torch.zeros(1, 64, 80, dtype=torch.bfloat16))
+    with pytest.raises(RuntimeError, match="bfloat16"):
+        stem(torch.zeros(1, 64, 80, device=dev))
+    with pytest.raises(RuntimeError, match="even"):
+        stem(torch.zeros(1, 63, 80, dtype=torch.bfloat16, device=dev))
+    with pytest.raises(RuntimeError, match="channels-last"):
+        stem(torch.zeros(1, 80, 64, dtype=torch.bfloat16, device=dev))
