@@ -27,6 +27,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -60,6 +61,7 @@ struct StemProblem {
   int32_t c_in;            // channels per tap
   int32_t tap_col[3];      // column offset of each tap inside a row of the A view
   int32_t tap_row[3];      // row offset of each tap
+  int32_t exp;             // timing experiments (wrong results): 1 no W loads, 2 no epilogue math / stores, 4 no A loads
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -74,6 +76,22 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+#ifdef BHSTEM_PROFILE
+// -DBHSTEM_PROFILE (tools only): cycles each role spends waiting on its barriers, summed over CTAs.
+// [0] producer on A-empty, [1] producer on W-empty, [2] MMA on A-full, [3] MMA on W-full, [4] MMA on
+// TMEM-empty, [5] epilogue on TMEM-full, [6] kernel cycles (per CTA, summed), [7] CTAs
+__device__ unsigned long long g_prof[8];
+#define PROF_T0() const long long prof_t0 = clock64()
+#define PROF_ADD(slot) prof[slot] += clock64() - prof_t0
+#define PROF_DECL() long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define PROF_FLUSH(slot) atomicAdd(&g_prof[slot], static_cast<unsigned long long>(prof[slot]))
+#else
+#define PROF_T0()
+#define PROF_ADD(slot)
+#define PROF_DECL()
+#define PROF_FLUSH(slot)
+#endif
+
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   for (;;) {
@@ -107,6 +125,13 @@ __device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
   return d;
 }
 
+// An operand may start any number of ROWS (128 bytes each) into a staged block: measured on B200, the
+// 128-byte swizzle is a function of the absolute shared-memory address bits (chunk ^= row & 7 with the
+// ring 1024-byte aligned), so a descriptor whose start address is moved down by k * 128 bytes reads rows
+// k, k+1, ... correctly with the base-offset field (bits 49-51) left at 0 -- setting it to
+// (address >> 7) & 7, or to its negative, gives wrong results.  This is what lets the three taps of the
+// convolution read ONE staged block of rows at row offsets 0 / 1 / 2.
+
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
@@ -135,11 +160,81 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // conv output rounded to bf16, exact GELU in fp32 on that value (torch: gelu(conv(x)) under bf16)
 __device__ __forceinline__ float conv_gelu(float acc_plus_bias) {
   const float x = __bfloat162float(__float2bfloat16_rn(acc_plus_bias));
+#ifdef BHSTEM_TIMING_NO_GELU      // timing experiments only: wrong results
+  return x;
+#endif
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+// Epilogue role (warps 2-5 of either kernel): TMEM accumulator -> + bias -> bf16 (the conv output) ->
+// erf GELU in fp32 -> bf16 -> HBM.  A lane owns one output ROW of the tile (TMEM lane = row), so storing
+// from registers would scatter 16-byte pieces over 32 rows per instruction (measured: the stores, not the
+// GELU, cost 27 % of the kernel).  Each 32-column chunk is therefore turned round through a 2 KB
+// per-warp staging block (16-byte pieces XOR-swizzled by (row >> 1) & 3: conflict-free both ways) and
+// leaves as 64-byte row segments, 8 rows per store instruction.
+constexpr int EPI_STAGE_BYTES = 32 * 64;
+
+template <int BN>
+__device__ __forceinline__ void epilogue_role(const StemProblem& p, const float* __restrict__ bias,
+                                              __nv_bfloat16* __restrict__ out, uint32_t tmem_base, uint32_t tfull0,
+                                              uint32_t tempty0, int warp, int lane, uint8_t* staging_all) {
+  const int tiles_per_batch = p.m_tiles * p.n_tiles;
+  const int num_tiles = p.batches * tiles_per_batch;
+  const int quarter = warp & 3;                            // TMEM lanes this warp may touch: 32 * (warp % 4) ...
+  uint8_t* staging = staging_all + quarter * EPI_STAGE_BYTES;
+  const int wr_swz = (lane >> 1) & 3;                      // my row's XOR phase when writing
+  const int rd_row = lane >> 2, rd_piece = lane & 3;       // read-back: 4 lanes per row, 8 rows per pass
+  uint32_t local = 0;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    const int b = tile / tiles_per_batch, rem = tile % tiles_per_batch;
+    const int mt = rem / p.n_tiles, nt = rem % p.n_tiles;
+    const uint32_t as = local & 1, aphase = (local >> 1) & 1;
+    const int row0 = mt * BLOCK_M + quarter * 32;          // first row of this warp's 32-row slab
+    __nv_bfloat16* oslab = out + (static_cast<size_t>(b) * p.rows_out + row0) * p.n_out + nt * BN;
+    const float* brow = bias + nt * BN;
+#ifdef BHSTEM_PROFILE
+    { const long long t0p = clock64(); mbar_wait(tfull0 + 8 * as, aphase); if (warp == 2 && lane == 0) atomicAdd(&g_prof[5], static_cast<unsigned long long>(clock64() - t0p)); }
+#else
+    mbar_wait(tfull0 + 8 * as, aphase);
+#endif
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      __syncwarp();                                        // tcgen05.ld is warp-collective; staging reads of the last chunk are done
+      tmem_ld32(taddr + c * 32, r);
+      if (c == BN / 32 - 1) {                              // everything is in registers: hand the stage back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+      }
+      if (p.exp & 2) continue;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(brow + c * 32 + j));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(brow + c * 32 + j + 4));
+        uint4 v;
+        v.x = pack_bf16(conv_gelu(__uint_as_float(r[j + 0]) + b0.x), conv_gelu(__uint_as_float(r[j + 1]) + b0.y));
+        v.y = pack_bf16(conv_gelu(__uint_as_float(r[j + 2]) + b0.z), conv_gelu(__uint_as_float(r[j + 3]) + b0.w));
+        v.z = pack_bf16(conv_gelu(__uint_as_float(r[j + 4]) + b1.x), conv_gelu(__uint_as_float(r[j + 5]) + b1.y));
+        v.w = pack_bf16(conv_gelu(__uint_as_float(r[j + 6]) + b1.z), conv_gelu(__uint_as_float(r[j + 7]) + b1.w));
+        *reinterpret_cast<uint4*>(staging + lane * 64 + (((j >> 3) ^ wr_swz) << 4)) = v;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int pass = 0; pass < 4; ++pass) {
+        const int rr = pass * 8 + rd_row;
+        const uint4 v = *reinterpret_cast<const uint4*>(staging + rr * 64 + ((rd_piece ^ ((rr >> 1) & 3)) << 4));
+        if (row0 + rr < p.rows_out)
+          *reinterpret_cast<uint4*>(oslab + static_cast<size_t>(rr) * p.n_out + c * 32 + rd_piece * 8) = v;
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------ kernel
@@ -151,6 +246,7 @@ bhstem_conv_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) unsigned long long bars[2 * STAGES + 4];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(128) uint8_t epi_staging[4 * EPI_STAGE_BYTES];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -230,47 +326,165 @@ bhstem_conv_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     }
   } else {
     // ===================================== epilogue =========================================
-    const int quarter = warp & 3;                          // TMEM lanes this warp may touch: 32 * (warp % 4) ...
-    const int row_in_tile = quarter * 32 + lane;
-    uint32_t local = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-      const int b = tile / tiles_per_batch, rem = tile % tiles_per_batch;
-      const int mt = rem / p.n_tiles, nt = rem % p.n_tiles;
-      const uint32_t as = local & 1, aphase = (local >> 1) & 1;
-      const int row = mt * BLOCK_M + row_in_tile;
-      const bool valid = row < p.rows_out;
-      __nv_bfloat16* orow = out + (static_cast<size_t>(b) * p.rows_out + (valid ? row : 0)) * p.n_out + nt * BN;
-      const float* brow = bias + nt * BN;
-      mbar_wait(tfull0 + 8 * as, aphase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        __syncwarp();                                      // tcgen05.ld is warp-collective (.sync.aligned)
-        tmem_ld32(taddr + c * 32, r);
-        if (c == BN / 32 - 1) {                            // everything is in registers: hand the stage back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty0 + 8 * as);
-        }
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(brow + c * 32 + j));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(brow + c * 32 + j + 4));
-            uint4 v;
-            v.x = pack_bf16(conv_gelu(__uint_as_float(r[j + 0]) + b0.x), conv_gelu(__uint_as_float(r[j + 1]) + b0.y));
-            v.y = pack_bf16(conv_gelu(__uint_as_float(r[j + 2]) + b0.z), conv_gelu(__uint_as_float(r[j + 3]) + b0.w));
-            v.z = pack_bf16(conv_gelu(__uint_as_float(r[j + 4]) + b1.x), conv_gelu(__uint_as_float(r[j + 5]) + b1.y));
-            v.w = pack_bf16(conv_gelu(__uint_as_float(r[j + 6]) + b1.z), conv_gelu(__uint_as_float(r[j + 7]) + b1.w));
-            *reinterpret_cast<uint4*>(orow + c * 32 + j) = v;
+    epilogue_role<BN>(p, bias, out, tmem_base, tfull0, tempty0, warp, lane, epi_staging);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS));
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------ kernel, shared taps
+// Same tiles, roles and epilogue, but the activation rows are staged ONCE per 64-channel block and all
+// taps that read them use row-shifted descriptors on that one block (sw128_desc_shifted):
+//   conv1   one block of 136 rows from row t0-1: taps 0 / 1 / 2 start 0 / 1 / 2 rows in
+//   conv2   (two-steps-per-row view) the odd half from row t0-1 (taps 0 and 2 at shifts 0 / 1) and the
+//           even half from row t0 (tap 1)
+// The per-SM TMA ingest rate (~46 B/clk) is what bounds this kernel, not the tensor pipe: per 64-channel
+// block and tile the per-tap kernel above stages 3 x 48 KB, this one 17 (+16) KB + 3 x 32 KB.
+constexpr int A0_ROWS = 136, A0_BYTES = A0_ROWS * 128, A1_BYTES = BLOCK_M * 128;
+constexpr int ASTAGE_BYTES = A0_BYTES + A1_BYTES;          // 33 KB, a multiple of 1024
+constexpr int A_STAGES = 2, W_STAGES = 4;
+
+template <int BN>
+struct CfgShared {
+  static constexpr int W_BYTES = BN * BLOCK_K * 2;
+  static constexpr int SMEM_BYTES = A_STAGES * ASTAGE_BYTES + W_STAGES * W_BYTES + 1024;
+  static constexpr int TMEM_COLS = 2 * BN;
+};
+
+struct SharedTaps {
+  int32_t n_aloads;        // 1 (conv1) or 2 (conv2)
+  int32_t a_col[2];        // column offset of each staged block inside a row of the A view
+  int32_t a_row[2];        // row offset of each staged block relative to the tile's first row
+  int32_t tap_buf[3];      // which staged block a tap reads
+  int32_t tap_shift[3];    // how many rows into it the tap starts
+};
+
+template <int BN>
+__global__ void __launch_bounds__(THREADS, 1)
+bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                               const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias,
+                               __nv_bfloat16* __restrict__ out, const StemProblem p, const SharedTaps st) {
+  using C = CfgShared<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) unsigned long long bars[2 * A_STAGES + 2 * W_STAGES + 4];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(128) uint8_t epi_staging[4 * EPI_STAGE_BYTES];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ring_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t ring_w = ring_a + A_STAGES * ASTAGE_BYTES;
+  const uint32_t afull0 = smem_u32(&bars[0]), aempty0 = smem_u32(&bars[A_STAGES]);
+  const uint32_t wfull0 = smem_u32(&bars[2 * A_STAGES]), wempty0 = smem_u32(&bars[2 * A_STAGES + W_STAGES]);
+  const uint32_t tfull0 = smem_u32(&bars[2 * A_STAGES + 2 * W_STAGES]), tempty0 = tfull0 + 16;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < A_STAGES; ++s) { mbar_init(afull0 + 8 * s, 1); mbar_init(aempty0 + 8 * s, 1); }
+    for (int s = 0; s < W_STAGES; ++s) { mbar_init(wfull0 + 8 * s, 1); mbar_init(wempty0 + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "n"(C::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int tiles_per_batch = p.m_tiles * p.n_tiles;
+  const int num_tiles = p.batches * tiles_per_batch;
+  const uint32_t a_bytes = A0_BYTES + (st.n_aloads == 2 ? A1_BYTES : 0);
+  PROF_DECL();
+#ifdef BHSTEM_PROFILE
+  const long long prof_start = clock64();
+#endif
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      uint32_t as = 0, aph = 0, ws = 0, wph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_batch, rem = tile % tiles_per_batch;
+        const int mt = rem / p.n_tiles, nt = rem % p.n_tiles;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          { PROF_T0(); mbar_wait(aempty0 + 8 * as, aph ^ 1); PROF_ADD(0); }
+          const uint32_t sa = ring_a + as * ASTAGE_BYTES;
+          if (p.exp & 4) {
+            mbar_arrive(afull0 + 8 * as);
+          } else {
+            mbar_expect_tx(afull0 + 8 * as, a_bytes);
+            tma_load_3d(&map_a0, afull0 + 8 * as, sa, st.a_col[0] + kb * BLOCK_K, mt * BLOCK_M + st.a_row[0], b);
+            if (st.n_aloads == 2)
+              tma_load_3d(&map_a1, afull0 + 8 * as, sa + A0_BYTES, st.a_col[1] + kb * BLOCK_K, mt * BLOCK_M + st.a_row[1], b);
+          }
+          if (++as == A_STAGES) { as = 0; aph ^= 1; }
+          for (int tap = 0; tap < 3; ++tap) {
+            { PROF_T0(); mbar_wait(wempty0 + 8 * ws, wph ^ 1); PROF_ADD(1); }
+            if (p.exp & 1) {
+              mbar_arrive(wfull0 + 8 * ws);
+            } else {
+              mbar_expect_tx(wfull0 + 8 * ws, C::W_BYTES);
+              tma_load_3d(&map_w, wfull0 + 8 * ws, ring_w + ws * C::W_BYTES, kb * BLOCK_K, nt * BN, tap);
+            }
+            if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
           }
         }
       }
     }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
+                                 (static_cast<uint32_t>(BLOCK_M >> 4) << 24);
+      uint32_t as = 0, aph = 0, ws = 0, wph = 0, local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const uint32_t acc = local & 1, accphase = (local >> 1) & 1;
+        { PROF_T0(); mbar_wait(tempty0 + 8 * acc, accphase ^ 1); PROF_ADD(4); }
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          const int rem_c = p.c_in - kb * BLOCK_K;
+          const int ksteps = rem_c >= BLOCK_K ? BLOCK_K / UMMA_K : (rem_c + UMMA_K - 1) / UMMA_K;
+          { PROF_T0(); mbar_wait(afull0 + 8 * as, aph); PROF_ADD(2); }
+          const uint32_t sa = ring_a + as * ASTAGE_BYTES;
+          for (int tap = 0; tap < 3; ++tap) {
+            { PROF_T0(); mbar_wait(wfull0 + 8 * ws, wph); PROF_ADD(3); }
+            tc_fence_after();
+            const uint32_t aaddr = sa + st.tap_buf[tap] * A0_BYTES + st.tap_shift[tap] * 128;
+            const uint64_t adesc = sw128_desc(aaddr);      // row-shifted start, base offset 0 (measured: see above)
+            const uint64_t bdesc = sw128_desc(ring_w + ws * C::W_BYTES);
+            for (int k = 0; k < ksteps; ++k)
+              umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | tap | k) != 0);
+            umma_commit(wempty0 + 8 * ws);
+            if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
+          }
+          umma_commit(aempty0 + 8 * as);                   // all three taps have read the staged rows
+          if (++as == A_STAGES) { as = 0; aph ^= 1; }
+        }
+        umma_commit(tfull0 + 8 * acc);
+      }
+    }
+  } else {
+    epilogue_role<BN>(p, bias, out, tmem_base, tfull0, tempty0, warp, lane, epi_staging);
   }
 
+#ifdef BHSTEM_PROFILE
+  if (lane == 0 && warp == 0) { PROF_FLUSH(0); PROF_FLUSH(1); }
+  if (lane == 0 && warp == 1) {
+    PROF_FLUSH(2); PROF_FLUSH(3); PROF_FLUSH(4);
+    atomicAdd(&g_prof[6], static_cast<unsigned long long>(clock64() - prof_start));
+    atomicAdd(&g_prof[7], 1ull);
+  }
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -327,6 +541,7 @@ struct bhstem_handle {
   CUtensorMap map_w1, map_w2;
   EncodeTiledFn enc = nullptr;
   long long launches = 0;
+  int variant = 1;      // 1: shared taps (row-shifted descriptors, default), 0: one TMA box per tap
 };
 
 namespace {
@@ -367,8 +582,41 @@ int launch_stage(bhstem_handle* h, int stage, const void* in, int64_t B, int64_t
   p.n_out = h->d;
   p.c_in = c;
   p.k_blocks = (c + BLOCK_K - 1) / BLOCK_K;
+  p.exp = getenv("BHSTEM_EXP") ? atoi(getenv("BHSTEM_EXP")) : 0;   // timing experiments only
   const long long tiles = static_cast<long long>(p.batches) * p.m_tiles * p.n_tiles;
   const int grid = static_cast<int>(tiles < h->sms ? tiles : h->sms);
+  if (h->variant == 1) {
+    SharedTaps st{};
+    CUtensorMap map_a0, map_a1;
+    if (stage == 1) {
+      st.n_aloads = 1;
+      st.a_col[0] = 0; st.a_row[0] = -1;
+      for (int t = 0; t < 3; ++t) { st.tap_buf[t] = 0; st.tap_shift[t] = t; }
+      rc = make_map(h->enc, &map_a0, in, c, T, B, static_cast<uint64_t>(c) * 2, static_cast<uint64_t>(T) * c * 2, A0_ROWS);
+      map_a1 = map_a0;
+    } else {
+      st.n_aloads = 2;
+      st.a_col[0] = c; st.a_row[0] = -1;                   // odd time steps, from the previous row on
+      st.a_col[1] = 0; st.a_row[1] = 0;                    // even time steps
+      st.tap_buf[0] = 0; st.tap_shift[0] = 0;
+      st.tap_buf[1] = 1; st.tap_shift[1] = 0;
+      st.tap_buf[2] = 0; st.tap_shift[2] = 1;
+      rc = make_map(h->enc, &map_a0, in, 2 * static_cast<uint64_t>(c), T / 2, B, static_cast<uint64_t>(c) * 4,
+                    static_cast<uint64_t>(T) * c * 2, A0_ROWS);
+      map_a1 = map_a;
+    }
+    if (rc != BHSTEM_OK) return rc;
+    auto kernel = bhstem_conv_gelu_shared_kernel<BN>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgShared<BN>::SMEM_BYTES);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+    kernel<<<grid, THREADS, CfgShared<BN>::SMEM_BYTES, stream>>>(map_a0, map_a1, stage == 1 ? h->map_w1 : h->map_w2,
+                                                                 stage == 1 ? h->b1 : h->b2,
+                                                                 static_cast<__nv_bfloat16*>(out), p, st);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    ++h->launches;
+    return BHSTEM_OK;
+  }
   auto kernel = bhstem_conv_gelu_kernel<BN>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
@@ -396,6 +644,15 @@ int check_call(bhstem_handle* h, const void* in, int64_t B, int64_t T, void* out
 
 extern "C" {
 
+#ifdef BHSTEM_PROFILE
+// tools only (not in include/bhstem.h): read and clear the role wait counters
+int bhstem_debug_profile(unsigned long long* out8) {
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (cudaMemcpyFromSymbol(out8, g_prof, sizeof(z)) != cudaSuccess) return 1;
+  return cudaMemcpyToSymbol(g_prof, z, sizeof(z)) != cudaSuccess;
+}
+#endif
+
 int bhstem_version(void) { return BHSTEM_VERSION; }
 const char* bhstem_last_error(void) { return g_err.c_str(); }
 int64_t bhstem_launch_count(const bhstem_handle* h) { return h ? h->launches : 0; }
@@ -421,6 +678,8 @@ int bhstem_create(int32_t c_in, int32_t d_model, const float* conv1_weight, cons
   h->c_in = c_in;
   h->d = d_model;
   h->bn = d_model % 256 == 0 ? 256 : 128;
+  h->variant = 1;
+  if (const char* v = getenv("BHSTEM_VARIANT")) h->variant = atoi(v) == 0 ? 0 : 1;   // A/B: 0 = one TMA box per tap
   h->enc = encode_tiled_fn();
   if (!h->enc) { delete h; return fail(BHSTEM_ECUDA, "cuTensorMapEncodeTiled is not available from this driver"); }
   const std::vector<__nv_bfloat16> w1 = pack_weight(conv1_weight, d_model, c_in), w2 = pack_weight(conv2_weight, d_model, d_model);
