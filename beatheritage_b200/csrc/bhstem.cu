@@ -76,11 +76,28 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {     // barrier in any CTA of the cluster
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t cta_addr, uint32_t rank) {   // shared::cta -> shared::cluster
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 #ifdef BHSTEM_PROFILE
 // -DBHSTEM_PROFILE (tools only): cycles each role spends waiting on its barriers, summed over CTAs.
 // [0] producer on A-empty, [1] producer on W-empty, [2] MMA on A-full, [3] MMA on W-full, [4] MMA on
 // TMEM-empty, [5] epilogue on TMEM-full, [6] kernel cycles (per CTA, summed), [7] CTAs
-__device__ unsigned long long g_prof[8];
+__device__ unsigned long long g_prof[12];   // [8] / [9]: SM cycles / nanoseconds of CTA 0 (the real SM clock)
 #define PROF_T0() const long long prof_t0 = clock64()
 #define PROF_ADD(slot) prof[slot] += clock64() - prof_t0
 #define PROF_DECL() long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}
@@ -181,7 +198,9 @@ constexpr int EPI_STAGE_BYTES = 32 * 64;
 template <int BN>
 __device__ __forceinline__ void epilogue_role(const StemProblem& p, const float* __restrict__ bias,
                                               __nv_bfloat16* __restrict__ out, uint32_t tmem_base, uint32_t tfull0,
-                                              uint32_t tempty0, int warp, int lane, uint8_t* staging_all) {
+                                              uint32_t tempty0, int warp, int lane, uint8_t* staging_all,
+                                              int tile0 = blockIdx.x, int tile_step = gridDim.x, int tile_rows = BLOCK_M,
+                                              int row_off = 0, bool tempty_is_cluster_addr = false) {
   const int tiles_per_batch = p.m_tiles * p.n_tiles;
   const int num_tiles = p.batches * tiles_per_batch;
   const int quarter = warp & 3;                            // TMEM lanes this warp may touch: 32 * (warp % 4) ...
@@ -189,11 +208,11 @@ __device__ __forceinline__ void epilogue_role(const StemProblem& p, const float*
   const int wr_swz = (lane >> 1) & 3;                      // my row's XOR phase when writing
   const int rd_row = lane >> 2, rd_piece = lane & 3;       // read-back: 4 lanes per row, 8 rows per pass
   uint32_t local = 0;
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+  for (int tile = tile0; tile < num_tiles; tile += tile_step, ++local) {
     const int b = tile / tiles_per_batch, rem = tile % tiles_per_batch;
     const int mt = rem / p.n_tiles, nt = rem % p.n_tiles;
     const uint32_t as = local & 1, aphase = (local >> 1) & 1;
-    const int row0 = mt * BLOCK_M + quarter * 32;          // first row of this warp's 32-row slab
+    const int row0 = mt * tile_rows + row_off + quarter * 32;          // first row of this warp's 32-row slab
     __nv_bfloat16* oslab = out + (static_cast<size_t>(b) * p.rows_out + row0) * p.n_out + nt * BN;
     const float* brow = bias + nt * BN;
 #ifdef BHSTEM_PROFILE
@@ -211,7 +230,10 @@ __device__ __forceinline__ void epilogue_role(const StemProblem& p, const float*
       if (c == BN / 32 - 1) {                              // everything is in registers: hand the stage back
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+        if (lane == 0) {
+          if (tempty_is_cluster_addr) mbar_arrive_cluster(tempty0 + 8 * as);
+          else mbar_arrive(tempty0 + 8 * as);
+        }
       }
       if (p.exp & 2) continue;
 #pragma unroll
@@ -406,6 +428,8 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
   PROF_DECL();
 #ifdef BHSTEM_PROFILE
   const long long prof_start = clock64();
+  unsigned long long prof_ns0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_ns0));
 #endif
 
   if (warp == 0) {
@@ -483,6 +507,12 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
     PROF_FLUSH(2); PROF_FLUSH(3); PROF_FLUSH(4);
     atomicAdd(&g_prof[6], static_cast<unsigned long long>(clock64() - prof_start));
     atomicAdd(&g_prof[7], 1ull);
+    if (blockIdx.x == 0) {
+      unsigned long long ns1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+      g_prof[8] = static_cast<unsigned long long>(clock64() - prof_start);
+      g_prof[9] = ns1 - prof_ns0;
+    }
   }
 #endif
   tc_fence_before();
@@ -491,6 +521,154 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
     tc_fence_after();
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS));
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------ kernel, CTA pairs
+// Two CTAs of a cluster (the two SMs of a TPC) own one 256-row x 256-channel tile: tcgen05.mma.cta_group::2
+// multiplies the pair's 256 activation rows (128 staged in each CTA) with a 256-row weight tile of which
+// each CTA stages only HALF (128 rows, 16 KB instead of 32) -- the weights are what the per-tap / shared-tap
+// kernels above spend most of their TMA ingest on.  The leader (cluster rank 0) issues every MMA; both
+// CTAs' TMA loads complete on the LEADER's full barriers (cp.async.bulk.tensor.cta_group::2), its
+// tcgen05.commit frees the stages / publishes the accumulators in BOTH CTAs (multicast), and both CTAs'
+// epilogue warps hand the accumulator stage back on the leader's TMEM-empty barrier.
+constexpr int PAIR_W_BYTES = 128 * BLOCK_K * 2;            // half of a 256-row weight tile
+constexpr int PAIR_W_STAGES = 8, PAIR_A_STAGES = 2;
+constexpr int PAIR_ASTAGE_BYTES = A0_BYTES + A1_BYTES;
+constexpr int PAIR_SMEM_BYTES = PAIR_A_STAGES * PAIR_ASTAGE_BYTES + PAIR_W_STAGES * PAIR_W_BYTES + 1024;
+constexpr int PAIR_BN = 256;
+
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* map, uint32_t leader_bar_cluster, uint32_t dst,
+                                                 int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(leader_bar_cluster)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {     // arrives on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                             const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias,
+                             __nv_bfloat16* __restrict__ out, const StemProblem p, const SharedTaps st) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) unsigned long long bars[2 * PAIR_A_STAGES + 2 * PAIR_W_STAGES + 4];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(128) uint8_t epi_staging[4 * EPI_STAGE_BYTES];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const bool leader = rank == 0;
+  const uint32_t ring_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t ring_w = ring_a + PAIR_A_STAGES * PAIR_ASTAGE_BYTES;
+  const uint32_t afull0 = smem_u32(&bars[0]), aempty0 = smem_u32(&bars[PAIR_A_STAGES]);
+  const uint32_t wfull0 = smem_u32(&bars[2 * PAIR_A_STAGES]), wempty0 = smem_u32(&bars[2 * PAIR_A_STAGES + PAIR_W_STAGES]);
+  const uint32_t tfull0 = smem_u32(&bars[2 * PAIR_A_STAGES + 2 * PAIR_W_STAGES]), tempty0 = tfull0 + 16;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < PAIR_A_STAGES; ++s) { mbar_init(afull0 + 8 * s, 1); mbar_init(aempty0 + 8 * s, 1); }
+    for (int s = 0; s < PAIR_W_STAGES; ++s) { mbar_init(wfull0 + 8 * s, 1); mbar_init(wempty0 + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 8); }   // 4 epilogue warps x 2 CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {          // the same warp of BOTH CTAs allocates (cta_group::2), same destination slot
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "n"(2 * PAIR_BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  cluster_sync_all();       // both CTAs' barriers are initialised before anyone signals across
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int tiles_per_batch = p.m_tiles * p.n_tiles;       // m_tiles counts 256-row tiles here
+  const int num_tiles = p.batches * tiles_per_batch;
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const uint32_t a_bytes = A0_BYTES + (st.n_aloads == 2 ? A1_BYTES : 0);
+
+  if (warp == 0) {
+    // ===================================== TMA producer (both CTAs) =========================
+    if (lane == 0) {
+      const uint32_t afull_leader = map_to_cta(afull0, 0), wfull_leader = map_to_cta(wfull0, 0);
+      uint32_t as = 0, aph = 0, ws = 0, wph = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        const int b = tile / tiles_per_batch, rem = tile % tiles_per_batch;
+        const int mt = rem / p.n_tiles, nt = rem % p.n_tiles;
+        const int my_row = mt * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(aempty0 + 8 * as, aph ^ 1);
+          const uint32_t sa = ring_a + as * PAIR_ASTAGE_BYTES;
+          if (leader) mbar_expect_tx(afull0 + 8 * as, 2 * a_bytes);           // both CTAs' activation blocks
+          tma_load_3d_pair(&map_a0, afull_leader + 8 * as, sa, st.a_col[0] + kb * BLOCK_K, my_row + st.a_row[0], b);
+          if (st.n_aloads == 2)
+            tma_load_3d_pair(&map_a1, afull_leader + 8 * as, sa + A0_BYTES, st.a_col[1] + kb * BLOCK_K, my_row + st.a_row[1], b);
+          if (++as == PAIR_A_STAGES) { as = 0; aph ^= 1; }
+          for (int tap = 0; tap < 3; ++tap) {
+            mbar_wait(wempty0 + 8 * ws, wph ^ 1);
+            if (leader) mbar_expect_tx(wfull0 + 8 * ws, 2 * PAIR_W_BYTES);    // both halves of the weight tile
+            tma_load_3d_pair(&map_w, wfull_leader + 8 * ws, ring_w + ws * PAIR_W_BYTES, kb * BLOCK_K,
+                             nt * PAIR_BN + static_cast<int>(rank) * 128, tap);
+            if (++ws == PAIR_W_STAGES) { ws = 0; wph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      // D = F32, A = B = BF16, K-major, N = 256, M = 256 across the pair
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(PAIR_BN >> 3) << 17) |
+                                 (static_cast<uint32_t>(256 >> 4) << 24);
+      uint32_t as = 0, aph = 0, ws = 0, wph = 0, local = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++local) {
+        const uint32_t acc = local & 1, accphase = (local >> 1) & 1;
+        mbar_wait(tempty0 + 8 * acc, accphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * PAIR_BN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          const int rem_c = p.c_in - kb * BLOCK_K;
+          const int ksteps = rem_c >= BLOCK_K ? BLOCK_K / UMMA_K : (rem_c + UMMA_K - 1) / UMMA_K;
+          mbar_wait(afull0 + 8 * as, aph);
+          const uint32_t sa = ring_a + as * PAIR_ASTAGE_BYTES;
+          for (int tap = 0; tap < 3; ++tap) {
+            mbar_wait(wfull0 + 8 * ws, wph);
+            tc_fence_after();
+            const uint64_t adesc = sw128_desc(sa + st.tap_buf[tap] * A0_BYTES + st.tap_shift[tap] * 128);
+            const uint64_t bdesc = sw128_desc(ring_w + ws * PAIR_W_BYTES);
+            for (int k = 0; k < ksteps; ++k)
+              umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | tap | k) != 0);
+            umma_commit_pair(wempty0 + 8 * ws);
+            if (++ws == PAIR_W_STAGES) { ws = 0; wph ^= 1; }
+          }
+          umma_commit_pair(aempty0 + 8 * as);
+          if (++as == PAIR_A_STAGES) { as = 0; aph ^= 1; }
+        }
+        umma_commit_pair(tfull0 + 8 * acc);
+      }
+    }
+  } else {
+    epilogue_role<PAIR_BN>(p, bias, out, tmem_base, tfull0, map_to_cta(tempty0, 0), warp, lane, epi_staging, pair_id,
+                           num_pairs, 2 * BLOCK_M, static_cast<int>(rank) * BLOCK_M, true);
+  }
+
+  tc_fence_before();
+  cluster_sync_all();       // the peer's shared memory and barriers stay alive until both CTAs are done
+  if (warp == 1) {
+    tc_fence_after();
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * PAIR_BN));
   }
 }
 
@@ -539,9 +717,11 @@ struct bhstem_handle {
   __nv_bfloat16 *w1 = nullptr, *w2 = nullptr;   // [3][D][C] tap-major, bf16
   float *b1 = nullptr, *b2 = nullptr;
   CUtensorMap map_w1, map_w2;
+  CUtensorMap map_w1_half, map_w2_half;   // 128-row boxes for the CTA-pair kernel (bn == 256 only)
   EncodeTiledFn enc = nullptr;
   long long launches = 0;
   int variant = 1;      // 1: shared taps (row-shifted descriptors, default), 0: one TMA box per tap
+  int pairs = 0;        // 1: CTA-pair kernel (tcgen05 cta_group::2) when d_model % 256 == 0
 };
 
 namespace {
@@ -606,6 +786,22 @@ int launch_stage(bhstem_handle* h, int stage, const void* in, int64_t B, int64_t
       map_a1 = map_a;
     }
     if (rc != BHSTEM_OK) return rc;
+    if (BN == 256 && h->pairs && (h->sms & 1) == 0) {
+      StemProblem pp = p;
+      pp.m_tiles = (p.rows_out + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+      const long long pair_tiles = static_cast<long long>(pp.batches) * pp.m_tiles * pp.n_tiles;
+      const int pgrid = 2 * static_cast<int>(pair_tiles < h->sms / 2 ? pair_tiles : h->sms / 2);
+      cudaError_t e = cudaFuncSetAttribute(bhstem_conv_gelu_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           PAIR_SMEM_BYTES);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+      bhstem_conv_gelu_pair_kernel<<<pgrid, THREADS, PAIR_SMEM_BYTES, stream>>>(
+          map_a0, map_a1, stage == 1 ? h->map_w1_half : h->map_w2_half, stage == 1 ? h->b1 : h->b2,
+          static_cast<__nv_bfloat16*>(out), pp, st);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+      ++h->launches;
+      return BHSTEM_OK;
+    }
     auto kernel = bhstem_conv_gelu_shared_kernel<BN>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgShared<BN>::SMEM_BYTES);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
@@ -647,7 +843,7 @@ extern "C" {
 #ifdef BHSTEM_PROFILE
 // tools only (not in include/bhstem.h): read and clear the role wait counters
 int bhstem_debug_profile(unsigned long long* out8) {
-  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long z[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (cudaMemcpyFromSymbol(out8, g_prof, sizeof(z)) != cudaSuccess) return 1;
   return cudaMemcpyToSymbol(g_prof, z, sizeof(z)) != cudaSuccess;
 }
@@ -679,7 +875,7 @@ int bhstem_create(int32_t c_in, int32_t d_model, const float* conv1_weight, cons
   h->d = d_model;
   h->bn = d_model % 256 == 0 ? 256 : 128;
   h->variant = 1;
-  if (const char* v = getenv("BHSTEM_VARIANT")) h->variant = atoi(v) == 0 ? 0 : 1;   // A/B: 0 = one TMA box per tap
+  if (const char* v = getenv("BHSTEM_VARIANT")) { h->variant = atoi(v) == 0 ? 0 : 1; h->pairs = atoi(v) == 2; }   // A/B: 0 = one TMA box per tap
   h->enc = encode_tiled_fn();
   if (!h->enc) { delete h; return fail(BHSTEM_ECUDA, "cuTensorMapEncodeTiled is not available from this driver"); }
   const std::vector<__nv_bfloat16> w1 = pack_weight(conv1_weight, d_model, c_in), w2 = pack_weight(conv2_weight, d_model, d_model);
@@ -705,6 +901,13 @@ int bhstem_create(int32_t c_in, int32_t d_model, const float* conv1_weight, cons
   if (rc == BHSTEM_OK)
     rc = make_map(h->enc, &h->map_w2, h->w2, d_model, d_model, 3, static_cast<uint64_t>(d_model) * 2,
                   static_cast<uint64_t>(d_model) * d_model * 2, h->bn);
+  if (rc == BHSTEM_OK && h->bn == 256) {
+    rc = make_map(h->enc, &h->map_w1_half, h->w1, c_in, d_model, 3, static_cast<uint64_t>(c_in) * 2,
+                  static_cast<uint64_t>(d_model) * c_in * 2, 128);
+    if (rc == BHSTEM_OK)
+      rc = make_map(h->enc, &h->map_w2_half, h->w2, d_model, d_model, 3, static_cast<uint64_t>(d_model) * 2,
+                    static_cast<uint64_t>(d_model) * d_model * 2, 128);
+  }
   if (rc != BHSTEM_OK) { bhstem_destroy(h); return rc; }
   *out = h;
   return BHSTEM_OK;

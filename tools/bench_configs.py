@@ -205,6 +205,40 @@ def main():
                     tf, tt = run(mel, batch, fused=True)
                     c5[f"ours_fused_encoder_input_{mode}"] = {"frontend_plus_assembly_ms_incl_h2d": 1e3 * tf,
                                                               "total_ms": 1e3 * tt, "frontend_share": tf / tt}
+            # N3: the encoder's conv stem (modeling_ropewhisper.py:1206-1209 / the stock encoder's first lines)
+            # behind the frontend: reference ops end to end vs forward_encoder_input (channels last) + ConvStem
+            from beatheritage_b200.conv_stem import ConvStem
+            stem = ConvStem.from_encoder(enc)
+            gelu = torch.nn.functional.gelu
+            stem_res = {}
+            with torch.no_grad():
+                for mode, batch in (("sequential_b1", 1), ("parallel_b6", 6)):
+                    xd = seq_host[:batch].to(dev)
+                    cvec = cond[:, 0].expand(batch, -1)
+
+                    def ref_ops():
+                        fr = mel(xd).to(torch.bfloat16)
+                        fr = torch.cat([fr, cond.expand(batch, fr.shape[1], -1)], dim=-1).swapaxes(1, 2)
+                        return gelu(enc.conv2(gelu(enc.conv1(fr)))).permute(0, 2, 1)
+
+                    def ref_stem_only(fr_bct):
+                        return gelu(enc.conv2(gelu(enc.conv1(fr_bct)))).permute(0, 2, 1)
+
+                    def ours():
+                        return stem(mel.forward_encoder_input(xd, [cvec], channels_first=False))
+
+                    fr_btc = mel.forward_encoder_input(xd, [cvec], channels_first=False)
+                    fr_bct = fr_btc.swapaxes(1, 2).contiguous()
+                    a, b = ref_ops().float(), ours().float()
+                    stem_res[mode] = {
+                        "reference_ops_frontend_to_stem_ms": timed(ref_ops, 20),
+                        "ours_frontend_to_stem_ms": timed(ours, 20),
+                        "stem_only_torch_cudnn_ms": timed(lambda: ref_stem_only(fr_bct), 20),
+                        "stem_only_ours_ms": timed(lambda: stem(fr_btc), 20),
+                        "max_abs_diff": float((a - b).abs().max()),
+                        "max_abs_value": float(a.abs().max()),
+                    }
+            c5["conv_stem_N3"] = stem_res
             res["C5_inference_slice"] = c5
         except Exception as e:
             res["C5_inference_slice"] = {"unavailable": f"{type(e).__name__}: {e}"}

@@ -23,7 +23,7 @@ stem = ConvStem(464, 768).to(dev)
 x = (torch.randn(B, 4096, 464, device=dev) * 1.5).to(torch.bfloat16)
 h = stem.forward_stage(1, x)
 lib = _stem_lib.lib()
-buf = (ctypes.c_ulonglong * 8)()
+buf = (ctypes.c_ulonglong * 12)()
 names = ["producer on A-empty", "producer on W-empty", "MMA on A-full", "MMA on W-full", "MMA on TMEM-empty",
          "epilogue on TMEM-full"]
 for stage, inp in ((1, x), (2, h)):
@@ -35,7 +35,8 @@ for stage, inp in ((1, x), (2, h)):
     torch.cuda.synchronize()
     lib.bhstem_debug_profile(buf)
     ctas, total = buf[7], buf[6]
-    print(f"stage {stage}: {ctas} CTAs, {total / ctas:.0f} cycles per CTA")
+    print(f"stage {stage}: {ctas} CTAs, {total / ctas:.0f} cycles per CTA, SM clock during the kernel "
+          f"{1e3 * buf[8] / max(buf[9], 1):.0f} MHz (clock64 / globaltimer of CTA 0)")
     for i, n in enumerate(names):
         print(f"   {n:24s} {100.0 * buf[i] / total:5.1f} %")
 
