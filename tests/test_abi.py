@@ -81,3 +81,53 @@ def test_sass_is_sm100_and_uses_tma_bulk_copy():
     assert "sm_100a" in sass
     assert "UBLKCP" in sass and "LDGSTS" in sass and "SYNCS" in sass
     assert "bhmel_logmel_kernel" in sass
+
+
+# ------------------------------------------------------------------ libbhstem.so
+STEM_HEADER = os.path.join(ROOT, "include", "bhstem.h")
+
+
+def stem_declared_functions():
+    src = re.sub(r"/\*.*?\*/", "", open(STEM_HEADER).read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(bhstem_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def stem_lib():
+    from beatheritage_b200 import _stem_lib
+    build.build_stem()
+    return _stem_lib.lib()
+
+
+def test_stem_header_binding_and_exports_agree(stem_lib):
+    from beatheritage_b200 import _stem_lib
+    assert stem_declared_functions() == sorted(_stem_lib.SIGNATURES)
+    for name in stem_declared_functions():
+        assert hasattr(stem_lib, name), f"libbhstem.so does not export {name}"
+    assert stem_lib.bhstem_version() == 1
+
+
+def test_stem_create_rejects_bad_parameters_before_touching_cuda(stem_lib):
+    out = ctypes.c_void_p()
+    fp = ctypes.POINTER(ctypes.c_float)
+    w = (ctypes.c_float * 16)()
+    wp = ctypes.cast(w, fp)
+    for c_in, d in ((0, 768), (465, 768), (464, 100), (464, 0)):
+        assert stem_lib.bhstem_create(c_in, d, wp, wp, wp, wp, ctypes.byref(out)) == 1
+        assert out.value is None and len(stem_lib.bhstem_last_error()) > 0
+    assert stem_lib.bhstem_create(464, 768, None, wp, wp, wp, ctypes.byref(out)) == 1
+    assert stem_lib.bhstem_forward(None, None, 1, 2, None, None, None) == 1
+
+
+def test_stem_sass_uses_tcgen05_tmem_and_tma():
+    """The stem must be a Blackwell-native kernel: UTC*MMA (tcgen05.mma), LDTM (tcgen05.ld), UTMALDG (TMA)."""
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([exe, "-sass", build.build_stem()], capture_output=True, text=True, check=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UTCBAR"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA.16816" not in sass            # no legacy mma.sync path
