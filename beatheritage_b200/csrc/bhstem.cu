@@ -12,13 +12,13 @@
 // activations through a [batch][T/2][2*D] view (two time steps per row): tap 0 is the odd half of
 // the previous row, taps 1 and 2 the even and odd halves of the current one.
 //
-// One persistent CTA per SM, 192 threads, warp-specialised:
+// One persistent CTA per SM, 320 threads, warp-specialised:
 //   warp 0      TMA producer    A box 128 rows x 64 ch + W box BN rows x 64 ch per stage, 128-byte
 //                                swizzle, 4-stage mbarrier ring
 //   warp 1      MMA issuer      one thread issues tcgen05.mma.kind::f16 (128 x BN x 16, bf16 -> fp32)
 //                                into one of two TMEM accumulator stages; tcgen05.commit frees the
 //                                shared-memory stage / publishes the accumulator
-//   warps 2-5   epilogue        tcgen05.ld 32 lanes x 32 columns -> + bias -> round to bf16 (the conv
+//   warps 2-9   epilogue        (two per TMEM lane quarter, half the columns each) tcgen05.ld 32 lanes x 32 columns -> + bias -> round to bf16 (the conv
 //                                output) -> erf GELU in fp32 -> bf16 -> 64-byte row segments to HBM;
 //                                overlaps the next tile's MMAs through the second accumulator stage
 #include <cuda.h>
@@ -41,7 +41,8 @@ constexpr int BLOCK_M = 128;      // output rows (time steps) per tile = TMEM la
 constexpr int BLOCK_K = 64;       // channels per stage: 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;        // K of one tcgen05.mma.kind::f16
 constexpr int STAGES = 4;
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;      // producer warp, MMA warp, 8 epilogue warps
+constexpr int EPI_WARPS = 8;      // two per TMEM lane quarter, each owning half of the tile's columns
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr long long SPIN_LIMIT_CYCLES = 4000000000LL;   // ~2 s: a protocol bug traps instead of hanging the GPU
 
@@ -63,6 +64,18 @@ struct StemProblem {
   int32_t tap_row[3];      // row offset of each tap
   int32_t exp;             // timing experiments (wrong results): 1 no W loads, 2 no epilogue math / stores, 4 no A loads
 };
+
+// The C channels of a tap are n16 = ceil(C / 16) MMA steps dealt EVENLY over k_blocks = ceil(n16 / 4)
+// stages (464 channels: 5 stages of 4 steps + 3 of 3, instead of 7 of 4 + a tail stage of 1 that
+// would occupy a whole stage of the ring for a quarter of the work -- three such stages in a row,
+// one per tap, drain the pipeline).  Every stage still loads a full 64-channel box from its first
+// channel; the steps it does not use belong to the next stage (or are TMA's zero fill past C).
+__device__ __forceinline__ void kblock_span(const int kb, const int c_in, const int k_blocks, int& c0, int& ksteps) {
+  const int n16 = (c_in + UMMA_K - 1) / UMMA_K;
+  const int base = n16 / k_blocks, extra = n16 % k_blocks;
+  ksteps = base + (kb < extra ? 1 : 0);
+  c0 = UMMA_K * (kb * base + (kb < extra ? kb : extra));
+}
 
 // ------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -187,7 +200,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-// Epilogue role (warps 2-5 of either kernel): TMEM accumulator -> + bias -> bf16 (the conv output) ->
+// Epilogue role (warps 2-9 of every kernel): TMEM accumulator -> + bias -> bf16 (the conv output) ->
 // erf GELU in fp32 -> bf16 -> HBM.  A lane owns one output ROW of the tile (TMEM lane = row), so storing
 // from registers would scatter 16-byte pieces over 32 rows per instruction (measured: the stores, not the
 // GELU, cost 27 % of the kernel).  Each 32-column chunk is therefore turned round through a 2 KB
@@ -204,7 +217,9 @@ __device__ __forceinline__ void epilogue_role(const StemProblem& p, const float*
   const int tiles_per_batch = p.m_tiles * p.n_tiles;
   const int num_tiles = p.batches * tiles_per_batch;
   const int quarter = warp & 3;                            // TMEM lanes this warp may touch: 32 * (warp % 4) ...
-  uint8_t* staging = staging_all + quarter * EPI_STAGE_BYTES;
+  const int half = (warp - 2) >> 2;                        // which half of the tile's columns (warps 2-5 / 6-9)
+  constexpr int CHUNKS = BN / 64;                          // 32-column chunks per warp
+  uint8_t* staging = staging_all + (warp - 2) * EPI_STAGE_BYTES;
   const int wr_swz = (lane >> 1) & 3;                      // my row's XOR phase when writing
   const int rd_row = lane >> 2, rd_piece = lane & 3;       // read-back: 4 lanes per row, 8 rows per pass
   uint32_t local = 0;
@@ -223,11 +238,11 @@ __device__ __forceinline__ void epilogue_role(const StemProblem& p, const float*
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = half * CHUNKS; c < (half + 1) * CHUNKS; ++c) {
       uint32_t r[32];
       __syncwarp();                                        // tcgen05.ld is warp-collective; staging reads of the last chunk are done
       tmem_ld32(taddr + c * 32, r);
-      if (c == BN / 32 - 1) {                              // everything is in registers: hand the stage back
+      if (c == (half + 1) * CHUNKS - 1) {                  // everything is in registers: hand the stage back
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -268,7 +283,7 @@ bhstem_conv_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) unsigned long long bars[2 * STAGES + 4];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ __align__(128) uint8_t epi_staging[4 * EPI_STAGE_BYTES];
+  __shared__ __align__(128) uint8_t epi_staging[EPI_WARPS * EPI_STAGE_BYTES];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -282,7 +297,7 @@ bhstem_conv_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, 4);          // one arrival per epilogue warp
+      mbar_init(tempty0 + 8 * a, EPI_WARPS);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -309,11 +324,13 @@ bhstem_conv_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         const int mt = rem / p.n_tiles, nt = rem % p.n_tiles;
         for (int it = 0; it < k_iters; ++it) {
           const int tap = it / p.k_blocks, kb = it % p.k_blocks;
+          int c0, ksteps_unused;
+          kblock_span(kb, p.c_in, p.k_blocks, c0, ksteps_unused);
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
           const uint32_t sa = ring + stage * C::STAGE_BYTES, sb = sa + A_BYTES;
           mbar_expect_tx(full0 + 8 * stage, C::STAGE_BYTES);
-          tma_load_3d(&map_a, full0 + 8 * stage, sa, p.tap_col[tap] + kb * BLOCK_K, mt * BLOCK_M + p.tap_row[tap], b);
-          tma_load_3d(&map_w, full0 + 8 * stage, sb, kb * BLOCK_K, nt * BN, tap);
+          tma_load_3d(&map_a, full0 + 8 * stage, sa, p.tap_col[tap] + c0, mt * BLOCK_M + p.tap_row[tap], b);
+          tma_load_3d(&map_w, full0 + 8 * stage, sb, c0, nt * BN, tap);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -332,8 +349,8 @@ bhstem_conv_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         const uint32_t tmem_d = tmem_base + as * BN;
         for (int it = 0; it < k_iters; ++it) {
           const int kb = it % p.k_blocks;
-          const int rem_c = p.c_in - kb * BLOCK_K;
-          const int ksteps = rem_c >= BLOCK_K ? BLOCK_K / UMMA_K : (rem_c + UMMA_K - 1) / UMMA_K;   // zero-filled tail skipped
+          int c0_unused, ksteps;
+          kblock_span(kb, p.c_in, p.k_blocks, c0_unused, ksteps);
           mbar_wait(full0 + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sa = ring + stage * C::STAGE_BYTES, sb = sa + A_BYTES;
@@ -397,7 +414,7 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) unsigned long long bars[2 * A_STAGES + 2 * W_STAGES + 4];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ __align__(128) uint8_t epi_staging[4 * EPI_STAGE_BYTES];
+  __shared__ __align__(128) uint8_t epi_staging[EPI_WARPS * EPI_STAGE_BYTES];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ring_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -409,7 +426,7 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
   if (threadIdx.x == 0) {
     for (int s = 0; s < A_STAGES; ++s) { mbar_init(afull0 + 8 * s, 1); mbar_init(aempty0 + 8 * s, 1); }
     for (int s = 0; s < W_STAGES; ++s) { mbar_init(wfull0 + 8 * s, 1); mbar_init(wempty0 + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -440,15 +457,17 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
         const int b = tile / tiles_per_batch, rem = tile % tiles_per_batch;
         const int mt = rem / p.n_tiles, nt = rem % p.n_tiles;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
+          int c0, ksteps_unused;
+          kblock_span(kb, p.c_in, p.k_blocks, c0, ksteps_unused);
           { PROF_T0(); mbar_wait(aempty0 + 8 * as, aph ^ 1); PROF_ADD(0); }
           const uint32_t sa = ring_a + as * ASTAGE_BYTES;
           if (p.exp & 4) {
             mbar_arrive(afull0 + 8 * as);
           } else {
             mbar_expect_tx(afull0 + 8 * as, a_bytes);
-            tma_load_3d(&map_a0, afull0 + 8 * as, sa, st.a_col[0] + kb * BLOCK_K, mt * BLOCK_M + st.a_row[0], b);
+            tma_load_3d(&map_a0, afull0 + 8 * as, sa, st.a_col[0] + c0, mt * BLOCK_M + st.a_row[0], b);
             if (st.n_aloads == 2)
-              tma_load_3d(&map_a1, afull0 + 8 * as, sa + A0_BYTES, st.a_col[1] + kb * BLOCK_K, mt * BLOCK_M + st.a_row[1], b);
+              tma_load_3d(&map_a1, afull0 + 8 * as, sa + A0_BYTES, st.a_col[1] + c0, mt * BLOCK_M + st.a_row[1], b);
           }
           if (++as == A_STAGES) { as = 0; aph ^= 1; }
           for (int tap = 0; tap < 3; ++tap) {
@@ -457,7 +476,7 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
               mbar_arrive(wfull0 + 8 * ws);
             } else {
               mbar_expect_tx(wfull0 + 8 * ws, C::W_BYTES);
-              tma_load_3d(&map_w, wfull0 + 8 * ws, ring_w + ws * C::W_BYTES, kb * BLOCK_K, nt * BN, tap);
+              tma_load_3d(&map_w, wfull0 + 8 * ws, ring_w + ws * C::W_BYTES, c0, nt * BN, tap);
             }
             if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
           }
@@ -476,8 +495,8 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
-          const int rem_c = p.c_in - kb * BLOCK_K;
-          const int ksteps = rem_c >= BLOCK_K ? BLOCK_K / UMMA_K : (rem_c + UMMA_K - 1) / UMMA_K;
+          int c0_unused, ksteps;
+          kblock_span(kb, p.c_in, p.k_blocks, c0_unused, ksteps);
           { PROF_T0(); mbar_wait(afull0 + 8 * as, aph); PROF_ADD(2); }
           const uint32_t sa = ring_a + as * ASTAGE_BYTES;
           for (int tap = 0; tap < 3; ++tap) {
@@ -566,7 +585,7 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) unsigned long long bars[2 * PAIR_A_STAGES + 2 * PAIR_W_STAGES + 4];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ __align__(128) uint8_t epi_staging[4 * EPI_STAGE_BYTES];
+  __shared__ __align__(128) uint8_t epi_staging[EPI_WARPS * EPI_STAGE_BYTES];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_rank();
@@ -580,7 +599,7 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
   if (threadIdx.x == 0) {
     for (int s = 0; s < PAIR_A_STAGES; ++s) { mbar_init(afull0 + 8 * s, 1); mbar_init(aempty0 + 8 * s, 1); }
     for (int s = 0; s < PAIR_W_STAGES; ++s) { mbar_init(wfull0 + 8 * s, 1); mbar_init(wempty0 + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 8); }   // 4 epilogue warps x 2 CTAs
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 2 * EPI_WARPS); }   // epilogue warps of both CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {          // the same warp of BOTH CTAs allocates (cta_group::2), same destination slot
@@ -608,17 +627,19 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
         const int mt = rem / p.n_tiles, nt = rem % p.n_tiles;
         const int my_row = mt * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
+          int c0, ksteps_unused;
+          kblock_span(kb, p.c_in, p.k_blocks, c0, ksteps_unused);
           mbar_wait(aempty0 + 8 * as, aph ^ 1);
           const uint32_t sa = ring_a + as * PAIR_ASTAGE_BYTES;
           if (leader) mbar_expect_tx(afull0 + 8 * as, 2 * a_bytes);           // both CTAs' activation blocks
-          tma_load_3d_pair(&map_a0, afull_leader + 8 * as, sa, st.a_col[0] + kb * BLOCK_K, my_row + st.a_row[0], b);
+          tma_load_3d_pair(&map_a0, afull_leader + 8 * as, sa, st.a_col[0] + c0, my_row + st.a_row[0], b);
           if (st.n_aloads == 2)
-            tma_load_3d_pair(&map_a1, afull_leader + 8 * as, sa + A0_BYTES, st.a_col[1] + kb * BLOCK_K, my_row + st.a_row[1], b);
+            tma_load_3d_pair(&map_a1, afull_leader + 8 * as, sa + A0_BYTES, st.a_col[1] + c0, my_row + st.a_row[1], b);
           if (++as == PAIR_A_STAGES) { as = 0; aph ^= 1; }
           for (int tap = 0; tap < 3; ++tap) {
             mbar_wait(wempty0 + 8 * ws, wph ^ 1);
             if (leader) mbar_expect_tx(wfull0 + 8 * ws, 2 * PAIR_W_BYTES);    // both halves of the weight tile
-            tma_load_3d_pair(&map_w, wfull_leader + 8 * ws, ring_w + ws * PAIR_W_BYTES, kb * BLOCK_K,
+            tma_load_3d_pair(&map_w, wfull_leader + 8 * ws, ring_w + ws * PAIR_W_BYTES, c0,
                              nt * PAIR_BN + static_cast<int>(rank) * 128, tap);
             if (++ws == PAIR_W_STAGES) { ws = 0; wph ^= 1; }
           }
@@ -638,8 +659,8 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * PAIR_BN;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
-          const int rem_c = p.c_in - kb * BLOCK_K;
-          const int ksteps = rem_c >= BLOCK_K ? BLOCK_K / UMMA_K : (rem_c + UMMA_K - 1) / UMMA_K;
+          int c0_unused, ksteps;
+          kblock_span(kb, p.c_in, p.k_blocks, c0_unused, ksteps);
           mbar_wait(afull0 + 8 * as, aph);
           const uint32_t sa = ring_a + as * PAIR_ASTAGE_BYTES;
           for (int tap = 0; tap < 3; ++tap) {
@@ -722,6 +743,7 @@ struct bhstem_handle {
   long long launches = 0;
   int variant = 1;      // 1: shared taps (row-shifted descriptors, default), 0: one TMA box per tap
   int pairs = 0;        // 1: CTA-pair kernel (tcgen05 cta_group::2) when d_model % 256 == 0
+  int exp = 0;          // BHSTEM_EXP: timing experiments (wrong results), read once at create
 };
 
 namespace {
@@ -762,7 +784,7 @@ int launch_stage(bhstem_handle* h, int stage, const void* in, int64_t B, int64_t
   p.n_out = h->d;
   p.c_in = c;
   p.k_blocks = (c + BLOCK_K - 1) / BLOCK_K;
-  p.exp = getenv("BHSTEM_EXP") ? atoi(getenv("BHSTEM_EXP")) : 0;   // timing experiments only
+  p.exp = h->exp;
   const long long tiles = static_cast<long long>(p.batches) * p.m_tiles * p.n_tiles;
   const int grid = static_cast<int>(tiles < h->sms ? tiles : h->sms);
   if (h->variant == 1) {
@@ -791,34 +813,27 @@ int launch_stage(bhstem_handle* h, int stage, const void* in, int64_t B, int64_t
       pp.m_tiles = (p.rows_out + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
       const long long pair_tiles = static_cast<long long>(pp.batches) * pp.m_tiles * pp.n_tiles;
       const int pgrid = 2 * static_cast<int>(pair_tiles < h->sms / 2 ? pair_tiles : h->sms / 2);
-      cudaError_t e = cudaFuncSetAttribute(bhstem_conv_gelu_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           PAIR_SMEM_BYTES);
-      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
       bhstem_conv_gelu_pair_kernel<<<pgrid, THREADS, PAIR_SMEM_BYTES, stream>>>(
           map_a0, map_a1, stage == 1 ? h->map_w1_half : h->map_w2_half, stage == 1 ? h->b1 : h->b2,
           static_cast<__nv_bfloat16*>(out), pp, st);
-      e = cudaGetLastError();
+      const cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
       ++h->launches;
       return BHSTEM_OK;
     }
     auto kernel = bhstem_conv_gelu_shared_kernel<BN>;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgShared<BN>::SMEM_BYTES);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
     kernel<<<grid, THREADS, CfgShared<BN>::SMEM_BYTES, stream>>>(map_a0, map_a1, stage == 1 ? h->map_w1 : h->map_w2,
                                                                  stage == 1 ? h->b1 : h->b2,
                                                                  static_cast<__nv_bfloat16*>(out), p, st);
-    e = cudaGetLastError();
+    const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     ++h->launches;
     return BHSTEM_OK;
   }
   auto kernel = bhstem_conv_gelu_kernel<BN>;
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
   kernel<<<grid, THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(map_a, stage == 1 ? h->map_w1 : h->map_w2,
                                                          stage == 1 ? h->b1 : h->b2, static_cast<__nv_bfloat16*>(out), p);
-  e = cudaGetLastError();
+  const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
   ++h->launches;
   return BHSTEM_OK;
@@ -876,6 +891,7 @@ int bhstem_create(int32_t c_in, int32_t d_model, const float* conv1_weight, cons
   h->bn = d_model % 256 == 0 ? 256 : 128;
   h->variant = 1;
   if (const char* v = getenv("BHSTEM_VARIANT")) { h->variant = atoi(v) == 0 ? 0 : 1; h->pairs = atoi(v) == 2; }   // A/B: 0 = one TMA box per tap
+  if (const char* v = getenv("BHSTEM_EXP")) h->exp = atoi(v);
   h->enc = encode_tiled_fn();
   if (!h->enc) { delete h; return fail(BHSTEM_ECUDA, "cuTensorMapEncodeTiled is not available from this driver"); }
   const std::vector<__nv_bfloat16> w1 = pack_weight(conv1_weight, d_model, c_in), w2 = pack_weight(conv2_weight, d_model, d_model);
@@ -907,6 +923,18 @@ int bhstem_create(int32_t c_in, int32_t d_model, const float* conv1_weight, cons
     if (rc == BHSTEM_OK)
       rc = make_map(h->enc, &h->map_w2_half, h->w2, d_model, d_model, 3, static_cast<uint64_t>(d_model) * 2,
                     static_cast<uint64_t>(d_model) * d_model * 2, 128);
+  }
+  if (rc == BHSTEM_OK) {          // opt in to > 48 KB of dynamic shared memory once, not per launch
+    cudaError_t ea = cudaSuccess;
+    auto opt_in = [&](const void* fn, int bytes) {
+      if (ea == cudaSuccess) ea = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    };
+    opt_in(reinterpret_cast<const void*>(bhstem_conv_gelu_kernel<256>), Cfg<256>::SMEM_BYTES);
+    opt_in(reinterpret_cast<const void*>(bhstem_conv_gelu_kernel<128>), Cfg<128>::SMEM_BYTES);
+    opt_in(reinterpret_cast<const void*>(bhstem_conv_gelu_shared_kernel<256>), CfgShared<256>::SMEM_BYTES);
+    opt_in(reinterpret_cast<const void*>(bhstem_conv_gelu_shared_kernel<128>), CfgShared<128>::SMEM_BYTES);
+    opt_in(reinterpret_cast<const void*>(bhstem_conv_gelu_pair_kernel), PAIR_SMEM_BYTES);
+    if (ea != cudaSuccess) { bhstem_destroy(h); return cuda_fail(ea, "cudaFuncSetAttribute"); }
   }
   if (rc != BHSTEM_OK) { bhstem_destroy(h); return rc; }
   *out = h;
