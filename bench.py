@@ -382,6 +382,33 @@ def run_ours(args):
         extra["c2_song_6_windows_ms"] = ms6
         xc = xs[2][:1, :160000].contiguous()
         extra["c1_10s_clip_us"] = 1e3 * timed(lambda: mel(xc), 50)
+        # next row N3: frontend -> assembled channels-last encoder input -> tcgen05 conv stem
+        # (libbhstem.so), 6 and 46 windows (C2), whisper-small dims (80 mel + 384 conditioning channels -> 768)
+        try:
+            from beatheritage_b200.conv_stem import ConvStem
+            torch.manual_seed(0)
+            stem = ConvStem(N_MELS + 384, 768).to(dev)
+            try:
+                bf16_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+            except Exception:
+                bf16_peak = 1590.0          # B200_PROFILING.md fallback
+            stem_rows = {}
+            for nw, xw in ((6, x6), (46, x46)):
+                cond = torch.randn(nw, 384, device=dev)
+                enc_in = mel.forward_encoder_input(xw, [cond], dtype=torch.bfloat16, channels_first=False)
+                ms_stem = timed(lambda: stem(enc_in), 20)
+                ms_all = timed(lambda: stem(mel.forward_encoder_input(xw, [cond], dtype=torch.bfloat16,
+                                                                      channels_first=False)), 20)
+                flop = 2.0 * nw * FRAMES * 768 * 3 * (N_MELS + 384) + 2.0 * nw * (FRAMES // 2) * 768 * 3 * 768
+                stem_rows[f"{nw}_windows"] = {
+                    "stem_ms": ms_stem, "stem_tflops": flop / ms_stem / 1e9,
+                    "stem_frac_of_measured_bf16_peak": flop / ms_stem / 1e9 / bf16_peak,
+                    "frontend_plus_assembly_plus_stem_ms": ms_all}
+            extra["conv_stem_n3"] = {"dims": "464 -> 768 channels, 4096 -> 2048 frames, bf16, fp32 accumulate",
+                                     "kernel": "bhstem_conv_gelu_shared_kernel (tcgen05 / TMEM / TMA)",
+                                     "launches": stem.launch_count(), **stem_rows}
+        except Exception as e:  # noqa: BLE001 -- the headline line must not depend on the next-row library
+            extra["conv_stem_n3"] = {"unavailable": f"{type(e).__name__}: {e}"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------------
     cpu = None
