@@ -70,12 +70,16 @@ struct StemProblem {
 // would occupy a whole stage of the ring for a quarter of the work -- three such stages in a row,
 // one per tap, drain the pipeline).  Every stage still loads a full 64-channel box from its first
 // channel; the steps it does not use belong to the next stage (or are TMA's zero fill past C).
-__device__ __forceinline__ void kblock_span(const int kb, const int c_in, const int k_blocks, int& c0, int& ksteps) {
-  const int n16 = (c_in + UMMA_K - 1) / UMMA_K;
-  const int base = n16 / k_blocks, extra = n16 % k_blocks;
-  ksteps = base + (kb < extra ? 1 : 0);
-  c0 = UMMA_K * (kb * base + (kb < extra ? kb : extra));
-}
+struct KSplit {
+  int base, extra;         // n16 / k_blocks, n16 % k_blocks -- computed once per thread, not per stage
+  __device__ __forceinline__ KSplit(int c_in, int k_blocks) {
+    const int n16 = (c_in + UMMA_K - 1) / UMMA_K;
+    base = n16 / k_blocks;
+    extra = n16 - base * k_blocks;
+  }
+  __device__ __forceinline__ int steps(int kb) const { return base + (kb < extra ? 1 : 0); }
+  __device__ __forceinline__ int first_channel(int kb) const { return UMMA_K * (kb * base + (kb < extra ? kb : extra)); }
+};
 
 // ------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -122,18 +126,22 @@ __device__ unsigned long long g_prof[12];   // [8] / [9]: SM cycles / nanosecond
 #define PROF_FLUSH(slot)
 #endif
 
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {     // off the fast path: bounded spin
   const long long t0 = clock64();
-  for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) return;
+  while (!mbar_try(bar, parity))
     if (clock64() - t0 > SPIN_LIMIT_CYCLES) __trap();
-  }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
 }
 
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
@@ -314,6 +322,7 @@ bhstem_conv_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   const int tiles_per_batch = p.m_tiles * p.n_tiles;
   const int num_tiles = p.batches * tiles_per_batch;
   const int k_iters = 3 * p.k_blocks;
+  const KSplit ks(p.c_in, p.k_blocks);
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -324,8 +333,7 @@ bhstem_conv_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         const int mt = rem / p.n_tiles, nt = rem % p.n_tiles;
         for (int it = 0; it < k_iters; ++it) {
           const int tap = it / p.k_blocks, kb = it % p.k_blocks;
-          int c0, ksteps_unused;
-          kblock_span(kb, p.c_in, p.k_blocks, c0, ksteps_unused);
+          const int c0 = ks.first_channel(kb);
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
           const uint32_t sa = ring + stage * C::STAGE_BYTES, sb = sa + A_BYTES;
           mbar_expect_tx(full0 + 8 * stage, C::STAGE_BYTES);
@@ -349,8 +357,7 @@ bhstem_conv_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         const uint32_t tmem_d = tmem_base + as * BN;
         for (int it = 0; it < k_iters; ++it) {
           const int kb = it % p.k_blocks;
-          int c0_unused, ksteps;
-          kblock_span(kb, p.c_in, p.k_blocks, c0_unused, ksteps);
+          const int ksteps = ks.steps(kb);
           mbar_wait(full0 + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sa = ring + stage * C::STAGE_BYTES, sb = sa + A_BYTES;
@@ -442,6 +449,7 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
   const int tiles_per_batch = p.m_tiles * p.n_tiles;
   const int num_tiles = p.batches * tiles_per_batch;
   const uint32_t a_bytes = A0_BYTES + (st.n_aloads == 2 ? A1_BYTES : 0);
+  const KSplit ks(p.c_in, p.k_blocks);
   PROF_DECL();
 #ifdef BHSTEM_PROFILE
   const long long prof_start = clock64();
@@ -457,8 +465,7 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
         const int b = tile / tiles_per_batch, rem = tile % tiles_per_batch;
         const int mt = rem / p.n_tiles, nt = rem % p.n_tiles;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
-          int c0, ksteps_unused;
-          kblock_span(kb, p.c_in, p.k_blocks, c0, ksteps_unused);
+          const int c0 = ks.first_channel(kb);
           { PROF_T0(); mbar_wait(aempty0 + 8 * as, aph ^ 1); PROF_ADD(0); }
           const uint32_t sa = ring_a + as * ASTAGE_BYTES;
           if (p.exp & 4) {
@@ -495,8 +502,7 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
-          int c0_unused, ksteps;
-          kblock_span(kb, p.c_in, p.k_blocks, c0_unused, ksteps);
+          const int ksteps = ks.steps(kb);
           { PROF_T0(); mbar_wait(afull0 + 8 * as, aph); PROF_ADD(2); }
           const uint32_t sa = ring_a + as * ASTAGE_BYTES;
           for (int tap = 0; tap < 3; ++tap) {
@@ -616,6 +622,13 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
   const int num_tiles = p.batches * tiles_per_batch;
   const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
   const uint32_t a_bytes = A0_BYTES + (st.n_aloads == 2 ? A1_BYTES : 0);
+  const KSplit ks(p.c_in, p.k_blocks);
+  PROF_DECL();
+#ifdef BHSTEM_PROFILE
+  const long long prof_start = clock64();
+  unsigned long long prof_ns0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_ns0));
+#endif
 
   if (warp == 0) {
     // ===================================== TMA producer (both CTAs) =========================
@@ -627,9 +640,8 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
         const int mt = rem / p.n_tiles, nt = rem % p.n_tiles;
         const int my_row = mt * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
-          int c0, ksteps_unused;
-          kblock_span(kb, p.c_in, p.k_blocks, c0, ksteps_unused);
-          mbar_wait(aempty0 + 8 * as, aph ^ 1);
+          const int c0 = ks.first_channel(kb);
+          { PROF_T0(); mbar_wait(aempty0 + 8 * as, aph ^ 1); PROF_ADD(0); }
           const uint32_t sa = ring_a + as * PAIR_ASTAGE_BYTES;
           if (leader) mbar_expect_tx(afull0 + 8 * as, 2 * a_bytes);           // both CTAs' activation blocks
           tma_load_3d_pair(&map_a0, afull_leader + 8 * as, sa, st.a_col[0] + c0, my_row + st.a_row[0], b);
@@ -637,7 +649,7 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
             tma_load_3d_pair(&map_a1, afull_leader + 8 * as, sa + A0_BYTES, st.a_col[1] + c0, my_row + st.a_row[1], b);
           if (++as == PAIR_A_STAGES) { as = 0; aph ^= 1; }
           for (int tap = 0; tap < 3; ++tap) {
-            mbar_wait(wempty0 + 8 * ws, wph ^ 1);
+            { PROF_T0(); mbar_wait(wempty0 + 8 * ws, wph ^ 1); PROF_ADD(1); }
             if (leader) mbar_expect_tx(wfull0 + 8 * ws, 2 * PAIR_W_BYTES);    // both halves of the weight tile
             tma_load_3d_pair(&map_w, wfull_leader + 8 * ws, ring_w + ws * PAIR_W_BYTES, c0,
                              nt * PAIR_BN + static_cast<int>(rank) * 128, tap);
@@ -655,16 +667,15 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
       uint32_t as = 0, aph = 0, ws = 0, wph = 0, local = 0;
       for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++local) {
         const uint32_t acc = local & 1, accphase = (local >> 1) & 1;
-        mbar_wait(tempty0 + 8 * acc, accphase ^ 1);
+        { PROF_T0(); mbar_wait(tempty0 + 8 * acc, accphase ^ 1); PROF_ADD(4); }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * PAIR_BN;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
-          int c0_unused, ksteps;
-          kblock_span(kb, p.c_in, p.k_blocks, c0_unused, ksteps);
-          mbar_wait(afull0 + 8 * as, aph);
+          const int ksteps = ks.steps(kb);
+          { PROF_T0(); mbar_wait(afull0 + 8 * as, aph); PROF_ADD(2); }
           const uint32_t sa = ring_a + as * PAIR_ASTAGE_BYTES;
           for (int tap = 0; tap < 3; ++tap) {
-            mbar_wait(wfull0 + 8 * ws, wph);
+            { PROF_T0(); mbar_wait(wfull0 + 8 * ws, wph); PROF_ADD(3); }
             tc_fence_after();
             const uint64_t adesc = sw128_desc(sa + st.tap_buf[tap] * A0_BYTES + st.tap_shift[tap] * 128);
             const uint64_t bdesc = sw128_desc(ring_w + ws * PAIR_W_BYTES);
@@ -684,6 +695,20 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
                            num_pairs, 2 * BLOCK_M, static_cast<int>(rank) * BLOCK_M, true);
   }
 
+#ifdef BHSTEM_PROFILE
+  if (lane == 0 && warp == 0 && leader) { PROF_FLUSH(0); PROF_FLUSH(1); }
+  if (lane == 0 && warp == 1 && leader) {
+    PROF_FLUSH(2); PROF_FLUSH(3); PROF_FLUSH(4);
+    atomicAdd(&g_prof[6], static_cast<unsigned long long>(clock64() - prof_start));
+    atomicAdd(&g_prof[7], 1ull);
+    if (blockIdx.x == 0) {
+      unsigned long long ns1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+      g_prof[8] = static_cast<unsigned long long>(clock64() - prof_start);
+      g_prof[9] = ns1 - prof_ns0;
+    }
+  }
+#endif
   tc_fence_before();
   cluster_sync_all();       // the peer's shared memory and barriers stay alive until both CTAs are done
   if (warp == 1) {
