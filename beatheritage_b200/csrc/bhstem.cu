@@ -396,6 +396,8 @@ bhstem_conv_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
 constexpr int A0_ROWS = 136, A0_BYTES = A0_ROWS * 128, A1_BYTES = BLOCK_M * 128;
 constexpr int ASTAGE_BYTES = A0_BYTES + A1_BYTES;          // 33 KB, a multiple of 1024
 constexpr int A_STAGES = 2, W_STAGES = 4;
+constexpr int A_PRODUCER_WARP = 10;                        // shared-tap kernel: 11 warps
+constexpr int THREADS_SHARED = THREADS + 32;
 
 template <int BN>
 struct CfgShared {
@@ -413,7 +415,7 @@ struct SharedTaps {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS_SHARED, 1)
 bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                                const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias,
                                __nv_bfloat16* __restrict__ out, const StemProblem p, const SharedTaps st) {
@@ -457,13 +459,14 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_ns0));
 #endif
 
-  if (warp == 0) {
-    // ===================================== TMA producer =====================================
-    if (lane == 0) {
-      uint32_t as = 0, aph = 0, ws = 0, wph = 0;
+  if (warp == 0 || warp == A_PRODUCER_WARP) {
+    // ===================================== TMA producers ====================================
+    // Two independent single-thread producers: warp 0 feeds the weight ring, the last warp the
+    // activation ring, so a full weight ring never delays the next activation block (and vice versa).
+    if (lane == 0 && warp == A_PRODUCER_WARP) {
+      uint32_t as = 0, aph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int b = tile / tiles_per_batch, rem = tile % tiles_per_batch;
-        const int mt = rem / p.n_tiles, nt = rem % p.n_tiles;
+        const int b = tile / tiles_per_batch, mt = (tile % tiles_per_batch) / p.n_tiles;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           const int c0 = ks.first_channel(kb);
           { PROF_T0(); mbar_wait(aempty0 + 8 * as, aph ^ 1); PROF_ADD(0); }
@@ -477,6 +480,14 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
               tma_load_3d(&map_a1, afull0 + 8 * as, sa + A0_BYTES, st.a_col[1] + c0, mt * BLOCK_M + st.a_row[1], b);
           }
           if (++as == A_STAGES) { as = 0; aph ^= 1; }
+        }
+      }
+    } else if (lane == 0) {
+      uint32_t ws = 0, wph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nt = (tile % tiles_per_batch) % p.n_tiles;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          const int c0 = ks.first_channel(kb);
           for (int tap = 0; tap < 3; ++tap) {
             { PROF_T0(); mbar_wait(wempty0 + 8 * ws, wph ^ 1); PROF_ADD(1); }
             if (p.exp & 1) {
@@ -527,7 +538,8 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
   }
 
 #ifdef BHSTEM_PROFILE
-  if (lane == 0 && warp == 0) { PROF_FLUSH(0); PROF_FLUSH(1); }
+  if (lane == 0 && warp == A_PRODUCER_WARP) { PROF_FLUSH(0); }
+  if (lane == 0 && warp == 0) { PROF_FLUSH(1); }
   if (lane == 0 && warp == 1) {
     PROF_FLUSH(2); PROF_FLUSH(3); PROF_FLUSH(4);
     atomicAdd(&g_prof[6], static_cast<unsigned long long>(clock64() - prof_start));
@@ -847,7 +859,7 @@ int launch_stage(bhstem_handle* h, int stage, const void* in, int64_t B, int64_t
       return BHSTEM_OK;
     }
     auto kernel = bhstem_conv_gelu_shared_kernel<BN>;
-    kernel<<<grid, THREADS, CfgShared<BN>::SMEM_BYTES, stream>>>(map_a0, map_a1, stage == 1 ? h->map_w1 : h->map_w2,
+    kernel<<<grid, THREADS_SHARED, CfgShared<BN>::SMEM_BYTES, stream>>>(map_a0, map_a1, stage == 1 ? h->map_w1 : h->map_w2,
                                                                  stage == 1 ? h->b1 : h->b2,
                                                                  static_cast<__nv_bfloat16*>(out), p, st);
     const cudaError_t e = cudaGetLastError();
