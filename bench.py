@@ -189,7 +189,7 @@ def run_reference(args):
         "note": "reference CPU path = torchaudio MelSpectrogram arithmetic restated with torch ops "
                 "(oracle/torch_port.py); runs on rank 0 only, all host threads",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -463,11 +463,30 @@ def run_ours(args):
             "parity_max_abs_err_vs_cpu_port": parity,
             "extra": extra,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier(device_ids=[local_rank])
         dist.destroy_process_group()
     return 0
+
+
+_JSON_OUT = None
+
+
+def _claim_stdout() -> None:
+    """Keep stdout for the ONE JSON line: everything else that writes to fd 1 (NCCL prints its version
+    banner there under torchrun) is sent to stderr; emit() writes the line to the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -488,6 +507,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
+    _claim_stdout()
     return run_reference(args) if args.impl == "reference" else run_ours(args)
 
 
