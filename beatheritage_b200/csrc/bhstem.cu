@@ -195,13 +195,32 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// conv output rounded to bf16, exact GELU in fp32 on that value (torch: gelu(conv(x)) under bf16)
+// conv output rounded to bf16, GELU in fp32 on that value (torch: gelu(conv(x)) under bf16).
+// GELU here is a pure function bf16 -> bf16, so its implementation is validated EXHAUSTIVELY (all 65 536
+// inputs: tests/test_oracle.py models it, tests/test_gpu_stem.py runs it through an identity convolution).
+// erf by Abramowitz-Stegun 7.1.26, 1 - (a1 t + ... + a5 t^5) e^{-z^2}, t = 1 / (1 + p z), |error| <= 1.5e-7:
+// 15 instructions + 2 MUFU against ~24 for erff (whose SASS spends 9 FSEL per element selecting
+// coefficients); after the bf16 rounding it equals torch's fp32 erf GELU everywhere except a handful of
+// inputs in the tail x <= -3.5 where 1 + erf cancels in both (|diff| <= 4e-6).  -DBHSTEM_ERFF restores erff.
 __device__ __forceinline__ float conv_gelu(float acc_plus_bias) {
   const float x = __bfloat162float(__float2bfloat16_rn(acc_plus_bias));
 #ifdef BHSTEM_TIMING_NO_GELU      // timing experiments only: wrong results
   return x;
 #endif
+#ifdef BHSTEM_ERFF
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+#else
+  const float u = fabsf(x);
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, u, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u * u * (-0.5f * 1.4426950408889634f)));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = fmaf(-poly * t, e, 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+#endif
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

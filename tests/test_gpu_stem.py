@@ -123,3 +123,46 @@ def test_errors(dev):
         stem(torch.zeros(1, 63, 80, dtype=torch.bfloat16, device=dev))
     with pytest.raises(RuntimeError, match="channels-last"):
         stem(torch.zeros(1, 80, 64, dtype=torch.bfloat16, device=dev))
+
+
+def gelu_model(x):
+    """numpy fp32 restatement of the kernel's GELU (csrc/bhstem.cu::conv_gelu: Abramowitz-Stegun 7.1.26),
+    with exact 1/x and 2^x where the GPU uses MUFU approximations."""
+    f = np.float32
+    u = np.abs(x)
+    t = (f(1) / (f(0.3275911 * 0.70710678118654752440) * u + f(1))).astype(f)
+    e = np.exp2((u * u * f(-0.5 * 1.4426950408889634)).astype(f)).astype(f)
+    poly = t * f(1.061405429) + f(-1.453152027)
+    poly = poly * t + f(1.421413741)
+    poly = poly * t + f(-0.284496736)
+    poly = poly * t + f(0.254829592)
+    erf_abs = f(1) - poly * t * e
+    return (f(0.5) * x * (f(1) + np.copysign(erf_abs, x))).astype(f)
+
+
+def test_gelu_is_checked_for_every_bf16_input(dev):
+    """GELU in the stem is a pure function bf16 -> bf16 (the conv output is rounded first).  An identity
+    convolution (centre tap = I, bias 0) makes gelu(conv1(x)) = gelu(x) exactly, so ALL finite bf16 values
+    below 1e30 go through the kernel's epilogue and are compared with torch's fp32 erf GELU on the same GPU:
+    identical except in the tail x <= -3.5, where 1 + erf cancels in both and |diff| <= 1e-5."""
+    from beatheritage_b200.conv_stem import ConvStem
+    bits = torch.arange(65536, dtype=torch.int32)
+    x = (bits << 16).view(torch.float32)
+    x = torch.where(torch.isfinite(x) & (x.abs() < 1e30), x, torch.zeros(()))
+    stem = ConvStem(128, 128)
+    with torch.no_grad():
+        for p in stem.parameters():
+            p.zero_()
+        stem.conv1.weight[:, :, 1] = torch.eye(128)
+    stem = stem.to(dev)
+    xb = x.to(torch.bfloat16).reshape(1, 512, 128).to(dev)
+    got = stem.forward_stage(1, xb).reshape(-1).float().cpu()
+    want = torch.nn.functional.gelu(xb.float()).to(torch.bfloat16).reshape(-1).float().cpu()
+    with np.errstate(all="ignore"):
+        model = torch.from_numpy(gelu_model(x.numpy())).to(torch.bfloat16).float()
+    differs = got != want
+    assert not bool((differs & (x > -3.5)).any()), x[differs & (x > -3.5)][:10]
+    assert float((got - want).abs().max()) <= 1e-5
+    assert int(differs.sum()) <= 64
+    # the CPU model of the same formula agrees with the GPU up to the MUFU approximations
+    assert int((got != model).sum()) <= 64 and float((got - model).abs().max()) <= 1e-5

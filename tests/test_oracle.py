@@ -150,3 +150,21 @@ def test_nnaudio_conv_stft_equals_the_pinned_fft_form():
     wsin, wcos, window = nnaudio_oracle.fourier_kernels()
     assert wsin.shape == wcos.shape == (513, 1, 1024)
     assert np.array_equal(wcos[0, 0], window) and not wsin[0].any()
+
+
+def test_stem_gelu_formula_matches_torch_for_every_bf16_input():
+    """N3: the conv stem's epilogue evaluates GELU with Abramowitz-Stegun 7.1.26 instead of erff
+    (csrc/bhstem.cu::conv_gelu).  Its input is always a bf16 value, so the claim is checked exhaustively:
+    the fp32 model of the formula, rounded to bf16, equals torch's fp32 erf GELU for every finite bf16
+    input below 1e30 except in the tail x <= -3.5 (|diff| <= 4e-6).  The GPU side of the same check is
+    tests/test_gpu_stem.py::test_gelu_is_checked_for_every_bf16_input."""
+    from tests.test_gpu_stem import gelu_model
+    bits = torch.arange(65536, dtype=torch.int32)
+    x = (bits << 16).view(torch.float32)
+    x = torch.where(torch.isfinite(x) & (x.abs() < 1e30), x, torch.zeros(()))
+    want = torch.nn.functional.gelu(x).to(torch.bfloat16).float()
+    with np.errstate(all="ignore"):
+        model = torch.from_numpy(gelu_model(x.numpy())).to(torch.bfloat16).float()
+    differs = model != want
+    assert not bool((differs & (x > -3.5)).any())
+    assert int(differs.sum()) <= 32 and float((model - want).abs().max()) <= 4e-6
