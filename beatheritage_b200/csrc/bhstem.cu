@@ -202,8 +202,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // 15 instructions + 2 MUFU against ~24 for erff (whose SASS spends 9 FSEL per element selecting
 // coefficients); after the bf16 rounding it equals torch's fp32 erf GELU everywhere except a handful of
 // inputs in the tail x <= -3.5 where 1 + erf cancels in both (|diff| <= 4e-6).  -DBHSTEM_ERFF restores erff.
-__device__ __forceinline__ float conv_gelu(float acc_plus_bias) {
-  const float x = __bfloat162float(__float2bfloat16_rn(acc_plus_bias));
+__device__ __forceinline__ float gelu_of_bf16(const float x) {
 #ifdef BHSTEM_TIMING_NO_GELU      // timing experiments only: wrong results
   return x;
 #endif
@@ -219,12 +218,18 @@ __device__ __forceinline__ float conv_gelu(float acc_plus_bias) {
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
   const float erf_abs = fmaf(-poly * t, e, 1.0f);
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+  const float h = 0.5f * x;
+  return fmaf(fabsf(h), erf_abs, h);          // 0.5 x (1 + sign(x) erf|.|) without forming 1 + erf
 #endif
 }
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<const uint32_t*>(&v);
+// Two accumulators at a time: + bias, ONE packed conversion to bf16 (the conv's output), GELU on the two
+// bf16 values, one packed conversion of the results.
+__device__ __forceinline__ uint32_t conv_gelu_pair(const float a, const float b) {
+  const __nv_bfloat162 c = __floats2bfloat162_rn(a, b);
+  const uint32_t bits = *reinterpret_cast<const uint32_t*>(&c);
+  const float xa = __uint_as_float(bits << 16), xb = __uint_as_float(bits & 0xffff0000u);
+  const __nv_bfloat162 y = __floats2bfloat162_rn(gelu_of_bf16(xa), gelu_of_bf16(xb));
+  return *reinterpret_cast<const uint32_t*>(&y);
 }
 
 // Epilogue role (warps 2-9 of every kernel): TMEM accumulator -> + bias -> bf16 (the conv output) ->
@@ -283,10 +288,10 @@ __device__ __forceinline__ void epilogue_role(const StemProblem& p, const float*
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(brow + c * 32 + j));
         const float4 b1 = __ldg(reinterpret_cast<const float4*>(brow + c * 32 + j + 4));
         uint4 v;
-        v.x = pack_bf16(conv_gelu(__uint_as_float(r[j + 0]) + b0.x), conv_gelu(__uint_as_float(r[j + 1]) + b0.y));
-        v.y = pack_bf16(conv_gelu(__uint_as_float(r[j + 2]) + b0.z), conv_gelu(__uint_as_float(r[j + 3]) + b0.w));
-        v.z = pack_bf16(conv_gelu(__uint_as_float(r[j + 4]) + b1.x), conv_gelu(__uint_as_float(r[j + 5]) + b1.y));
-        v.w = pack_bf16(conv_gelu(__uint_as_float(r[j + 6]) + b1.z), conv_gelu(__uint_as_float(r[j + 7]) + b1.w));
+        v.x = conv_gelu_pair(__uint_as_float(r[j + 0]) + b0.x, __uint_as_float(r[j + 1]) + b0.y);
+        v.y = conv_gelu_pair(__uint_as_float(r[j + 2]) + b0.z, __uint_as_float(r[j + 3]) + b0.w);
+        v.z = conv_gelu_pair(__uint_as_float(r[j + 4]) + b1.x, __uint_as_float(r[j + 5]) + b1.y);
+        v.w = conv_gelu_pair(__uint_as_float(r[j + 6]) + b1.z, __uint_as_float(r[j + 7]) + b1.w);
         *reinterpret_cast<uint4*>(staging + lane * 64 + (((j >> 3) ^ wr_swz) << 4)) = v;
       }
       __syncwarp();

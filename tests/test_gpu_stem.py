@@ -137,7 +137,8 @@ def gelu_model(x):
     poly = poly * t + f(-0.284496736)
     poly = poly * t + f(0.254829592)
     erf_abs = f(1) - poly * t * e
-    return (f(0.5) * x * (f(1) + np.copysign(erf_abs, x))).astype(f)
+    h = f(0.5) * x
+    return (np.abs(h).astype(np.float64) * erf_abs.astype(np.float64) + h.astype(np.float64)).astype(f)   # one fma
 
 
 def test_gelu_is_checked_for_every_bf16_input(dev):
