@@ -25,6 +25,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -801,7 +802,7 @@ struct bhstem_handle {
   CUtensorMap map_w1, map_w2;
   CUtensorMap map_w1_half, map_w2_half;   // 128-row boxes for the CTA-pair kernel (bn == 256 only)
   EncodeTiledFn enc = nullptr;
-  long long launches = 0;
+  std::atomic<long long> launches{0};   // the only state forward calls mutate: handles may be shared by threads
   int variant = 1;      // 1: shared taps (row-shifted descriptors, default), 0: one TMA box per tap
   int pairs = 0;        // 1: CTA-pair kernel (tcgen05 cta_group::2) when d_model % 256 == 0
   int exp = 0;          // BHSTEM_EXP: timing experiments (wrong results), read once at create
@@ -927,7 +928,7 @@ int bhstem_debug_profile(unsigned long long* out8) {
 
 int bhstem_version(void) { return BHSTEM_VERSION; }
 const char* bhstem_last_error(void) { return g_err.c_str(); }
-int64_t bhstem_launch_count(const bhstem_handle* h) { return h ? h->launches : 0; }
+int64_t bhstem_launch_count(const bhstem_handle* h) { return h ? h->launches.load() : 0; }
 
 int bhstem_create(int32_t c_in, int32_t d_model, const float* conv1_weight, const float* conv1_bias,
                   const float* conv2_weight, const float* conv2_bias, bhstem_handle** out) {

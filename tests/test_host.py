@@ -255,3 +255,36 @@ def test_nnaudio_module_copies_and_pickles(nnaudio_published):
     for c in (copy.deepcopy(m), pickle.loads(pickle.dumps(m))):
         assert list(c.state_dict()) == list(m.state_dict())
         c.load_state_dict(m.state_dict(), strict=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# N3: host side of the conv stem (no kernel launches)
+# ---------------------------------------------------------------------------------------------
+def test_conv_stem_mirrors_the_encoders_parameters_and_has_no_cpu_path():
+    from beatheritage_b200.conv_stem import ConvStem
+
+    class Encoder(torch.nn.Module):                       # modeling_ropewhisper.py:1135-1136
+        def __init__(self):
+            super().__init__()
+            self.conv1 = torch.nn.Conv1d(464, 768, kernel_size=3, padding=1)
+            self.conv2 = torch.nn.Conv1d(768, 768, kernel_size=3, stride=2, padding=1)
+            self.layer_norm = torch.nn.LayerNorm(768)
+    enc = Encoder()
+    stem = ConvStem.from_encoder(enc)
+    assert list(stem.state_dict()) == ["conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias"]
+    for k, v in stem.state_dict().items():
+        assert torch.equal(v, enc.state_dict()[k])
+    assert stem.conv2.stride == (2,) and stem.conv1.padding == (1,) and stem.conv1.kernel_size == (3,)
+    stamp = stem._param_stamp()
+    stem.load_state_dict({k: v * 2 for k, v in stem.state_dict().items()})
+    assert stem._param_stamp() != stamp                   # a reload repacks the device weights at the next call
+    with pytest.raises(ValueError):
+        ConvStem(465, 768)                                # TMA needs 16-byte rows
+    with pytest.raises(ValueError):
+        ConvStem(464, 100)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        stem(torch.zeros(1, 64, 464, dtype=torch.bfloat16))
+    with pytest.raises(RuntimeError, match="channels-last"):
+        stem(torch.zeros(1, 464, 64, dtype=torch.bfloat16))
+    p = pickle.loads(pickle.dumps(stem))
+    assert p._handles == {} and list(p.state_dict()) == list(stem.state_dict())
