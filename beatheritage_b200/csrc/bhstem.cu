@@ -12,15 +12,24 @@
 // activations through a [batch][T/2][2*D] view (two time steps per row): tap 0 is the odd half of
 // the previous row, taps 1 and 2 the even and odd halves of the current one.
 //
-// One persistent CTA per SM, 320 threads, warp-specialised:
-//   warp 0      TMA producer    A box 128 rows x 64 ch + W box BN rows x 64 ch per stage, 128-byte
-//                                swizzle, 4-stage mbarrier ring
-//   warp 1      MMA issuer      one thread issues tcgen05.mma.kind::f16 (128 x BN x 16, bf16 -> fp32)
-//                                into one of two TMEM accumulator stages; tcgen05.commit frees the
-//                                shared-memory stage / publishes the accumulator
-//   warps 2-9   epilogue        (two per TMEM lane quarter, half the columns each) tcgen05.ld 32 lanes x 32 columns -> + bias -> round to bf16 (the conv
-//                                output) -> erf GELU in fp32 -> bf16 -> 64-byte row segments to HBM;
-//                                overlaps the next tile's MMAs through the second accumulator stage
+// Three kernels share the tile shape (128 rows x BN channels), the epilogue and the barrier protocol:
+//   bhstem_conv_gelu_shared_kernel  DEFAULT.  One staged block of rows per 64-channel step feeds all taps
+//                                   through row-shifted descriptors; separate weight / activation rings.
+//   bhstem_conv_gelu_kernel         BHSTEM_VARIANT=0: one TMA box per (tap, channel step); the first
+//                                   working version, kept as the A/B baseline.
+//   bhstem_conv_gelu_pair_kernel    BHSTEM_VARIANT=2: CTA pairs, tcgen05.mma.cta_group::2, half a weight
+//                                   tile per CTA; correct, measured no faster.
+// One persistent CTA per SM, warp-specialised (default kernel: 352 threads):
+//   warp 0      weight producer       one thread: TMA box BN rows x 64 ch per (channel step, tap), 128-byte
+//                                      swizzle, 4-stage mbarrier ring
+//   warp 10     activation producer   one thread: the staged block(s) of rows per channel step, 2-stage ring
+//   warp 1      MMA issuer            one thread issues tcgen05.mma.kind::f16 (128 x BN x 16, bf16 -> fp32)
+//                                      into one of two TMEM accumulator stages; tcgen05.commit frees the
+//                                      shared-memory stages / publishes the accumulator
+//   warps 2-9   epilogue              two per TMEM lane quarter, half the columns each: tcgen05.ld 32 lanes x
+//                                      32 columns -> + bias -> round to bf16 (the conv output) -> erf GELU in
+//                                      fp32 -> bf16 -> staged -> 64-byte row segments to HBM; overlaps the
+//                                      next tile's MMAs through the second accumulator stage
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -42,7 +51,7 @@ constexpr int BLOCK_M = 128;      // output rows (time steps) per tile = TMEM la
 constexpr int BLOCK_K = 64;       // channels per stage: 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;        // K of one tcgen05.mma.kind::f16
 constexpr int STAGES = 4;
-constexpr int THREADS = 320;      // producer warp, MMA warp, 8 epilogue warps
+constexpr int THREADS = 320;      // producer warp, MMA warp, 8 epilogue warps (the default kernel adds a second producer warp)
 constexpr int EPI_WARPS = 8;      // two per TMEM lane quarter, each owning half of the tile's columns
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr long long SPIN_LIMIT_CYCLES = 4000000000LL;   // ~2 s: a protocol bug traps instead of hanging the GPU
