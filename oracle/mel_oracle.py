@@ -158,8 +158,9 @@ def segment_params(src_seq_len: int = 4096, hop: int = HOP, lookback: float = 0.
 
 def segment(samples: np.ndarray, samples_per_sequence: int, stride: int,
             begin_pad: int = 0, end_pad: int = 0) -> np.ndarray:
-    """Preprocessor.segment (preprocessor.py:58-71) without the start/end-time trimming:
-    right-pad so the strided windows tile the song exactly, then take windows every `stride`."""
+    """Preprocessor.segment (preprocessor.py:58-71): right-pad so the strided windows tile the song
+    exactly, then take windows every `stride`.  `sequence_times` and the start/end-time trimming
+    (preprocessor.py:72-90) are restated by segment_times_and_trim below."""
     s = np.pad(np.asarray(samples), [begin_pad, end_pad])
     if len(s) < samples_per_sequence:
         padding = samples_per_sequence - len(s)
@@ -169,6 +170,38 @@ def segment(samples: np.ndarray, samples_per_sequence: int, stride: int,
     s = np.pad(s, [0, padding])
     view = np.lib.stride_tricks.sliding_window_view(s, samples_per_sequence)[::stride]
     return np.ascontiguousarray(view, dtype=np.float32)
+
+
+def segment_times_and_trim(n_windows: int, samples_per_sequence: int, stride: int, sample_rate: int = 16000,
+                           lookback: float = 0.5, lookahead: float = 0.4, start_time=None, end_time=None):
+    """The rest of Preprocessor.segment (preprocessor.py:72-90) and the constants it uses
+    (preprocessor.py:22-25): `sequence_times` and the start_time / end_time trimming.
+    Returns (first_window, n_kept, sequence_times int32 of the kept windows).
+
+    torch.arange(0, W * ms, ms) with Python floats is a float32 tensor whose element i is
+    float32(i * ms) (the product formed in double), and `.to(int32)` truncates; the float32
+    rounding is visible for long songs (values >= 2^20 ms lose their 1/16 ms fractions), so it is
+    restated, not idealised.  torch.searchsorted compares the int32 boundaries with the Python
+    float as real numbers (probed: 3275 < 3275.5)."""
+    ms_per_stride = stride * 1000 / sample_rate                            # :22
+    ms_per_sequence = samples_per_sequence * 1000 / sample_rate            # :23
+    lookback_max_time = lookback * ms_per_sequence                         # :24
+    lookahead_max_time = (1 - lookahead) * ms_per_sequence                 # :25
+    n = int(np.ceil((n_windows * ms_per_stride) / ms_per_stride)) if n_windows > 0 else 0   # arange's length
+    times = (np.arange(n, dtype=np.float64) * ms_per_stride).astype(np.float32).astype(np.int32)   # :72-73
+    first = 0
+    if start_time is not None:                                             # :75-82
+        first = int(np.searchsorted(times.astype(np.float64), start_time - lookahead_max_time, side="right"))
+        if first == len(times):
+            first -= 1
+        times = times[first:]
+    kept = len(times)
+    if end_time is not None:                                               # :83-90
+        kept = int(np.searchsorted(times.astype(np.float64), end_time - lookback_max_time, side="left"))
+        if kept == 0:
+            kept += 1
+        times = times[:kept]
+    return first, len(times), times
 
 
 # --------------------------------------------------------------------------------------

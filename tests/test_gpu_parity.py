@@ -272,6 +272,24 @@ def test_full_context_batch_c2(mods, dev):
     assert np.array_equal(y6.cpu().numpy(), run(m, seq6, dev))
 
 
+def test_forward_gather_on_a_trimmed_plan_equals_the_reference_trimmed_windows(mods, dev):
+    """a10: start_time / end_time trimming (preprocessor.py:75-90).  forward_gather on the trimmed plan
+    must equal the frontend applied to the windows the reference keeps, bit for bit."""
+    from beatheritage_b200 import segment as seg
+    m = mods["P0"]
+    song = signals.music(1_500_000, seed=4)
+    for (st, en, bp, ep) in [(20_000, 60_000, 0, 0), (None, 30_000, 4096, 100), (70_000, None, 0, 0), (1e9, None, 0, 0)]:
+        plan = seg.segment_plan(len(song), 1024, 128, 0.5, 0.4, False, 16000, st, en, bp, ep)
+        seq = mel_oracle.segment(song, plan.window_len, plan.stride, bp, ep)
+        first, kept, times = mel_oracle.segment_times_and_trim(len(seq), plan.window_len, plan.stride, 16000, 0.5, 0.4, st, en)
+        assert (first, kept) == (plan.first_window, plan.n_windows) and times.tolist() == list(plan.sequence_times)
+        want = run(m, seq[first:first + kept], dev)
+        resident = torch.from_numpy(np.pad(song, [bp, ep])).to(dev)        # segment()'s begin / end padding
+        got = m.forward_gather(resident, plan.first_offset, plan.stride, plan.n_windows, plan.window_len)
+        torch.cuda.synchronize()
+        assert np.array_equal(got.cpu().numpy(), want)
+
+
 def test_forward_host_matches_forward(mods, dev):
     m = mods["P0"]
     x = torch.from_numpy(signals.noise(37, 65536, 99))

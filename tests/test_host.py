@@ -121,6 +121,37 @@ def test_segment_plan_matches_oracle_segment():
     assert seg.segment_plan(57_600_000, parallel=True).n_windows == 110
 
 
+def test_segment_plan_trimming_matches_reference_cases_and_oracle():
+    """a10: sequence_times / start_time / end_time (preprocessor.py:72-90): the plan against the
+    reference's own outputs (tests/golden/segment_cases.json) and, on random songs, the oracle."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "segment_cases.json")) as f:
+        cases = json.load(f)["cases"]
+    for c in cases:
+        plan = seg.segment_plan(c["n_samples"], c["src_seq_len"], 128, c["lookback"], c["lookahead"], c["parallel"], 16000,
+                                c["start_time"], c["end_time"], c["begin_pad"], c["end_pad"])
+        assert plan.n_windows == c["n_windows"] and list(plan.sequence_times) == c["sequence_times"]
+        assert plan.song_length_ms == c["song_length"]
+        for i, g in enumerate(c["starts"]):
+            if g is not None:
+                assert plan.first_offset + i * plan.stride == g
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        n = int(rng.integers(1, 5_000_000))
+        ssl = int(rng.choice([512, 1024, 2048, 4096]))
+        lb, la = float(rng.choice([0.0, 0.25, 0.5])), float(rng.choice([0.0, 0.2, 0.4]))
+        dur = n / 16.0
+        st = None if rng.random() < 0.3 else float(rng.uniform(-0.3, 1.4) * dur)
+        en = None if rng.random() < 0.3 else float(rng.uniform(-0.3, 1.4) * dur)
+        plan = seg.segment_plan(n, ssl, 128, lb, la, False, 16000, st, en)
+        w, s = mel_oracle.segment_params(ssl, 128, lb, la)
+        untrimmed = seg.segment_plan(n, ssl, 128, lb, la).n_windows
+        first, kept, times = mel_oracle.segment_times_and_trim(untrimmed, w, s, 16000, lb, la, st, en)
+        assert (plan.first_window, plan.n_windows, list(plan.sequence_times)) == (first, kept, times.tolist())
+        assert plan.n_windows >= 1 and plan.first_offset == first * s
+
+
 def test_dataset_window_plan_matches_oracle():
     for n in (2_880_000, 2_880_001, 1280, 100):
         plan = seg.dataset_window_plan(n)

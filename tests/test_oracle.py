@@ -1,6 +1,8 @@
 """CPU: pins the oracle (oracle/mel_oracle.py, oracle/torch_port.py) to the golden fixtures that
 tests/golden/make_golden.py produced by running the UNMODIFIED reference module, and -- when the
 reference tree is present (build container) -- to the live reference."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -86,6 +88,52 @@ def test_segment_matches_reference_numbers():
     assert seq[3, 0] == 3 * 52415 and seq[-1, -1] == 0.0     # right padding is zeros
     assert mel_oracle.segment(song, w, w).shape == (6, 524160)
     assert mel_oracle.segment(np.zeros(1000, np.float32), w, s).shape == (1, 524160)
+
+
+def _segment_cases():
+    import json
+    with open(os.path.join(os.path.dirname(__file__), "golden", "segment_cases.json")) as f:
+        return json.load(f)["cases"]
+
+
+def test_segment_trimming_matches_the_reference_preprocessor():
+    """sequence_times and the start_time / end_time trimming (preprocessor.py:72-90) against outputs of
+    the unmodified reference Preprocessor.segment (tests/golden/make_segment_golden.py, 52 cases)."""
+    cases = _segment_cases()
+    assert len(cases) >= 50
+    for c in cases:
+        w, s = mel_oracle.segment_params(c["src_seq_len"], 128, c["lookback"], c["lookahead"], c["parallel"])
+        assert (w, s) == (c["samples_per_sequence"], c["sequence_stride"])
+        n_total = c["n_samples"] + c["begin_pad"] + c["end_pad"]
+        padded = w if n_total < w else n_total + (-(n_total - w)) % s
+        first, kept, times = mel_oracle.segment_times_and_trim((padded - w) // s + 1, w, s, 16000, c["lookback"],
+                                                               c["lookahead"], c["start_time"], c["end_time"])
+        assert kept == c["n_windows"] and times.dtype == np.int32 and times.tolist() == c["sequence_times"]
+        for i, (g, lead) in enumerate(zip(c["starts"], c["leading_zeros"])):
+            if g is not None:
+                assert (first + i) * s == g, (c, i)
+    # the restated windows themselves, trimmed, on a small case the oracle materialises
+    c = next(c for c in cases if c["n_samples"] == 1_000_000 and c["src_seq_len"] == 1024)
+    song = np.arange(1, c["n_samples"] + 1, dtype=np.float32)
+    seq = mel_oracle.segment(song, c["samples_per_sequence"], c["sequence_stride"], c["begin_pad"], c["end_pad"])
+    first, kept, _ = mel_oracle.segment_times_and_trim(len(seq), c["samples_per_sequence"], c["sequence_stride"], 16000,
+                                                       c["lookback"], c["lookahead"], c["start_time"], c["end_time"])
+    seq = seq[first:first + kept]
+    assert len(seq) == c["n_windows"]
+    for w_, g in zip(seq, c["starts"]):
+        nz = np.flatnonzero(w_)
+        assert c["begin_pad"] + int(w_[nz[0]]) - 1 - int(nz[0]) == g
+
+
+def test_sequence_times_keep_the_float32_rounding_of_torch_arange():
+    # 1-hour song: 1 090 windows, times beyond 2^20 ms lose their 1/16 ms fractions in float32
+    import torch
+    w, s = mel_oracle.segment_params()
+    _, kept, times = mel_oracle.segment_times_and_trim(1090, w, s)
+    ms = s * 1000 / 16000
+    want = torch.arange(0, 1090 * ms, ms).to(torch.int32).numpy()     # the reference's expression, verbatim
+    assert kept == 1090 and np.array_equal(times, want)
+    assert not np.array_equal(times, np.floor(np.arange(1090) * ms).astype(np.int32))   # the rounding is real
 
 
 def test_dataset_windows_match_reference_numbers():
