@@ -38,6 +38,7 @@ class ConvStem(nn.Module):
         self.conv2 = nn.Conv1d(d_model, d_model, kernel_size=3, stride=2, padding=1)
         self._handles: dict[int, int] = {}
         self._stamp: dict[int, tuple] = {}
+        self._retired: list[int] = []     # handles of superseded parameters: freed with the module, never earlier
 
     @classmethod
     def from_encoder(cls, encoder: nn.Module) -> "ConvStem":
@@ -48,7 +49,7 @@ class ConvStem(nn.Module):
 
     def __getstate__(self):
         state = self.__dict__.copy()
-        state["_handles"], state["_stamp"] = {}, {}
+        state["_handles"], state["_stamp"], state["_retired"] = {}, {}, []
         return state
 
     def _param_stamp(self) -> tuple:
@@ -63,8 +64,11 @@ class ConvStem(nn.Module):
             if h is not None and self._stamp.get(idx) == stamp:
                 return h
             lib = _stem_lib.lib()
-            if h is not None:                       # parameters were reloaded / edited: repack
-                lib.bhstem_destroy(h)
+            if h is not None:
+                # Parameters were reloaded / edited: repack into a NEW handle.  Another thread may still
+                # be inside bhstem_forward with the old one (the lock is released before the launch), so
+                # it is only retired here and destroyed together with the module.
+                self._retired.append(h)
                 del self._handles[idx]
             host = [p.detach().to("cpu", torch.float32).contiguous()
                     for p in (self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias)]
@@ -80,7 +84,7 @@ class ConvStem(nn.Module):
     def __del__(self):
         try:
             lib = _stem_lib.lib()
-            for h in self._handles.values():
+            for h in [*self._handles.values(), *self._retired]:
                 lib.bhstem_destroy(h)
         except Exception:
             pass

@@ -81,8 +81,10 @@ __global__ void bhmel_absmax_pcm16_kernel(const int16_t* __restrict__ in, long l
   if ((threadIdx.x & 31) == 0 && m) atomicMax(out_max, m);
 }
 
-__global__ void bhmel_peak_to_scale_kernel(const unsigned* __restrict__ max_abs, float* __restrict__ scale) {
-  *scale = 1.0f / static_cast<float>(*max_abs);   // 1/0 -> +inf, like the reference's division by zero
+// In place: the 4 bytes at `scale` hold max|pcm| as an unsigned integer on entry and 1.0f / max on exit.
+__global__ void bhmel_peak_to_scale_kernel(float* __restrict__ scale) {
+  const unsigned m = *reinterpret_cast<const unsigned*>(scale);
+  *scale = 1.0f / static_cast<float>(m);   // 1/0 -> +inf, like the reference's division by zero
 }
 
 // ---- encoder-input assembly helpers (bhmel_forward_encoder_input); T = float or __nv_bfloat16 ----
@@ -176,10 +178,9 @@ struct bhmel_handle {
   int16_t* d_pcm[kHostSlots] = {nullptr, nullptr, nullptr};
   float* d_scales = nullptr;
   size_t cap_in = 0, cap_out = 0, cap_pcm = 0, cap_scales = 0;
-  // bhmel_peak_scale_pcm16 / bhmel_forward_gather_pcm16 (lazily created)
+  // bhmel_forward_encoder_input / bhmel_forward_gather_pcm16 scratch (lazily created, only when the caller passes none)
   void* d_stage = nullptr;     // bhmel_forward_encoder_input, BCT layout: [B][T][n_mels] of the output dtype
   size_t cap_stage = 0;
-  unsigned* d_peak = nullptr;
   float* d_song = nullptr;     // float32 copy of the int16 song the gather kernel reads
   size_t cap_song = 0;
 };
@@ -491,7 +492,6 @@ void bhmel_destroy(bhmel_handle* h) {
   }
   if (h->d_scales) cudaFree(h->d_scales);
   if (h->d_stage) cudaFree(h->d_stage);
-  if (h->d_peak) cudaFree(h->d_peak);
   if (h->d_song) cudaFree(h->d_song);
   if (h->d_win) cudaFree(h->d_win);
   if (h->d_tw) cudaFree(h->d_tw);
@@ -630,14 +630,15 @@ int bhmel_peak_scale_pcm16(bhmel_handle* h, const int16_t* pcm_dev, int64_t n, f
   if (n <= 0) return fail(BHMEL_ESHAPE, "sample count must be positive");
   if (reinterpret_cast<uintptr_t>(pcm_dev) & 1) return fail(BHMEL_EINVAL, "pcm_dev must be 2-byte aligned");
   if (int rc = check_device(h)) return rc;
-  std::lock_guard<std::mutex> lock(h->host_mu);
+  // The reduction runs in the caller's own 4 bytes (integer max first, converted in place), so the
+  // entry owns no handle state: any number of threads / streams may share one handle.
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (!h->d_peak) BH_CUDA(cudaMalloc(&h->d_peak, sizeof(unsigned)));
-  BH_CUDA(cudaMemsetAsync(h->d_peak, 0, sizeof(unsigned), s));
+  unsigned* peak = reinterpret_cast<unsigned*>(scale_dev);
+  BH_CUDA(cudaMemsetAsync(peak, 0, sizeof(unsigned), s));
   const long long work = (n + 8 * 256 - 1) / (8 * 256);
   const unsigned blocks = static_cast<unsigned>(work < h->num_sms * 8 ? (work < 1 ? 1 : work) : h->num_sms * 8);
-  bhmel_absmax_pcm16_kernel<<<blocks, 256, 0, s>>>(pcm_dev, n, h->d_peak);
-  bhmel_peak_to_scale_kernel<<<1, 1, 0, s>>>(h->d_peak, scale_dev);
+  bhmel_absmax_pcm16_kernel<<<blocks, 256, 0, s>>>(pcm_dev, n, peak);
+  bhmel_peak_to_scale_kernel<<<1, 1, 0, s>>>(scale_dev);
   BH_CUDA(cudaGetLastError());
   h->launches.fetch_add(2, std::memory_order_relaxed);
   return BHMEL_OK;

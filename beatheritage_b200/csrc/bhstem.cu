@@ -15,9 +15,9 @@
 // Three kernels share the tile shape (128 rows x BN channels), the epilogue and the barrier protocol:
 //   bhstem_conv_gelu_shared_kernel  DEFAULT.  One staged block of rows per 64-channel step feeds all taps
 //                                   through row-shifted descriptors; separate weight / activation rings.
-//   bhstem_conv_gelu_kernel         BHSTEM_VARIANT=0: one TMA box per (tap, channel step); the first
+//   bhstem_conv_gelu_kernel         BHSTEM_VARIANT_TAP_BOXES: one TMA box per (tap, channel step); the first
 //                                   working version, kept as the A/B baseline.
-//   bhstem_conv_gelu_pair_kernel    BHSTEM_VARIANT=2: CTA pairs, tcgen05.mma.cta_group::2, half a weight
+//   bhstem_conv_gelu_pair_kernel    BHSTEM_VARIANT_CTA_PAIRS: CTA pairs, tcgen05.mma.cta_group::2, half a weight
 //                                   tile per CTA; correct, measured no faster.
 // One persistent CTA per SM, warp-specialised (default kernel: 352 threads):
 //   warp 0      weight producer       one thread: TMA box BN rows x 64 ch per (channel step, tap), 128-byte
@@ -72,7 +72,7 @@ struct StemProblem {
   int32_t c_in;            // channels per tap
   int32_t tap_col[3];      // column offset of each tap inside a row of the A view
   int32_t tap_row[3];      // row offset of each tap
-  int32_t exp;             // timing experiments (wrong results): 1 no W loads, 2 no epilogue math / stores, 4 no A loads
+  int32_t exp;             // -DBHSTEM_PROFILE builds only (always 0 otherwise): 1 no W loads, 2 no epilogue math / stores, 4 no A loads
 };
 
 // The C channels of a tap are n16 = ceil(C / 16) MMA steps dealt EVENLY over k_blocks = ceil(n16 / 4)
@@ -292,7 +292,9 @@ __device__ __forceinline__ void epilogue_role(const StemProblem& p, const float*
           else mbar_arrive(tempty0 + 8 * as);
         }
       }
+#ifdef BHSTEM_PROFILE
       if (p.exp & 2) continue;
+#endif
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(brow + c * 32 + j));
@@ -505,9 +507,12 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
           const int c0 = ks.first_channel(kb);
           { PROF_T0(); mbar_wait(aempty0 + 8 * as, aph ^ 1); PROF_ADD(0); }
           const uint32_t sa = ring_a + as * ASTAGE_BYTES;
+#ifdef BHSTEM_PROFILE
           if (p.exp & 4) {
             mbar_arrive(afull0 + 8 * as);
-          } else {
+          } else
+#endif
+          {
             mbar_expect_tx(afull0 + 8 * as, a_bytes);
             tma_load_3d(&map_a0, afull0 + 8 * as, sa, st.a_col[0] + c0, mt * BLOCK_M + st.a_row[0], b);
             if (st.n_aloads == 2)
@@ -524,9 +529,12 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
           const int c0 = ks.first_channel(kb);
           for (int tap = 0; tap < 3; ++tap) {
             { PROF_T0(); mbar_wait(wempty0 + 8 * ws, wph ^ 1); PROF_ADD(1); }
+#ifdef BHSTEM_PROFILE
             if (p.exp & 1) {
               mbar_arrive(wfull0 + 8 * ws);
-            } else {
+            } else
+#endif
+            {
               mbar_expect_tx(wfull0 + 8 * ws, C::W_BYTES);
               tma_load_3d(&map_w, wfull0 + 8 * ws, ring_w + ws * C::W_BYTES, c0, nt * BN, tap);
             }
@@ -814,7 +822,7 @@ struct bhstem_handle {
   std::atomic<long long> launches{0};   // the only state forward calls mutate: handles may be shared by threads
   int variant = 1;      // 1: shared taps (row-shifted descriptors, default), 0: one TMA box per tap
   int pairs = 0;        // 1: CTA-pair kernel (tcgen05 cta_group::2) when d_model % 256 == 0
-  int exp = 0;          // BHSTEM_EXP: timing experiments (wrong results), read once at create
+  int exp = 0;          // -DBHSTEM_PROFILE builds only: BHSTEM_EXP timing experiments (wrong results)
 };
 
 namespace {
@@ -961,8 +969,9 @@ int bhstem_create(int32_t c_in, int32_t d_model, const float* conv1_weight, cons
   h->d = d_model;
   h->bn = d_model % 256 == 0 ? 256 : 128;
   h->variant = 1;
-  if (const char* v = getenv("BHSTEM_VARIANT")) { h->variant = atoi(v) == 0 ? 0 : 1; h->pairs = atoi(v) == 2; }   // A/B: 0 = one TMA box per tap
+#ifdef BHSTEM_PROFILE   // tools-only build: timing experiments that skip loads / stores (wrong results)
   if (const char* v = getenv("BHSTEM_EXP")) h->exp = atoi(v);
+#endif
   h->enc = encode_tiled_fn();
   if (!h->enc) { delete h; return fail(BHSTEM_ECUDA, "cuTensorMapEncodeTiled is not available from this driver"); }
   const std::vector<__nv_bfloat16> w1 = pack_weight(conv1_weight, d_model, c_in), w2 = pack_weight(conv2_weight, d_model, d_model);
@@ -1019,6 +1028,16 @@ void bhstem_destroy(bhstem_handle* h) {
   cudaFree(h->b1);
   cudaFree(h->b2);
   delete h;
+}
+
+int bhstem_set_option(bhstem_handle* h, int32_t option, int64_t value) {
+  if (!h) return fail(BHSTEM_EINVAL, "null handle");
+  if (option != BHSTEM_OPT_VARIANT) return fail(BHSTEM_EINVAL, "unknown option");
+  if (value != BHSTEM_VARIANT_TAP_BOXES && value != BHSTEM_VARIANT_SHARED_TAPS && value != BHSTEM_VARIANT_CTA_PAIRS)
+    return fail(BHSTEM_EINVAL, "unknown kernel variant");
+  h->variant = value == BHSTEM_VARIANT_TAP_BOXES ? 0 : 1;
+  h->pairs = value == BHSTEM_VARIANT_CTA_PAIRS;
+  return BHSTEM_OK;
 }
 
 int bhstem_forward_stage(bhstem_handle* h, int32_t stage, const void* in, int64_t B, int64_t T, void* out, void* stream) {

@@ -119,6 +119,16 @@ def _(samples, module_key, n_mels):
     return samples.new_empty((samples.shape[0], samples.shape[1] // HOP + 1, n_mels), dtype=torch.float32)
 
 
+def _no_backward(ctx, grad):
+    raise RuntimeError(
+        "beatheritage_b200.MelSpectrogram is a forward-only replacement: the reference never differentiates "
+        "through its frontend (no parameters; the input never requires grad), so no backward is provided. "
+        "Detach the samples, or keep torchaudio's transform for an input that needs gradients.")
+
+
+_mel_forward_op.register_autograd(_no_backward)
+
+
 # ----------------------------------------------------------------------------------------
 # State dict in nnAudio's layout (implementation="nnAudio", nnaudio_arithmetic="published").
 # nnAudio 0.3.x registers (names restated from its published source, UNPINNED like the rest of N4):

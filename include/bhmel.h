@@ -144,7 +144,9 @@ int bhmel_forward_gather(bhmel_handle* h, const float* song, int64_t n_song, int
  * the factor of the reference's `samples *= 1.0 / np.max(np.abs(samples))` after its
  * `.astype(np.float32)` (ref: osuT5/osuT5/dataset/data_utils.py:94-96).  An all-zero song gives
  * +inf exactly like the reference's division by zero (its samples then become NaN).
- * pcm_dev DEVICE int16 [n];  scale_dev DEVICE float32 [1].  Asynchronous on `stream`. */
+ * pcm_dev DEVICE int16 [n];  scale_dev DEVICE float32 [1], 4-byte aligned: it doubles as the
+ * reduction's scratch (integer max first, converted in place), so the call owns no handle state
+ * and is re-entrant across threads and streams sharing one handle.  Asynchronous on `stream`. */
 int bhmel_peak_scale_pcm16(bhmel_handle* h, const int16_t* pcm_dev, int64_t n, float* scale_dev, void* stream);
 
 /* bhmel_forward_gather for a song kept on the device as int16 PCM (2 bytes per sample resident

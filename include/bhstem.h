@@ -67,6 +67,14 @@ int bhstem_forward(bhstem_handle* h, const void* x, int64_t B, int64_t T, void* 
 int bhstem_forward_stage(bhstem_handle* h, int32_t stage, const void* in, int64_t B, int64_t T, void* out,
                          void* stream);
 
+/* Kernel schedule of this handle (A/B experiments and wider models; all variants give the same results
+ * within the bf16 tolerance).  The choice is explicit -- no environment variable is read by the library. */
+#define BHSTEM_OPT_VARIANT 1
+#define BHSTEM_VARIANT_TAP_BOXES 0    /* one TMA box per (tap, channel step) */
+#define BHSTEM_VARIANT_SHARED_TAPS 1  /* default: one staged block, three row-shifted descriptors */
+#define BHSTEM_VARIANT_CTA_PAIRS 2    /* tcgen05.mma.cta_group::2 (d_model % 256 == 0, even SM count) */
+int bhstem_set_option(bhstem_handle* h, int32_t option, int64_t value);
+
 int bhstem_version(void);
 const char* bhstem_last_error(void);
 /* Kernel launches issued through this handle so far. */

@@ -171,6 +171,42 @@ def test_peak_scale_of_a_resident_int16_song(mods, dev, n, offset):
     assert np.isinf(m.peak_scale(zeros).cpu().numpy()[0])          # the reference divides by zero here too
 
 
+def test_peak_scale_is_reentrant_across_threads_and_streams_of_one_handle(mods, dev):
+    """two host threads share ONE module (one handle) and reduce different songs on their own
+    streams; the reduction lives in each call's own output word, so neither disturbs the other."""
+    import threading
+    m = mods["P0"]
+    rng = np.random.default_rng(77)
+    songs, wants = [], []
+    for peak in (1234, 31000):
+        pcm = rng.integers(-peak, peak, size=3_000_001, dtype=np.int16)
+        pcm[int(rng.integers(len(pcm)))] = peak
+        songs.append(torch.from_numpy(pcm).to(dev))
+        wants.append(np.float32(1.0) / np.float32(peak))
+    m.peak_scale(songs[0])
+    torch.cuda.synchronize()
+    errors = []
+
+    def worker(song, want):
+        try:
+            s = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(s):
+                got = [m.peak_scale(song) for _ in range(200)]
+            s.synchronize()
+            bad = sum(float(g.cpu()[0]) != float(want) for g in got)
+            if bad:
+                errors.append(f"{bad} wrong scales")
+        except Exception as e:   # pragma: no cover
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=a) for a in zip(songs, wants)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert errors == []
+
+
 def test_gather_from_a_resident_int16_song_matches_the_reference_loader(mods, dev):
     """int16 song on the device -> on-device peak -> fused convert + gather  ==  the reference's host
     path: astype(float32), samples *= 1/max|samples| (data_utils.py:94-96), segment, forward."""
