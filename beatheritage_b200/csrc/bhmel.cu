@@ -168,8 +168,8 @@ struct bhmel_handle {
   std::atomic<int64_t> launches{0};
   int use_bulk = 1;
   int kernel_variant = BHMEL_KERNEL_WARP_SPECIALIZED;
-  int baked_fb = 0;      // 1: the filterbank is bit-identical to the baked P0 table (bhmel_fb_baked.h)
-  int static_mel = 1;    // BHMEL_OPT_STATIC_MEL: use the statically scheduled mel stage when baked_fb != 0
+  int baked_fb = 0;      // id of the baked table (bhmel_fb_baked.h) the filterbank equals bit for bit: 1 = P0, 2.. = all-static sets; 0 = none
+  int static_mel = 1;    // BHMEL_OPT_STATIC_MEL: 0 generic stage always, 1 the baked table's default static stage, 2 P0 takes its direct form too
   // bhmel_forward_host pipeline (lazily created)
   std::mutex host_mu;
   cudaStream_t hs[kHostSlots] = {nullptr, nullptr, nullptr};
@@ -187,12 +187,23 @@ struct bhmel_handle {
 
 namespace {
 
-// Which baked filterbank (bhmel_fb_baked.h) the host table equals bit for bit; 0 = none.
+// Which baked filterbank (bhmel_fb_baked.h) the host table equals bit for bit: its id, or 0 for none.
 int match_baked_fb(const std::vector<float>& fb, int n_mels) {
-  if (n_mels != kBakedP0Mels) return 0;
-  std::vector<uint32_t> want(static_cast<size_t>(bhmel::kBins) * n_mels, 0u);
-  for (int i = 0; i < kBakedP0Nnz; ++i) want[static_cast<size_t>(kBakedP0[i][0]) * n_mels + kBakedP0[i][1]] = kBakedP0[i][2];
-  return std::memcmp(want.data(), fb.data(), want.size() * sizeof(uint32_t)) == 0 ? 1 : 0;
+  for (int t = 0; t < kNumBakedFbs; ++t) {
+    const BakedFb& b = kBakedFbs[t];
+    if (b.n_mels != n_mels) continue;
+    std::vector<uint32_t> want(static_cast<size_t>(bhmel::kBins) * n_mels, 0u);
+    int pos = 0;
+    for (int m = 0; m < n_mels; ++m)
+      for (int j = 0; j < b.count[m]; ++j) want[static_cast<size_t>(b.start[m] + j) * n_mels + m] = b.bits[pos++];
+    // value equality with -0 == +0: torchaudio's P1 / T5 tables carry a negative zero at [0][0]
+    // (max(0, min(down, up)) of a -0 slope); a zero weight of either sign contributes nothing
+    const uint32_t* got = reinterpret_cast<const uint32_t*>(fb.data());
+    bool same = true;
+    for (size_t i = 0; i < want.size() && same; ++i) same = want[i] == got[i] || ((want[i] | got[i]) & 0x7fffffffu) == 0;
+    if (same) return b.id;
+  }
+  return 0;
 }
 
 int upload_filterbank(bhmel_handle* h) {
@@ -337,21 +348,52 @@ int launch(bhmel_handle* h, const float* x, long long row_stride, long long row0
       bhmel::iw::bhmel_logmel_iw_kernel<false><<<grid, bhmel::iw::kIwThreads, sizeof(bhmel::iw::SmemIW), stream>>>(q);
   } else if (ws) {
     const unsigned grid = static_cast<unsigned>(p.n_tiles < h->num_sms ? p.n_tiles : h->num_sms);
-    const bool st = h->static_mel && h->baked_fb == 1;
+    // Which mel stage: 0 generic, 1 P0 hybrid, >= 2 a direct form (vector stores from registers: the
+    // output rows must be 16-byte (float32) / 8-byte (bfloat16) aligned, else the generic stage runs).
+    int st = h->static_mel ? h->baked_fb : 0;
+    if (st == 1 && h->static_mel == 2) st = bhmel::kStaticP0Direct;
+    if (st >= 2) {
+      const uintptr_t align = out.bf16 ? 8 : 16;
+      const bool ok = (reinterpret_cast<uintptr_t>(y) % align) == 0 && p.y_frame_pitch % 4 == 0 && p.y_row_pitch % 4 == 0;
+      if (!ok) st = st == bhmel::kStaticP0Direct ? 1 : 0;
+    }
     constexpr size_t smem = sizeof(bhmel::ws::SmemWS);
-    if (st) {   // the generic stage only sees the filters the generated code leaves
+    if (st == 1) {   // hybrid: the generic stage only sees the filters the generated code leaves
       p.pairs = h->d_pairs_rem;
       p.weights = h->d_weights_rem;
       p.n_pairs = h->n_pairs_rem;
       p.n_weights = h->n_weights_rem;
+    } else if (st >= 2) {   // direct: no tables at all
+      p.n_pairs = 0;
+      p.n_weights = 0;
     }
-    if (p.log_scale) {
-      if (st) bhmel::ws::bhmel_logmel_ws_kernel<true, 1><<<grid, bhmel::ws::kThreadsW, smem, stream>>>(p);
-      else bhmel::ws::bhmel_logmel_ws_kernel<true, 0><<<grid, bhmel::ws::kThreadsW, smem, stream>>>(p);
-    } else {
-      if (st) bhmel::ws::bhmel_logmel_ws_kernel<false, 1><<<grid, bhmel::ws::kThreadsW, smem, stream>>>(p);
-      else bhmel::ws::bhmel_logmel_ws_kernel<false, 0><<<grid, bhmel::ws::kThreadsW, smem, stream>>>(p);
+#define BHMEL_WS_LAUNCH(LOG, ST, BF) bhmel::ws::bhmel_logmel_ws_kernel<LOG, ST, BF><<<grid, bhmel::ws::kThreadsW, smem, stream>>>(p)
+#define BHMEL_WS_DIRECT(ST)                                        \
+  case ST:                                                         \
+    if (p.log_scale) {                                             \
+      if (p.y_bf16) BHMEL_WS_LAUNCH(true, ST, true);               \
+      else BHMEL_WS_LAUNCH(true, ST, false);                       \
+    } else {                                                       \
+      if (p.y_bf16) BHMEL_WS_LAUNCH(false, ST, true);              \
+      else BHMEL_WS_LAUNCH(false, ST, false);                      \
+    }                                                              \
+    break
+    switch (st) {
+      case 1:
+        if (p.log_scale) BHMEL_WS_LAUNCH(true, 1, false);
+        else BHMEL_WS_LAUNCH(false, 1, false);
+        break;
+      BHMEL_WS_DIRECT(2);
+      BHMEL_WS_DIRECT(3);
+      BHMEL_WS_DIRECT(4);
+      BHMEL_WS_DIRECT(5);
+      default:
+        if (p.log_scale) BHMEL_WS_LAUNCH(true, 0, false);
+        else BHMEL_WS_LAUNCH(false, 0, false);
+        break;
     }
+#undef BHMEL_WS_DIRECT
+#undef BHMEL_WS_LAUNCH
   } else {
     const unsigned grid = static_cast<unsigned>(p.n_tiles < h->num_sms ? p.n_tiles : h->num_sms);
     if (p.log_scale)
@@ -437,14 +479,19 @@ int bhmel_create(const bhmel_params* prm, bhmel_handle** out) {
                                static_cast<int>(sizeof(bhmel::SmemLayout))));
   BH_CUDA(cudaFuncSetAttribute(bhmel::bhmel_logmel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(sizeof(bhmel::SmemLayout))));
-  BH_CUDA(cudaFuncSetAttribute(bhmel::ws::bhmel_logmel_ws_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               static_cast<int>(sizeof(bhmel::ws::SmemWS))));
-  BH_CUDA(cudaFuncSetAttribute(bhmel::ws::bhmel_logmel_ws_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               static_cast<int>(sizeof(bhmel::ws::SmemWS))));
-  BH_CUDA(cudaFuncSetAttribute(bhmel::ws::bhmel_logmel_ws_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               static_cast<int>(sizeof(bhmel::ws::SmemWS))));
-  BH_CUDA(cudaFuncSetAttribute(bhmel::ws::bhmel_logmel_ws_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               static_cast<int>(sizeof(bhmel::ws::SmemWS))));
+#define BHMEL_WS_ATTR(ST, BF)                                                                                             \
+  BH_CUDA(cudaFuncSetAttribute(bhmel::ws::bhmel_logmel_ws_kernel<true, ST, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                               static_cast<int>(sizeof(bhmel::ws::SmemWS))));                                               \
+  BH_CUDA(cudaFuncSetAttribute(bhmel::ws::bhmel_logmel_ws_kernel<false, ST, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                               static_cast<int>(sizeof(bhmel::ws::SmemWS))))
+  static_assert(bhmel::kStaticP0Direct == 5, "launch() and bhmel_create() enumerate the direct forms 2..5");
+  BHMEL_WS_ATTR(0, false);
+  BHMEL_WS_ATTR(1, false);
+  BHMEL_WS_ATTR(2, false); BHMEL_WS_ATTR(2, true);
+  BHMEL_WS_ATTR(3, false); BHMEL_WS_ATTR(3, true);
+  BHMEL_WS_ATTR(4, false); BHMEL_WS_ATTR(4, true);
+  BHMEL_WS_ATTR(5, false); BHMEL_WS_ATTR(5, true);
+#undef BHMEL_WS_ATTR
   BH_CUDA(cudaFuncSetAttribute(bhmel::iw::bhmel_logmel_iw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(sizeof(bhmel::iw::SmemIW))));
   BH_CUDA(cudaFuncSetAttribute(bhmel::iw::bhmel_logmel_iw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -550,7 +597,8 @@ int bhmel_set_option(bhmel_handle* h, int32_t option, int64_t value) {
       h->kernel_variant = static_cast<int>(value);
       return BHMEL_OK;
     case BHMEL_OPT_STATIC_MEL:
-      h->static_mel = value != 0;
+      if (value < 0 || value > 2) return fail(BHMEL_EINVAL, "BHMEL_OPT_STATIC_MEL takes 0, 1 or 2");
+      h->static_mel = static_cast<int>(value);
       return BHMEL_OK;
     default:
       return fail(BHMEL_EINVAL, "unknown option " + std::to_string(option));

@@ -20,6 +20,49 @@
 //             256-thread role group (named barrier 1).
 #pragma once
 #include "bhmel_kernel.cuh"
+
+namespace bhmel {
+// Output path of the direct static mel stages.  Each mel warp owns a staging block [32 frames][kStageCols
+// filters] (row pitch kStagePitch floats: pitch / 4 odd, so the lane = frame 128-bit stores are conflict
+// free); four finished filters of this lane's frame go in with one store (mel_stage4), and a full block
+// is written out by the same warp as row segments of up to 128 contiguous bytes (mel_flush, one shared
+// loop) -- float32, or bfloat16 rounded to nearest even.
+constexpr int kStageCols = 32;
+constexpr int kStagePitch = kStageCols + 4;
+__device__ __forceinline__ void mel_stage4(float* __restrict__ srow, int col, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(srow + col) = make_float4(a, b, c, d);
+}
+// Writes the first `ncols` (multiple of 4) columns of the warp's staging block to rows 0..nf-1 of the
+// tile: lane -> 16-byte column group lane & 7 of rows (lane >> 3) + 4 i, so one instruction moves four
+// row segments of up to 128 contiguous bytes.
+template <bool kBf16>
+__device__ __forceinline__ void mel_flush(const float* __restrict__ stage, void* __restrict__ ytile, long long fpitch,
+                                          int m0, int ncols, int nf, int lane) {
+  __syncwarp();
+  const int c = 4 * (lane & 7);
+  if (c < ncols) {
+    const float* sp = stage + (lane >> 3) * kStagePitch + c;
+    long long off = static_cast<long long>(lane >> 3) * fpitch + m0 + c;
+#pragma unroll
+    for (int i = 0; i < kTileF / 4; ++i, sp += 4 * kStagePitch, off += 4 * fpitch) {
+      if ((lane >> 3) + 4 * i < nf) {
+        const float4 v = *reinterpret_cast<const float4*>(sp);
+        if constexpr (kBf16) {
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+          uint2 q;
+          q.x = *reinterpret_cast<const unsigned*>(&lo);
+          q.y = *reinterpret_cast<const unsigned*>(&hi);
+          *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(ytile) + off) = q;
+        } else {
+          *reinterpret_cast<float4*>(static_cast<float*>(ytile) + off) = v;
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+}  // namespace bhmel
+
 #include "mel_static_gen.h"
 
 namespace bhmel {
@@ -46,13 +89,17 @@ constexpr int kMelRegs = ((2 + kMelGroups) * kLaunchRegs - 2 * kFftRegs) / kMelG
 static_assert(2 * kFftRegs + kMelGroups * kMelRegs <= (2 + kMelGroups) * kLaunchRegs, "setmaxnreg pool would deadlock");
 static_assert(kMelRegs >= 24 && kMelRegs <= 256 && kFftRegs <= 256, "setmaxnreg range");
 static_assert(2 * kPPitchW * 4 >= 32 * kPlanePitch * 4, "a pair's two P rows must hold one transposed plane");
+static_assert(kMelWarps * kTileF * kStagePitch * 4 <= (kTileF * kOutPitch + kFwCap) * 4 + kPairCap * 16 &&
+                  (kTileF * kOutPitch * 4) % 16 == 0 && (kFwCap * 4) % 16 == 0,
+              "the direct stages' staging blocks overlay out / fw / pairs, which must be contiguous");
 
 struct SmemWS {
   float P[2][kTileF * kPPitchW];              // 136 192 B
   float span[2][kSpan + 4];                   //  39 968 B  (+4: slack for the aligned-down TMA copy of unaligned rows)
-  float out[kTileF * kOutPitch];              //  12 416 B
-  float fw[kFwCap];                           //  16 384 B
-  int4 pairs[kPairCap];                       //   8 192 B
+  float out[kTileF * kOutPitch];              //  12 416 B  } generic / hybrid stages; the direct stages use the
+  float fw[kFwCap];                           //  16 384 B  } same 36 992 bytes as eight private staging blocks
+  int4 pairs[kPairCap];                       //   8 192 B  } [32][kStagePitch] (mel_stage())
+  __device__ float* mel_stage() { return out; }
   unsigned long long span_full[2];
   unsigned long long p_full[2];
   unsigned long long p_empty[2];
@@ -129,11 +176,17 @@ __device__ __forceinline__ void issue_span(const KParams& p, long long tile, flo
 }
 
 // kStatic selects the mel stage: 0 = generic (pair descriptors + weight table, any filterbank);
-// 1 = the baked P0 filterbank: mel warps 0..kStaticP0Warps-1 run generated straight-line code
-// (mel_static_gen.h: weights as FFMA immediates, every power block read once) for filters
-// 0..kStaticP0Filters-1, the other mel warps run the generic stage on the pair tables of the
-// remaining filters.  Results are bit-identical to kStatic = 0.
-template <bool kLog, int kStatic = 0>
+// otherwise the id of a baked reference filterbank (bhmel_fb_baked.h kBakedFbs):
+// 1 = P0: mel warps 0..kStaticP0Warps-1 run generated straight-line code (mel_static_gen.h: weights
+// as FFMA immediates, every power block read once) for filters 0..kStaticP0Filters-1, the other mel
+// warps run the generic stage on the pair tables of the remaining filters;
+// >= 2 (P128, P1, T5; kStaticP0Direct = P0 again, for A/B runs): the DIRECT form -- all eight mel
+// warps run generated code, one block per warp and tile, results leave through the warp's private
+// staging block (mel_stage4 / mel_flush): no chunk loop, no cross-warp barriers.  kBf16 is the output type
+// of the direct forms (the others read p.y_bf16).
+// kStatic <= 1 is bit-identical to the generic stage; the direct forms sum each filter in one or two
+// chains instead of four and agree with it to a few ulp.
+template <bool kLog, int kStatic = 0, bool kBf16 = false>
 __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemWS& S = *reinterpret_cast<SmemWS*>(smem_raw);
@@ -142,6 +195,9 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
   const int lane = tid & 31;
 
   static_assert(kStatic == 0 || (kMelWarps == 8 && kStaticP0Warps < kMelWarps), "static mel stage: 8 mel warps");
+  static_assert(kStatic >= 0 && kStatic <= kStaticP0Direct, "kStatic is 0 or the id of a baked filterbank");
+  constexpr bool kDirect = kStatic >= 2;
+  static_assert(kDirect || !kBf16, "kBf16 only selects the store type of the direct forms");
   const bool fw_in_smem = p.n_weights <= kFwCap;   // the host guarantees this for kStatic != 0
   if (fw_in_smem)
     for (int i = tid; i < p.n_weights; i += kThreadsW) S.fw[i] = p.weights[i];
@@ -271,6 +327,22 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
       const long long ybase = static_cast<long long>(r) * p.y_row_pitch + static_cast<long long>(t0) * p.y_frame_pitch;
       const float4* prow = reinterpret_cast<const float4*>(S.P[b] + lane * kPPitchW);
       float* orow = S.out + lane * kOutPitch;
+      if constexpr (kDirect) {
+        void* ytile = kBf16 ? static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(p.y) + ybase) : static_cast<void*>(p.y + ybase);
+        float* stage = S.mel_stage() + mw * (kTileF * kStagePitch);
+        constexpr int kParts = mel_direct_parts<kStatic>();
+#pragma unroll 1
+        for (int part = 0; part < kParts; ++part) {
+          mel_direct<kStatic, kLog>(prow, stage + lane * kStagePitch, mw, part);
+          if (part == kParts - 1) {   // this warp no longer reads P[b]
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.p_empty[b]);
+          }
+          int m0, ncols;
+          mel_direct_run<kStatic>(mw * kParts + part, m0, ncols);
+          mel_flush<kBf16>(stage, ytile, p.y_frame_pitch, m0, ncols, nf, lane);
+        }
+      } else {
 #ifdef BHMEL_DEBUG_SKIP_MEL
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.p_empty[b]);
@@ -329,6 +401,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
         BHMEL_TR(4);
         mel_group_sync();   // staging free again
         BHMEL_TR(5);
+      }
       }
       r += step_r;
       tb += step_tb;

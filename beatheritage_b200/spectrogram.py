@@ -260,7 +260,7 @@ class MelSpectrogram(nn.Module):
         self._stamp: dict[int, tuple] = {}        # device index -> buffer versions the handle was built from
         self._bulk = True
         self._variant = _lib.KERNEL_WARP_SPECIALIZED
-        self._static_mel = True
+        self._static_mel = 1
         self._register()
 
     def _register(self) -> None:
@@ -311,8 +311,8 @@ class MelSpectrogram(nn.Module):
                     if not self._bulk:
                         _lib.check(lib.bhmel_set_option(h, _lib.OPT_BULK_COPY, 0))
                     _lib.check(lib.bhmel_set_option(h, _lib.OPT_KERNEL, self._variant))
-                    if not getattr(self, "_static_mel", True):
-                        _lib.check(lib.bhmel_set_option(h, _lib.OPT_STATIC_MEL, 0))
+                    if int(getattr(self, "_static_mel", 1)) != 1:
+                        _lib.check(lib.bhmel_set_option(h, _lib.OPT_STATIC_MEL, int(self._static_mel)))
                 else:   # buffers were reloaded / edited: refresh the device tables
                     _lib.check(lib.bhmel_set_fb(h, ctypes.cast(fb.data_ptr(), fp)))
                     _lib.check(lib.bhmel_set_window(h, ctypes.cast(win.data_ptr(), fp)))
@@ -346,10 +346,11 @@ class MelSpectrogram(nn.Module):
         for h in self._handles.values():
             _lib.check(_lib.lib().bhmel_set_option(h, _lib.OPT_KERNEL, self._variant))
 
-    def set_static_mel(self, enabled: bool) -> None:
-        """Debug / A-B switch: False forces the generic mel stage even for the baked default
-        filterbank (results are bit-identical; see BHMEL_OPT_STATIC_MEL in include/bhmel.h)."""
-        self._static_mel = bool(enabled)
+    def set_static_mel(self, enabled) -> None:
+        """Debug / A-B switch: False / 0 forces the generic mel stage even for the baked reference
+        filterbanks, True / 1 is the default, 2 also gives P0 its direct form (see BHMEL_OPT_STATIC_MEL
+        in include/bhmel.h)."""
+        self._static_mel = int(enabled)
         for h in self._handles.values():
             _lib.check(_lib.lib().bhmel_set_option(h, _lib.OPT_STATIC_MEL, int(self._static_mel)))
 

@@ -105,7 +105,8 @@ def emu_lib():
     def run(x, n_mels, fb=None, window=None, f_min=20.0, f_max=8000.0, reflect=True, log=True,
             gather=None, rounds=False, static_mel=False):
         """gather = (first_offset, stride, W, window_len) treats x as a 1-D song.  rounds / static_mel pick
-        the mel stage of the independent-warp kernel / the hybrid generated-code stage (baked P0 table)."""
+        the mel stage of the independent-warp kernel / the generated-code stage of a baked filterbank
+        (static_mel=True: the default form -- P0 hybrid, the others direct; static_mel=2: P0 direct too)."""
         x = np.ascontiguousarray(x, np.float32)
         if gather is None:
             B, N = x.shape
@@ -118,7 +119,7 @@ def emu_lib():
         wp = window.ctypes.data_as(fp) if window is not None else None
         rc = lib.bhmel_emu_forward(x.ctypes.data_as(fp), B, N, stride, row0, n_total, n_mels, fbp, wp,
                                    float(f_min), float(f_max), 16000, int(reflect), int(log),
-                                   (2 if rounds else 0) | (4 if static_mel else 0),
+                                   (2 if rounds else 0) | (4 if static_mel else 0) | (8 if static_mel == 2 else 0),
                                    y.ctypes.data_as(fp))
         assert rc == 0
         return y

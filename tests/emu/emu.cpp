@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #define BHMEL_HD static inline
@@ -18,9 +19,17 @@
 struct float4 { float x, y, z, w; };
 #define __device__
 #define __forceinline__ inline
+#define __constant__
 static inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
 static inline float __fmul_rn(float a, float b) { return a * b; }   // built with -ffp-contract=off
-namespace bhmel { static inline float fast_log1p(float v) { return logf(1.0f + v); } }
+namespace bhmel {
+static inline float fast_log1p(float v) { return logf(1.0f + v); }
+// direct static stages: the staging block of one frame (lane) is a plain array here, mel_flush copies it out
+constexpr int kStageCols = 32, kStagePitch = kStageCols + 4;
+static inline void mel_stage4(float* srow, int col, float a, float b, float c, float d) {
+  srow[col] = a; srow[col + 1] = b; srow[col + 2] = c; srow[col + 3] = d;
+}
+}  // namespace bhmel
 #include "../../beatheritage_b200/csrc/mel_static_gen.h"
 
 namespace {
@@ -44,14 +53,26 @@ extern "C" int bhmel_emu_forward(const float* x, long long B, long long N, long 
   // bit 2: the warp-specialised kernel's hybrid mel stage for the baked P0 filterbank -- generated
   // code for filters < kStaticP0Filters, pair tables of the remaining filters for the rest
   const bool use_static = (exact_log1p & 4) != 0;
+  const bool p0_direct = (exact_log1p & 8) != 0;    // bit 3: P0 takes its direct form (BHMEL_OPT_STATIC_MEL = 2)
   exact_log1p &= 1;
   PairTables pt_rem;
+  int baked_id = 0;
   if (use_static) {
-    if (n_mels != kBakedP0Mels) return 2;
-    std::vector<uint32_t> want((size_t)kBins * n_mels, 0u);
-    for (int i = 0; i < kBakedP0Nnz; ++i) want[(size_t)kBakedP0[i][0] * n_mels + kBakedP0[i][1]] = kBakedP0[i][2];
-    if (std::memcmp(want.data(), fb.data(), want.size() * 4) != 0) return 2;   // not the baked table
-    pt_rem = make_pairs(fb.data(), n_mels, kStaticP0Filters);
+    for (int t = 0; t < kNumBakedFbs && !baked_id; ++t) {   // same bit-for-bit match as the library's match_baked_fb
+      const BakedFb& b = kBakedFbs[t];
+      if (b.n_mels != n_mels) continue;
+      std::vector<uint32_t> want((size_t)kBins * n_mels, 0u);
+      int pos = 0;
+      for (int m = 0; m < n_mels; ++m)
+        for (int j = 0; j < b.count[m]; ++j) want[(size_t)(b.start[m] + j) * n_mels + m] = b.bits[pos++];
+      const uint32_t* got = reinterpret_cast<const uint32_t*>(fb.data());
+      bool same = true;
+      for (size_t i = 0; i < want.size() && same; ++i) same = want[i] == got[i] || ((want[i] | got[i]) & 0x7fffffffu) == 0;
+      if (same) baked_id = b.id;
+    }
+    if (!baked_id) return 2;   // not a baked table
+    if (baked_id == 1 && p0_direct) baked_id = kStaticP0Direct;
+    if (baked_id == 1) pt_rem = make_pairs(fb.data(), n_mels, kStaticP0Filters);
   }
 
   const long long T = N / kHop + 1;
@@ -124,7 +145,31 @@ extern "C" int bhmel_emu_forward(const float* x, long long B, long long N, long 
       for (int f = 0; f < nf; ++f) {
         const float* prow = P.data() + (size_t)f * kPPitch;
         float* yrow = y + ((r * T + t0 + f) * (long long)n_mels);
-        if (use_static) {
+        if (use_static && baked_id >= 2) {   // direct forms: one generated block per mel warp, stores to the frame row
+          std::vector<float> tmp(n_mels);
+          float srow[kStagePitch];   // this frame's row of the warp's staging block
+          const float4* pr = reinterpret_cast<const float4*>(prow);
+          auto run_set = [&](auto tag) {
+            constexpr int kS = decltype(tag)::value;
+            constexpr int kParts = mel_direct_parts<kS>();
+            for (int mw = 0; mw < 8; ++mw)
+              for (int part = 0; part < kParts; ++part) {
+                mel_direct<kS, false>(pr, srow, mw, part);
+                int m0, ncols;
+                mel_direct_run<kS>(mw * kParts + part, m0, ncols);
+                for (int j = 0; j < ncols; ++j) tmp[m0 + j] = srow[j];   // mel_flush
+              }
+          };
+          if (baked_id == 2) run_set(std::integral_constant<int, 2>{});
+          if (baked_id == 3) run_set(std::integral_constant<int, 3>{});
+          if (baked_id == 4) run_set(std::integral_constant<int, 4>{});
+          if (baked_id == 5) run_set(std::integral_constant<int, 5>{});
+          for (int m = 0; m < n_mels; ++m) {
+            float v = tmp[m];
+            if (log_scale) v = exact_log1p ? log1pf(v) : logf(1.0f + v);
+            yrow[m] = v;
+          }
+        } else if (use_static) {
           float orow[96];
           for (int mw = 0; mw < kStaticP0Warps; ++mw)
             mel_static_P0<false>(reinterpret_cast<const float4*>(prow), orow, mw);

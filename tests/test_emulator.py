@@ -113,12 +113,38 @@ def test_round_tables_dense_and_odd_filter_counts(emu_lib):
 
 @pytest.mark.parametrize("log", [True, False])
 def test_static_mel_stage_is_bit_identical_to_the_generic_one(emu_lib, log):
-    """The generated straight-line mel code for the baked P0 filterbank (mel_static_gen.h, filters
-    below kStaticP0Filters) plus the pair tables of the remaining filters reproduce the generic
-    pair-table stage bit for bit -- same chains, same order, zero weights dropped."""
+    """The generated straight-line mel code for the baked P0 filterbank (mel_static_gen.h: the hybrid
+    form -- filters below kStaticP0Filters generated, pair tables for the rest) reproduces the generic
+    pair-table stage bit for bit: same chains, same order, zero weights dropped."""
     window, fb = load_params("P0")
     for x in (signals.noise(2, 9000, 11), signals.music(6000, seed=3)[None, :], 40.0 * signals.noise(1, 3000, 5),
               np.zeros((1, 2000), np.float32)):
         y_gen = emu_lib(x, 80, fb=fb, window=window, log=log)
         y_st = emu_lib(x, 80, fb=fb, window=window, log=log, static_mel=True)
         assert np.array_equal(y_st.view(np.uint32), y_gen.view(np.uint32))
+
+
+@pytest.mark.parametrize("pset,log,mode", [("P128", True, True), ("P1", False, True), ("T5", False, True), ("T5", True, True),
+                                           ("P0", True, 2), ("P0", False, 2)])
+def test_direct_mel_stages_agree_with_the_generic_one_and_the_oracle(emu_lib, pset, log, mode):
+    """The direct forms (P128 / P1 / T5 by default, P0 on request) sum every filter in one or two
+    chains instead of four, so they are not bit-identical to the generic stage: they must agree with
+    it to a few ulp, keep all-zero filters and silence exactly 0, and meet
+    the fp64 oracle like every other path."""
+    window, fb = load_params(pset)
+    n_mels = fb.shape[1]
+    empty = np.flatnonzero(~(fb != 0).any(axis=0))
+    for x in (signals.noise(2, 9000, 11), signals.music(6000, seed=3)[None, :], 40.0 * signals.noise(1, 3000, 5),
+              np.zeros((1, 2000), np.float32)):
+        y_gen = emu_lib(x, n_mels, fb=fb, window=window, log=log)
+        y_dir = emu_lib(x, n_mels, fb=fb, window=window, log=log, static_mel=mode)
+        if log:   # log domain: a few float32 ulp of values <= ~12
+            assert np.abs(y_dir - y_gen).max() <= 2e-6
+        else:
+            assert np.all(np.abs(y_dir - y_gen) <= 4e-6 * np.abs(y_gen))
+        assert np.all(y_dir[..., empty] == 0.0)
+        if not x.any():
+            assert np.all(y_dir == 0.0)
+        ref = mel_oracle.mel_forward(x, fb=fb, window=window, log_scale=log, dtype=np.float64)
+        err = np.abs(y_dir - ref).max() if log else np.abs(np.log1p(y_dir.astype(np.float64)) - np.log1p(ref)).max()
+        assert err < 2e-5

@@ -73,7 +73,9 @@ def test_golden_fixtures(mods, dev, name):
 @pytest.mark.parametrize("pset,shape", [("P0", (3, 40000)), ("P0", (2, 524160)), ("P0", (5, 513)), ("P0C", (2, 100)),
                                         ("P1", (2, 30000)), ("T5", (1, 20000)), ("P128", (3, 9999))])
 def test_kernel_variants_are_bit_identical(mods, dev, pset, shape):
-    """The independent-warps schedule (default) and the barrier schedule run the same arithmetic."""
+    """The three schedules (barrier, independent warps, warp-specialised with the generic or P0's hybrid
+    mel stage) run the same arithmetic bit for bit; the warp-specialised kernel's direct mel stages
+    (P128 / P1 / T5 by default) sum in a different order and stay within a few ulp."""
     m = mods[pset]
     x = signals.noise(shape[0], shape[1], 77 + shape[1])
     m.set_kernel_variant("barrier")
@@ -81,10 +83,19 @@ def test_kernel_variants_are_bit_identical(mods, dev, pset, shape):
     m.set_kernel_variant("warp")
     y_iw = run(m, x, dev)
     m.set_kernel_variant("ws")
+    y_ws_default = run(m, x, dev)
+    m.set_static_mel(False)
     y_ws = run(m, x, dev)
+    m.set_static_mel(True)
     m.set_kernel_variant(DEFAULT_VARIANT)
     assert np.array_equal(y_iw, y_bar)
     assert np.array_equal(y_ws, y_bar)
+    if pset in ("P0", "P0C"):
+        assert np.array_equal(y_ws_default, y_bar)
+    elif PSET_ARGS[pset][0]:
+        assert np.abs(y_ws_default - y_bar).max() <= 2e-6
+    else:
+        assert np.all(np.abs(y_ws_default - y_bar) <= 4e-6 * np.abs(y_bar))
     log, n_mels, f_min, f_max, pad = PSET_ARGS[pset]
     window, fb = load_params(pset)
     ref = mel_oracle.mel_forward(x, fb=fb, window=window, pad_mode=pad, log_scale=log, dtype=np.float64)
@@ -116,6 +127,66 @@ def test_static_mel_stage_is_bit_identical_to_generic(dev, log, shape):
     y2 = run(m, x, dev)
     ref2 = mel_oracle.mel_forward(x, fb=fb2, window=window, pad_mode="reflect", log_scale=log, dtype=np.float64)
     assert parity_error(y2, ref2, log) < TARGET
+
+
+@pytest.mark.parametrize("pset,args", [
+    ("P128", ("torchaudio", True, 16000, 1024, 128, 128, 20, 8000, "reflect")),
+    ("P1", ("torchaudio", False, 16000, 1024, 388, 128, 0, 8000, "constant")),
+    ("T5", ("torchaudio", False, 16000, 1024, 512, 128, 0, 8000, "constant")),
+    ("T5log", ("torchaudio", True, 16000, 1024, 512, 128, 0, 8000, "reflect")),
+])
+@pytest.mark.parametrize("shape", [(1, 513), (3, 40000), (2, 262016)])
+def test_direct_mel_stages_agree_with_generic_and_oracle(dev, pset, args, shape):
+    """The other reference filterbanks (128 / 388 / 512 mels) are recognised too and take their direct
+    generated stage (one or two chains per filter, vector stores from registers).  Against the generic
+    stage: a few ulp of the linear mel value, all-zero filters (20 of P1's, 54 of T5's) exactly 0; the
+    result meets the oracle; bfloat16 / pitched output and an unaligned output (falls back to the
+    generic stage) behave like forward + cast."""
+    from beatheritage_b200 import MelSpectrogram
+    m = MelSpectrogram(*args).to(dev)
+    x = signals.noise(shape[0], shape[1], 11 + shape[1])
+    y_static = run(m, x, dev)
+    m.set_static_mel(False)
+    y_generic = run(m, x, dev)
+    m.set_static_mel(True)
+    log = args[1]
+    if log:   # log domain: a few float32 ulp of values <= ~12
+        assert np.abs(y_static - y_generic).max() <= 2e-6
+    else:
+        assert np.all(np.abs(y_static - y_generic) <= 4e-6 * np.abs(y_generic))
+    window, fb = load_params(pset.replace("log", ""))
+    ref = mel_oracle.mel_forward(x, fb=fb, window=window, pad_mode=args[8], log_scale=log, dtype=np.float64)
+    assert parity_error(y_static, ref, log) < TARGET
+    empty = np.flatnonzero(~(fb != 0).any(axis=0))
+    assert np.all(y_static[..., empty] == 0.0)
+    # typed / pitched output through the direct stores: [B, T, n_mels + 8] bf16, mel channels first
+    xt = torch.from_numpy(x).to(dev)
+    T, M = x.shape[1] // 128 + 1, fb.shape[1]
+    wide = torch.full((x.shape[0], T, M + 8), 7.0, dtype=torch.bfloat16, device=dev)
+    m.forward_into(xt, wide)
+    torch.cuda.synchronize()
+    assert torch.equal(wide[..., :M].cpu(), torch.from_numpy(y_static).to(torch.bfloat16))
+    assert bool((wide[..., M:] == 7.0).all())
+    # channel offset 2: rows are no longer 8-byte aligned -> generic stage, same values as its float32 run
+    wide2 = torch.zeros((x.shape[0], T, M + 8), dtype=torch.bfloat16, device=dev)
+    m.forward_into(xt, wide2, channel_offset=2)
+    torch.cuda.synchronize()
+    assert torch.equal(wide2[..., 2:M + 2].cpu(), torch.from_numpy(y_generic).to(torch.bfloat16))
+
+
+def test_p0_direct_form_on_request(dev):
+    """BHMEL_OPT_STATIC_MEL = 2: P0 through its direct form (A/B runs): same tolerance, silence exactly 0."""
+    from beatheritage_b200 import MelSpectrogram
+    m = MelSpectrogram("torchaudio", True, 16000, 1024, 80, 128, 20, 8000, "reflect").to(dev)
+    x = signals.noise(3, 70000, 21)
+    y_hybrid = run(m, x, dev)
+    m.set_static_mel(2)
+    y_direct = run(m, x, dev)
+    window, fb = load_params("P0")
+    ref = mel_oracle.mel_forward(x, fb=fb, window=window, dtype=np.float64)
+    assert parity_error(y_direct, ref, True) < TARGET
+    assert np.abs(y_direct - y_hybrid).max() < 2e-6
+    assert np.all(run(m, np.zeros((1, 4096), np.float32), dev) == 0.0)
 
 
 @pytest.mark.parametrize("offset", [0, 1, 2, 3])

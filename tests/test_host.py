@@ -167,21 +167,48 @@ def test_shard_range_partitions_everything_once():
         seg.shard_range(10, 4, 4)
 
 
-def test_baked_filterbank_header_is_the_reference_p0_table():
-    """csrc/bhmel_fb_baked.h (committed; selects the statically scheduled mel stage at run time and feeds
-    its code generator) holds exactly the non-zeros of the reference's P0 `mel_scale.fb` buffer."""
+def _baked_tables():
+    """name -> dense uint32 [513, n_mels] table restated from csrc/bhmel_fb_baked.h (start / count / bits)."""
     import os
     import re
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     txt = open(os.path.join(root, "beatheritage_b200", "csrc", "bhmel_fb_baked.h")).read()
-    t = np.zeros((513, 80), np.uint32)
-    ent = re.findall(r"\{(\d+), (\d+), 0x([0-9a-f]+)u\}", txt)
-    assert len(ent) == int(re.search(r"kBakedP0Nnz = (\d+)", txt).group(1)) == 1003
-    for k, m, bits in ent:
-        t[int(k), int(m)] = int(bits, 16)
-    _, fb = load_params("P0")
-    assert np.array_equal(t, fb.view(np.uint32))
-    assert np.array_equal(t, melscale_fbanks_htk(513, 20.0, 8000.0, 80, 16000).numpy().view(np.uint32))
+
+    def arr(kind, name):
+        body = re.search(rf"kBaked{name}{kind}\[\] = \{{(.*?)\}};", txt, re.S).group(1)
+        return [int(v.rstrip("u"), 0) for v in body.replace("\n", " ").split(",") if v.strip()]
+
+    out = {}
+    for name, ident in re.findall(r'\{"(\w+)", (\d+), kBaked', txt):
+        n_mels = int(re.search(rf"kBaked{name}Mels = (\d+)", txt).group(1))
+        start, count, bits = arr("Start", name), arr("Count", name), arr("Bits", name)
+        assert len(bits) == int(re.search(rf"kBaked{name}Nnz = (\d+)", txt).group(1)) == sum(count)
+        t = np.zeros((513, n_mels), np.uint32)
+        pos = 0
+        for m in range(n_mels):
+            for j in range(count[m]):
+                t[start[m] + j, m] = bits[pos]
+                pos += 1
+        out[name] = (int(ident), t)
+    return out
+
+
+def test_baked_filterbank_header_holds_the_reference_tables():
+    """csrc/bhmel_fb_baked.h (committed; selects the statically scheduled mel stage at run time and feeds
+    its code generator) holds exactly the reference's `mel_scale.fb` buffers of every parameter set its
+    configs use (the golden `params_*.npz` come from the unmodified reference module)."""
+    tables = _baked_tables()
+    assert {k: v[0] for k, v in tables.items()} == {"P0": 1, "P128": 2, "P1": 3, "T5": 4}
+    ctor = {"P0": (20.0, 80), "P128": (20.0, 128), "P1": (0.0, 388), "T5": (0.0, 512)}
+    for name, (_, t) in tables.items():
+        _, fb = load_params(name)
+        ref_bits = fb.view(np.uint32).copy()
+        ref_bits[fb == 0] = 0          # the reference's P1 / T5 tables carry one negative zero (fb[0, 0] = -0.0)
+        assert np.array_equal(t, ref_bits), name
+        f_min, n_mels = ctor[name]
+        mine = melscale_fbanks_htk(513, f_min, 8000.0, n_mels, 16000).numpy()
+        assert np.array_equal(mine.view(np.uint32), fb.view(np.uint32))      # the host mirror keeps even that bit
+    assert int((tables["P0"][1] != 0).sum()) == 1003
 
 
 def test_static_mel_generator_covers_each_weight_once(tmp_path):
@@ -197,11 +224,30 @@ def test_static_mel_generator_covers_each_weight_once(tmp_path):
     n_static = int(re.search(r"kStaticP0Filters = (\d+)", txt).group(1))
     n_warps = int(re.search(r"kStaticP0Warps = (\d+)", txt).group(1))
     assert 0 < n_static < 80 and 0 < n_warps < 8
-    _, fb = load_params("P0")
-    want = sorted(int(b) for b in fb[:, :n_static].view(np.uint32)[fb[:, :n_static] != 0])
-    got = sorted(int(h, 16) for h in re.findall(r"__uint_as_float\(0x([0-9a-f]+)u\)", txt))
-    assert got == want                                    # every non-zero weight of the static filters, once
-    assert sorted(int(f) for f in re.findall(r"orow\[(\d+)\] = ", txt)) == list(range(n_static))
+    tables = _baked_tables()
+    for name, (_, t) in tables.items():
+        fb = t.view(np.float32)
+        n_mels = fb.shape[1]
+        all_bits = sorted(int(b) for b in t[fb != 0])
+        # direct form (every set): every non-zero weight once, every aligned group of four filters stored once
+        body = re.search(rf"void mel_direct_{name}\(.*?\n}}\n", txt, re.S).group(0)
+        assert sorted(int(h, 16) for h in re.findall(r"__uint_as_float\(0x([0-9a-f]+)u\)", body)) == all_bits, name
+        staged = re.findall(r"mel_stage4\(srow, (\d+), v(\d+), v(\d+), v(\d+), v(\d+)\);", body)
+        assert sorted(int(g[1]) for g in staged) == list(range(0, n_mels, 4))            # every aligned group of four, once
+        assert all([int(g[1]) + j for j in range(4)] == [int(v) for v in g[1:]] and int(g[0]) % 4 == 0 and int(g[0]) < 32
+                   for g in staged)
+        runs = re.search(rf"kRun{name}\[\d+\]\[2\] = \{{(.*?)\}};", txt).group(1)
+        runs = [(int(a), int(b)) for a, b in re.findall(r"\{(\d+), (\d+)\}", runs)]
+        assert sorted(m for m0, n in runs for m in range(m0, m0 + n)) == list(range(n_mels))   # parts tile the filters
+        assert all(n <= 32 and n % 4 == 0 and m0 % 4 == 0 for m0, n in runs)
+        assert len(re.findall(r"const float v\d+ = ", body)) == n_mels
+    # P0's hybrid form: the static warps cover every non-zero weight of filters below n_static once
+    body = re.search(r"void mel_static_P0\(.*?\n}\n", txt, re.S).group(0)
+    t = tables["P0"][1]
+    fb = t.view(np.float32)
+    want = sorted(int(b) for b in t[:, :n_static][fb[:, :n_static] != 0])
+    assert sorted(int(h, 16) for h in re.findall(r"__uint_as_float\(0x([0-9a-f]+)u\)", body)) == want
+    assert sorted(int(c) for c in re.findall(r"orow\[(\d+)\] = ", body)) == list(range(n_static))
 
 
 # ---------------------------------------------------------------------------------------------
