@@ -167,3 +167,45 @@ def test_gelu_is_checked_for_every_bf16_input(dev):
     assert int(differs.sum()) <= 64
     # the CPU model of the same formula agrees with the GPU up to the MUFU approximations
     assert int((got != model).sum()) <= 64 and float((got - model).abs().max()) <= 1e-5
+
+
+def test_c5_slice_song_to_stem_output_matches_the_reference_op_chain(dev):
+    """C5 as a parity test, not only a measurement: one model-context window of a
+    music-like song through  OUR frontend -> fused encoder-input assembly (80 mel + 384 conditioning
+    channels, channels last, bf16) -> tcgen05 conv stem  against the REFERENCE's op chain on the same
+    GPU: torchaudio MelSpectrogram + log1p + permute (spectrogram.py:38-49, 79-82), .to(bf16), expand +
+    cat of the conditioning channels, swapaxes (modeling_mapperatorinator.py:351-376), then
+    gelu(conv1) / gelu(conv2) / permute with torch's bf16 Conv1d (modeling_ropewhisper.py:1206-1209)."""
+    torchaudio = pytest.importorskip("torchaudio")
+    from beatheritage_b200 import MelSpectrogram
+    from tests.golden import signals
+    mel = MelSpectrogram("torchaudio", True, 16000, 1024, 80, 128, 20, 8000, "reflect").to(dev)
+    ta = torchaudio.transforms.MelSpectrogram(sample_rate=16000, n_fft=1024, n_mels=80, hop_length=128, center=True,
+                                              f_min=20, f_max=8000, pad_mode="reflect").to(dev)
+    stem = make_stem(464, 768, dev, seed=5)
+    x = torch.from_numpy(signals.music(2 * 524160, seed=9).reshape(2, 524160)).to(dev)
+    torch.manual_seed(1)
+    cond = torch.randn(2, 384, device=dev)
+    with torch.no_grad():
+        # reference chain
+        frames = torch.log1p(ta(x)).permute(0, 2, 1)                                   # spectrogram.py:79-82
+        frames = frames.to(torch.bfloat16)                                             # :352
+        emb = torch.cat([frames, cond.to(torch.bfloat16).unsqueeze(1).expand(-1, frames.shape[1], -1)], dim=-1)
+        ref_in = emb.swapaxes(1, 2)                                                    # :375-376  [B, 464, T]
+        conv1 = stem.conv1.to(torch.bfloat16)
+        conv2 = stem.conv2.to(torch.bfloat16)
+        want = torch.nn.functional.gelu(conv2(torch.nn.functional.gelu(conv1(ref_in)))).permute(0, 2, 1)
+        conv1.float(), conv2.float()
+        # ours
+        enc_in = mel.forward_encoder_input(x, [cond], dtype=torch.bfloat16, channels_first=False)
+        got = stem(enc_in)
+    torch.cuda.synchronize()
+    # the two front ends differ by ~1e-6 before the bf16 rounding, so a handful of mel values round the
+    # other way; everything downstream is the stem's own tolerance
+    mel_diff = (enc_in[..., :80].float() - frames.float()).abs()
+    assert float(mel_diff.max()) <= 2.0 ** -7 * float(frames.float().abs().max())      # at most one bf16 ulp
+    assert float((mel_diff > 0).float().mean()) < 0.01
+    assert torch.equal(enc_in[..., 80:], emb[..., 80:])
+    # (a flipped mel value reaches 3 x 768 hidden values and every output under them, so most outputs move
+    # by an fp32 hair and many bf16 roundings flip: only the magnitude bound is meaningful here)
+    assert_close(got, want, "song -> stem output (C5 slice)", max_frac=1.01)

@@ -66,25 +66,35 @@ def algo_bytes(n_in_samples, n_windows):
     return 4 * n_in_samples + 4 * n_windows * (WINDOW // HOP + 1) * M
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r1_configs.json"))
-    ap.add_argument("--skip-c5", action="store_true")
-    args = ap.parse_args()
-    res = {"gpu": torch.cuda.get_device_name(0), "torch": torch.__version__}
-    mel = MelSpectrogram(*P0).to(dev)
-    try:
-        ta = TorchaudioGpu().to(dev)
-    except Exception as e:   # torchaudio missing
-        ta = None
-        res["torchaudio_gpu"] = f"unavailable: {e}"
+class Ctx:
+    """Modules and inputs shared by the per-config functions (built lazily)."""
 
-    def materialise(song_t, plan):
-        """What Preprocessor.segment builds on the host: zero-pad to plan.padded_len, strided windows."""
-        sp = torch.nn.functional.pad(song_t, (0, plan.padded_len - song_t.numel()))
-        return sp.as_strided((plan.n_windows, plan.window_len), (plan.stride, 1)).contiguous()
+    def __init__(self):
+        self.mel = MelSpectrogram(*P0).to(dev)
+        try:
+            self.ta = TorchaudioGpu().to(dev)
+            self.ta_error = None
+        except Exception as e:   # torchaudio missing
+            self.ta, self.ta_error = None, str(e)
+        self._song = None
 
-    # ------------------------------------------------------------------ C1
+    @property
+    def song(self):
+        if self._song is None:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from tests.golden import signals
+            self._song = signals.music(2_880_000, seed=1)
+        return self._song
+
+
+def materialise(song_t, plan):
+    """What Preprocessor.segment builds on the host: zero-pad to plan.padded_len, strided windows."""
+    sp = torch.nn.functional.pad(song_t, (0, plan.padded_len - song_t.numel()))
+    return sp.as_strided((plan.n_windows, plan.window_len), (plan.stride, 1)).contiguous()
+
+
+def run_c1(ctx):
+    mel, ta = ctx.mel, ctx.ta
     g = torch.Generator().manual_seed(0)
     x1 = torch.rand(1, 160000, generator=g) * 2 - 1
     x1d = x1.to(dev)
@@ -92,12 +102,14 @@ def main():
     if ta is not None:
         c1["torchaudio_gpu_us"] = 1e3 * timed(lambda: ta(x1d), 200)
         c1["max_abs_diff_vs_torchaudio_gpu"] = float((mel(x1d) - ta(x1d)).abs().max())
-    res["C1_clip_10s"] = c1
 
-    # ------------------------------------------------------------------ C2
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from tests.golden import signals
-    song = signals.music(2_880_000, seed=1)
+
+    return c1
+
+
+def run_c2(ctx):
+    mel, ta = ctx.mel, ctx.ta
+    song = ctx.song
     song_d = torch.from_numpy(song).to(dev)
     c2 = {}
     for name, parallel in (("sequential_46", False), ("parallel_6", True)):
@@ -112,9 +124,13 @@ def main():
         if ta is not None:
             entry["torchaudio_gpu_ms"] = timed(lambda: ta(seq), 20)
         c2[name] = entry
-    res["C2_song_3min"] = c2
 
-    # ------------------------------------------------------------------ C4
+
+    return c2
+
+
+def run_c4(ctx):
+    mel, ta = ctx.mel, ctx.ta
     n_hour = 57_600_000
     gd = torch.Generator(device=dev).manual_seed(2)
     hour = torch.rand(n_hour, device=dev, generator=gd).mul_(2).sub_(1)
@@ -144,105 +160,126 @@ def main():
                                           "algorithmic_GBps": algo_bytes(b * WINDOW, b) / (ms / 1e3) / 1e9})
         del batch, hp
         c4["stride_sweep"].append(entry)
-    res["C4_one_hour_stream"] = c4
     del hour
     torch.cuda.empty_cache()
 
-    # ------------------------------------------------------------------ C5
+
+    return c4
+
+
+def run_c5(ctx):
+    mel, ta = ctx.mel, ctx.ta
+    song = ctx.song
+    song_d = torch.from_numpy(song).to(dev)
+    try:
+        from transformers import WhisperConfig
+        from transformers.models.whisper.modeling_whisper import WhisperEncoder
+        torch.manual_seed(0)
+        cfg = WhisperConfig(d_model=768, encoder_layers=12, encoder_attention_heads=12, encoder_ffn_dim=3072,
+                            num_mel_bins=M + 384, max_source_positions=2048)
+        enc = WhisperEncoder(cfg).to(dev).to(torch.bfloat16).eval()
+        plan = segment_plan(len(song))
+        seq_host = materialise(song_d, plan).cpu().pin_memory()
+        cond = torch.randn(1, 1, 384, device=dev, dtype=torch.bfloat16)
+
+        def run(frontend, batch, fused=False):
+            """fused=True: mel + conditioning channels + channels-first layout in one library call
+            (forward_encoder_input); the 'frontend' time then includes the assembly."""
+            t_front = t_total = 0.0
+            for i in range(0, seq_host.shape[0], batch):
+                xb = seq_host[i:i + batch]
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                xd = xb.to(dev, non_blocking=True)                    # server.py:42
+                if fused:
+                    fr = frontend.forward_encoder_input(xd, [cond[:, 0].expand(xd.shape[0], -1)], channels_first=True)
+                else:
+                    fr = frontend(xd)                                 # modeling_mapperatorinator.py:351
+                torch.cuda.synchronize()
+                t1 = time.perf_counter()
+                if not fused:
+                    fr = fr.to(torch.bfloat16)                        # :352
+                    fr = torch.cat([fr, cond.expand(fr.shape[0], fr.shape[1], -1)], dim=-1)   # :369-370
+                    fr = fr.swapaxes(1, 2)                            # :375-376
+                with torch.no_grad():
+                    enc(fr)                                           # encoder
+                torch.cuda.synchronize()
+                t2 = time.perf_counter()
+                t_front += t1 - t0
+                t_total += t2 - t0
+            return t_front, t_total
+
+        c5 = {"encoder": "HF WhisperEncoder random init, d_model 768, 12 layers, 464 input channels, bf16",
+              "windows": int(seq_host.shape[0])}
+        fronts = {"ours": mel}
+        if ta is not None:
+            fronts["torchaudio_gpu"] = ta
+        with torch.no_grad():
+            for fname, f in fronts.items():
+                for mode, batch in (("sequential_b1", 1), ("parallel_b6", 6)):
+                    run(f, batch)
+                    tf, tt = run(f, batch)
+                    c5[f"{fname}_{mode}"] = {"frontend_ms_incl_h2d": 1e3 * tf, "total_ms": 1e3 * tt,
+                                             "frontend_share": tf / tt}
+            for mode, batch in (("sequential_b1", 1), ("parallel_b6", 6)):
+                run(mel, batch, fused=True)
+                tf, tt = run(mel, batch, fused=True)
+                c5[f"ours_fused_encoder_input_{mode}"] = {"frontend_plus_assembly_ms_incl_h2d": 1e3 * tf,
+                                                          "total_ms": 1e3 * tt, "frontend_share": tf / tt}
+        # N3: the encoder's conv stem (modeling_ropewhisper.py:1206-1209 / the stock encoder's first lines)
+        # behind the frontend: reference ops end to end vs forward_encoder_input (channels last) + ConvStem
+        from beatheritage_b200.conv_stem import ConvStem
+        stem = ConvStem.from_encoder(enc)
+        gelu = torch.nn.functional.gelu
+        stem_res = {}
+        with torch.no_grad():
+            for mode, batch in (("sequential_b1", 1), ("parallel_b6", 6)):
+                xd = seq_host[:batch].to(dev)
+                cvec = cond[:, 0].expand(batch, -1)
+
+                def ref_ops():
+                    fr = mel(xd).to(torch.bfloat16)
+                    fr = torch.cat([fr, cond.expand(batch, fr.shape[1], -1)], dim=-1).swapaxes(1, 2)
+                    return gelu(enc.conv2(gelu(enc.conv1(fr)))).permute(0, 2, 1)
+
+                def ref_stem_only(fr_bct):
+                    return gelu(enc.conv2(gelu(enc.conv1(fr_bct)))).permute(0, 2, 1)
+
+                def ours():
+                    return stem(mel.forward_encoder_input(xd, [cvec], channels_first=False))
+
+                fr_btc = mel.forward_encoder_input(xd, [cvec], channels_first=False)
+                fr_bct = fr_btc.swapaxes(1, 2).contiguous()
+                a, b = ref_ops().float(), ours().float()
+                stem_res[mode] = {
+                    "reference_ops_frontend_to_stem_ms": timed(ref_ops, 20),
+                    "ours_frontend_to_stem_ms": timed(ours, 20),
+                    "stem_only_torch_cudnn_ms": timed(lambda: ref_stem_only(fr_bct), 20),
+                    "stem_only_ours_ms": timed(lambda: stem(fr_btc), 20),
+                    "max_abs_diff": float((a - b).abs().max()),
+                    "max_abs_value": float(a.abs().max()),
+                }
+        c5["conv_stem_N3"] = stem_res
+        return c5
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r2_configs.json"))
+    ap.add_argument("--skip-c5", action="store_true")
+    args = ap.parse_args()
+    res = {"gpu": torch.cuda.get_device_name(0), "torch": torch.__version__}
+    ctx = Ctx()
+    if ctx.ta is None:
+        res["torchaudio_gpu"] = f"unavailable: {ctx.ta_error}"
+    res["C1_clip_10s"] = run_c1(ctx)
+    res["C2_song_3min"] = run_c2(ctx)
+    res["C4_one_hour_stream"] = run_c4(ctx)
     if not args.skip_c5:
-        try:
-            from transformers import WhisperConfig
-            from transformers.models.whisper.modeling_whisper import WhisperEncoder
-            torch.manual_seed(0)
-            cfg = WhisperConfig(d_model=768, encoder_layers=12, encoder_attention_heads=12, encoder_ffn_dim=3072,
-                                num_mel_bins=M + 384, max_source_positions=2048)
-            enc = WhisperEncoder(cfg).to(dev).to(torch.bfloat16).eval()
-            plan = segment_plan(len(song))
-            seq_host = materialise(song_d, plan).cpu().pin_memory()
-            cond = torch.randn(1, 1, 384, device=dev, dtype=torch.bfloat16)
-
-            def run(frontend, batch, fused=False):
-                """fused=True: mel + conditioning channels + channels-first layout in one library call
-                (forward_encoder_input); the 'frontend' time then includes the assembly."""
-                t_front = t_total = 0.0
-                for i in range(0, seq_host.shape[0], batch):
-                    xb = seq_host[i:i + batch]
-                    torch.cuda.synchronize()
-                    t0 = time.perf_counter()
-                    xd = xb.to(dev, non_blocking=True)                    # server.py:42
-                    if fused:
-                        fr = frontend.forward_encoder_input(xd, [cond[:, 0].expand(xd.shape[0], -1)], channels_first=True)
-                    else:
-                        fr = frontend(xd)                                 # modeling_mapperatorinator.py:351
-                    torch.cuda.synchronize()
-                    t1 = time.perf_counter()
-                    if not fused:
-                        fr = fr.to(torch.bfloat16)                        # :352
-                        fr = torch.cat([fr, cond.expand(fr.shape[0], fr.shape[1], -1)], dim=-1)   # :369-370
-                        fr = fr.swapaxes(1, 2)                            # :375-376
-                    with torch.no_grad():
-                        enc(fr)                                           # encoder
-                    torch.cuda.synchronize()
-                    t2 = time.perf_counter()
-                    t_front += t1 - t0
-                    t_total += t2 - t0
-                return t_front, t_total
-
-            c5 = {"encoder": "HF WhisperEncoder random init, d_model 768, 12 layers, 464 input channels, bf16",
-                  "windows": int(seq_host.shape[0])}
-            fronts = {"ours": mel}
-            if ta is not None:
-                fronts["torchaudio_gpu"] = ta
-            with torch.no_grad():
-                for fname, f in fronts.items():
-                    for mode, batch in (("sequential_b1", 1), ("parallel_b6", 6)):
-                        run(f, batch)
-                        tf, tt = run(f, batch)
-                        c5[f"{fname}_{mode}"] = {"frontend_ms_incl_h2d": 1e3 * tf, "total_ms": 1e3 * tt,
-                                                 "frontend_share": tf / tt}
-                for mode, batch in (("sequential_b1", 1), ("parallel_b6", 6)):
-                    run(mel, batch, fused=True)
-                    tf, tt = run(mel, batch, fused=True)
-                    c5[f"ours_fused_encoder_input_{mode}"] = {"frontend_plus_assembly_ms_incl_h2d": 1e3 * tf,
-                                                              "total_ms": 1e3 * tt, "frontend_share": tf / tt}
-            # N3: the encoder's conv stem (modeling_ropewhisper.py:1206-1209 / the stock encoder's first lines)
-            # behind the frontend: reference ops end to end vs forward_encoder_input (channels last) + ConvStem
-            from beatheritage_b200.conv_stem import ConvStem
-            stem = ConvStem.from_encoder(enc)
-            gelu = torch.nn.functional.gelu
-            stem_res = {}
-            with torch.no_grad():
-                for mode, batch in (("sequential_b1", 1), ("parallel_b6", 6)):
-                    xd = seq_host[:batch].to(dev)
-                    cvec = cond[:, 0].expand(batch, -1)
-
-                    def ref_ops():
-                        fr = mel(xd).to(torch.bfloat16)
-                        fr = torch.cat([fr, cond.expand(batch, fr.shape[1], -1)], dim=-1).swapaxes(1, 2)
-                        return gelu(enc.conv2(gelu(enc.conv1(fr)))).permute(0, 2, 1)
-
-                    def ref_stem_only(fr_bct):
-                        return gelu(enc.conv2(gelu(enc.conv1(fr_bct)))).permute(0, 2, 1)
-
-                    def ours():
-                        return stem(mel.forward_encoder_input(xd, [cvec], channels_first=False))
-
-                    fr_btc = mel.forward_encoder_input(xd, [cvec], channels_first=False)
-                    fr_bct = fr_btc.swapaxes(1, 2).contiguous()
-                    a, b = ref_ops().float(), ours().float()
-                    stem_res[mode] = {
-                        "reference_ops_frontend_to_stem_ms": timed(ref_ops, 20),
-                        "ours_frontend_to_stem_ms": timed(ours, 20),
-                        "stem_only_torch_cudnn_ms": timed(lambda: ref_stem_only(fr_bct), 20),
-                        "stem_only_ours_ms": timed(lambda: stem(fr_btc), 20),
-                        "max_abs_diff": float((a - b).abs().max()),
-                        "max_abs_value": float(a.abs().max()),
-                    }
-            c5["conv_stem_N3"] = stem_res
-            res["C5_inference_slice"] = c5
-        except Exception as e:
-            res["C5_inference_slice"] = {"unavailable": f"{type(e).__name__}: {e}"}
-
+        res["C5_inference_slice"] = run_c5(ctx)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump(res, open(args.out, "w"), indent=1)
     print(json.dumps(res, indent=1))
