@@ -16,6 +16,7 @@
 #include "bhmel_kernel_iw.cuh"
 #include "bhmel_kernel_ws.cuh"
 
+
 namespace {
 
 thread_local std::string g_err;
@@ -318,6 +319,7 @@ int launch(bhmel_handle* h, const float* x, long long row_stride, long long row0
   p.y_frame_pitch = out.frame_pitch > 0 ? out.frame_pitch : h->prm.n_mels;
   p.y_row_pitch = out.row_pitch > 0 ? out.row_pitch : p.T * p.y_frame_pitch;
   p.y_bf16 = out.bf16;
+  p.y_limit = (B - 1) * p.y_row_pitch + (p.T - 1) * p.y_frame_pitch + h->prm.n_mels;
   if (p.y_frame_pitch < h->prm.n_mels || p.y_row_pitch < p.T * p.y_frame_pitch)
     return fail(BHMEL_EINVAL, "output pitches too small for [T][n_mels]");
   p.win_half = h->d_win;
@@ -352,7 +354,7 @@ int launch(bhmel_handle* h, const float* x, long long row_stride, long long row0
     // output rows must be 16-byte (float32) / 8-byte (bfloat16) aligned, else the generic stage runs).
     int st = h->static_mel ? h->baked_fb : 0;
     if (st == 1 && h->static_mel == 2) st = bhmel::kStaticP0Direct;
-    if (st >= 2) {
+    if (st >= 2) {   // direct forms store vectors
       const uintptr_t align = out.bf16 ? 8 : 16;
       const bool ok = (reinterpret_cast<uintptr_t>(y) % align) == 0 && p.y_frame_pitch % 4 == 0 && p.y_row_pitch % 4 == 0;
       if (!ok) st = st == bhmel::kStaticP0Direct ? 1 : 0;

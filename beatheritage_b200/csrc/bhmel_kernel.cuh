@@ -33,6 +33,24 @@
 #endif
 #include "fft32_gen.h"
 
+// -DBHMEL_BOUNDS (debug library libbhmel_bounds.so, built by beatheritage_b200.build and exercised by
+// tests/test_gpu_bounds.py): every shared- and global-memory index of the staging, transpose, power-buffer,
+// mel and store paths is asserted; a violation prints the expression and traps (compute-sanitizer is
+// closed on the GPU pool this was developed on).  Compiled out of the shipped library.
+#ifdef BHMEL_BOUNDS
+#include <cstdio>
+#define BH_CHECK(cond)                                                                                          \
+  do {                                                                                                          \
+    if (!(cond)) {                                                                                              \
+      printf("BHMEL_BOUNDS violated: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__,            \
+             static_cast<int>(blockIdx.x), static_cast<int>(threadIdx.x));                                     \
+      __trap();                                                                                                 \
+    }                                                                                                           \
+  } while (0)
+#else
+#define BH_CHECK(cond) do {} while (0)
+#endif
+
 namespace bhmel {
 
 constexpr int kTileF = 32;                                // frames per tile
@@ -82,6 +100,7 @@ struct KParams {
   int n_weights;           // floats in `weights` (multiple of 8)
   int n_pairs;
   int y_bf16;              // 0: float32 output, 1: bfloat16 (round to nearest even)
+  long long y_limit;       // one past the largest output element index the call may write (BH_CHECK only)
 };
 
 // Output element store: float32 or bfloat16, any frame / row pitch (N1: writes the mel channels
@@ -126,6 +145,34 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t 
 // branch and reconverges the warp afterwards.
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// Waiting for a barrier that is expected to take a while (the mel role waiting for the FFT role's next
+// tile): every poll is an issue slot taken from the warps that do the work -- ncu showed 28 % of the
+// kernel's executed instructions in these loops -- so the poll carries a suspend-time hint (the warp is
+// parked in hardware until the phase completes or the time is up) and backs off with nanosleep.
+#ifndef BHMEL_IDLE_HINT_NS
+#define BHMEL_IDLE_HINT_NS 20000
+#endif
+#ifndef BHMEL_IDLE_SLEEP_NS
+#define BHMEL_IDLE_SLEEP_NS 0
+#endif
+__device__ __forceinline__ bool mbar_try_wait_hint(unsigned long long* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_idle(unsigned long long* bar, uint32_t parity) {
+  while (!mbar_try_wait_hint(bar, parity, BHMEL_IDLE_HINT_NS)) {
+    if (BHMEL_IDLE_SLEEP_NS > 0) __nanosleep(BHMEL_IDLE_SLEEP_NS);
   }
 }
 // TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
@@ -273,6 +320,8 @@ __device__ __forceinline__ void mel_chunk(const float4* __restrict__ prow, const
     const float4* wp = reinterpret_cast<const float4*>(wbase + d.y);
     const float4* pa = prow + (d.x & 0xFFFF);
     const float4* pb = prow + (static_cast<unsigned>(d.x) >> 16);
+    BH_CHECK(d.z >= 0 && (d.x & 0xFFFF) + d.z <= (kBins + 3) / 4 && (static_cast<unsigned>(d.x) >> 16) + d.z <= (kBins + 3) / 4);
+    BH_CHECK(d.y >= 0 && d.y % 4 == 0);
     float va, vb;
 #if defined(BHMEL_MEL_COMPACT)
     constexpr int kForm = 1;
@@ -306,6 +355,7 @@ __device__ __forceinline__ void mel_chunk(const float4* __restrict__ prow, const
       vb = fast_log1p(vb);
     }
     const int ca = d.w & 0xFFFF, cb = static_cast<unsigned>(d.w) >> 16;
+    BH_CHECK(ca < kMChunk && (cb == 0xFFFF || cb < kMChunk));
     orow[ca] = va;
     if (cb != 0xFFFF) orow[cb] = vb;
   }

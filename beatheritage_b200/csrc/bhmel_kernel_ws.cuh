@@ -30,22 +30,26 @@ namespace bhmel {
 constexpr int kStageCols = 32;
 constexpr int kStagePitch = kStageCols + 4;
 __device__ __forceinline__ void mel_stage4(float* __restrict__ srow, int col, float a, float b, float c, float d) {
+  BH_CHECK(col >= 0 && col % 4 == 0 && col + 4 <= kStageCols);
   *reinterpret_cast<float4*>(srow + col) = make_float4(a, b, c, d);
 }
 // Writes the first `ncols` (multiple of 4) columns of the warp's staging block to rows 0..nf-1 of the
 // tile: lane -> 16-byte column group lane & 7 of rows (lane >> 3) + 4 i, so one instruction moves four
 // row segments of up to 128 contiguous bytes.
-template <bool kBf16>
+template <bool kBf16, int kPitch = kStagePitch>
 __device__ __forceinline__ void mel_flush(const float* __restrict__ stage, void* __restrict__ ytile, long long fpitch,
-                                          int m0, int ncols, int nf, int lane) {
+                                          int m0, int ncols, int nf, int lane, long long y_room = 0) {
+  BH_CHECK(ncols % 4 == 0 && ncols + 4 <= kPitch && nf >= 1 && nf <= 32);
   __syncwarp();
   const int c = 4 * (lane & 7);
   if (c < ncols) {
-    const float* sp = stage + (lane >> 3) * kStagePitch + c;
+    const float* sp = stage + (lane >> 3) * kPitch + c;
     long long off = static_cast<long long>(lane >> 3) * fpitch + m0 + c;
 #pragma unroll
-    for (int i = 0; i < kTileF / 4; ++i, sp += 4 * kStagePitch, off += 4 * fpitch) {
+    for (int i = 0; i < kTileF / 4; ++i, sp += 4 * kPitch, off += 4 * fpitch) {
       if ((lane >> 3) + 4 * i < nf) {
+        BH_CHECK(off >= 0 && off + 4 <= y_room && (kBf16 ? (reinterpret_cast<uintptr_t>(static_cast<__nv_bfloat16*>(ytile) + off) & 7) == 0
+                                                          : (reinterpret_cast<uintptr_t>(static_cast<float*>(ytile) + off) & 15) == 0));
         const float4 v = *reinterpret_cast<const float4*>(sp);
         if constexpr (kBf16) {
           const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
@@ -61,6 +65,7 @@ __device__ __forceinline__ void mel_flush(const float* __restrict__ stage, void*
   }
   __syncwarp();
 }
+
 }  // namespace bhmel
 
 #include "mel_static_gen.h"
@@ -147,6 +152,8 @@ __device__ __forceinline__ void issue_span(const KParams& p, long long tile, flo
     if (mt == 0) {
       const uint32_t bytes = delta ? kSpanBytes + 16 : kSpanBytes;
       *delta_out = delta;
+      BH_CHECK(s0 - delta >= 0 && s0 - delta + bytes / 4 <= valid && bytes / 4 <= kSpan + 4);
+      BH_CHECK((reinterpret_cast<uintptr_t>(row + s0 - delta) & 15) == 0 && (smem_u32(dst) & 15) == 0);
       fence_proxy_async();
       mbar_expect_tx(bar, bytes);
       bulk_g2s(dst, row + s0 - delta, bytes, bar);
@@ -161,6 +168,7 @@ __device__ __forceinline__ void issue_span(const KParams& p, long long tile, flo
   }
   if (interior) {   // fully inside the row but not coverable by an aligned bulk copy: element copies
     const float* src = row + s0;
+    BH_CHECK(s0 >= 0 && s0 + kSpan <= valid);
     for (int e = mt; e < kSpan; e += kMelThreads) cp_async_4(dst + e, src + e, 4);
   } else {
     const long long N = p.N;
@@ -169,6 +177,7 @@ __device__ __forceinline__ void issue_span(const KParams& p, long long tile, flo
       if (i < 0) i = p.pad_reflect ? -i : -1;
       else if (i >= N) i = p.pad_reflect ? 2 * (N - 1) - i : -1;
       const bool ok = (i >= 0) && (i < valid);
+      BH_CHECK(!ok || (i < N && row_off + i < p.n_total));
       cp_async_4(dst + e, row + (ok ? i : 0), ok ? 4 : 0);
     }
   }
@@ -243,6 +252,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
         {
           float v[36];
           const float* sp = span_b + (2 * j) * kHop + lane;
+          BH_CHECK(S.span_delta[b] >= 0 && S.span_delta[b] <= 3 && (sp - S.span[b]) + 32 * 35 < kSpan + 4);
 #pragma unroll
           for (int m = 0; m < 36; ++m) v[m] = sp[32 * m];
           fft32_pass_a(v, wreg, ar, ai);
@@ -250,6 +260,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
         BHMEL_TR(1 + 5 * (j / kFftWarps));
         // transpose the real plane, then the imaginary plane, through the pair's own rows
         float ur[32], ui[32];
+        BH_CHECK((rows - S.P[b]) + 31 * kPlanePitch + 31 < kTileF * kPPitchW && 31 * kPlanePitch + 31 < 2 * kPPitchW);
 #pragma unroll
         for (int k = 0; k < 32; ++k) rows[k * kPlanePitch + lane] = ar[k];
         __syncwarp();
@@ -268,6 +279,8 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
         BHMEL_TR(3 + 5 * (j / kFftWarps));
         float* Pa = rows + lane;
         float* Pb = Pa + kPPitchW;
+        BH_CHECK((Pb - S.P[b]) + 32 * 15 < kTileF * kPPitchW && (lane != 0 || (Pb - S.P[b]) + 512 < kTileF * kPPitchW) &&
+                 kBins + 2 < kPPitchW);
 #pragma unroll
         for (int k2 = 0; k2 < 16; ++k2) {
           const int s = 31 - k2;
@@ -315,7 +328,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
       const int b = it & 1;
       const uint32_t ph = (it >> 1) & 1;
       BHMEL_TR(0);
-      mbar_wait(&S.p_full[b], ph);
+      mbar_wait_idle(&S.p_full[b], ph);
       BHMEL_TR(1);
       // every FFT warp is done with tile `it`, so span[b] is free: fetch the tile two steps ahead
       const long long tile2 = tile + 2 * static_cast<long long>(gridDim.x);
@@ -333,14 +346,19 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
         constexpr int kParts = mel_direct_parts<kStatic>();
 #pragma unroll 1
         for (int part = 0; part < kParts; ++part) {
+#ifdef BHMEL_DEBUG_ONE_BLOCK   // timing experiment (wrong results): every mel warp runs warp 0's code -> 1/8 of the footprint
+          mel_direct<kStatic, kLog>(prow, stage + lane * kStagePitch, 0, part);
+#else
           mel_direct<kStatic, kLog>(prow, stage + lane * kStagePitch, mw, part);
+#endif
           if (part == kParts - 1) {   // this warp no longer reads P[b]
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.p_empty[b]);
           }
           int m0, ncols;
           mel_direct_run<kStatic>(mw * kParts + part, m0, ncols);
-          mel_flush<kBf16>(stage, ytile, p.y_frame_pitch, m0, ncols, nf, lane);
+          BH_CHECK(m0 + ncols <= p.n_mels && (stage - S.mel_stage()) + kTileF * kStagePitch <= kMelWarps * kTileF * kStagePitch);
+          mel_flush<kBf16>(stage, ytile, p.y_frame_pitch, m0, ncols, nf, lane, p.y_limit - ybase);
         }
       } else {
 #ifdef BHMEL_DEBUG_SKIP_MEL
@@ -376,6 +394,13 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
             for (int bb = 0; bb < kCo; ++bb) vals[a][bb] = S.out[(mw + a * kMelWarps) * kOutPitch + lane + 32 * bb];
           const long long fpitch = p.y_frame_pitch;
           const long long y0 = ybase + static_cast<long long>(mw) * fpitch + mc + lane;
+          BH_CHECK((mw + (kFr - 1) * kMelWarps) * kOutPitch + lane + 32 * (kCo - 1) < kTileF * kOutPitch);
+#ifdef BHMEL_BOUNDS
+          for (int a = 0; a < kFr; ++a)
+            for (int bb = 0; bb < kCo; ++bb)
+              if (mw + a * kMelWarps < nf && lane + 32 * bb < mcount)
+                BH_CHECK(y0 + a * kMelWarps * fpitch + 32 * bb >= 0 && y0 + a * kMelWarps * fpitch + 32 * bb < p.y_limit);
+#endif
           if (!p.y_bf16) {
             float* yp = p.y + y0;
 #pragma unroll

@@ -45,6 +45,21 @@
 
 #include "../../include/bhstem.h"
 
+// -DBHSTEM_BOUNDS (debug library libbhstem_bounds.so; tests/test_gpu_bounds.py): asserts the epilogue's
+// TMEM columns, staging indices and output addresses, and the MMA role's shared-memory operand windows.
+#ifdef BHSTEM_BOUNDS
+#define BHS_CHECK(cond)                                                                                         \
+  do {                                                                                                          \
+    if (!(cond)) {                                                                                              \
+      printf("BHSTEM_BOUNDS violated: %s  (line %d, block %d thread %d)\n", #cond, __LINE__,                   \
+             static_cast<int>(blockIdx.x), static_cast<int>(threadIdx.x));                                     \
+      __trap();                                                                                                 \
+    }                                                                                                           \
+  } while (0)
+#else
+#define BHS_CHECK(cond) do {} while (0)
+#endif
+
 namespace {
 
 constexpr int BLOCK_M = 128;      // output rows (time steps) per tile = TMEM lanes
@@ -283,6 +298,7 @@ __device__ __forceinline__ void epilogue_role(const StemProblem& p, const float*
     for (int c = half * CHUNKS; c < (half + 1) * CHUNKS; ++c) {
       uint32_t r[32];
       __syncwarp();                                        // tcgen05.ld is warp-collective; staging reads of the last chunk are done
+      BHS_CHECK(as * BN + c * 32 + 32 <= 2 * BN && c * 32 + 32 <= BN && nt * BN + c * 32 + 32 <= p.n_out);
       tmem_ld32(taddr + c * 32, r);
       if (c == (half + 1) * CHUNKS - 1) {                  // everything is in registers: hand the stage back
         tc_fence_before();
@@ -304,6 +320,7 @@ __device__ __forceinline__ void epilogue_role(const StemProblem& p, const float*
         v.y = conv_gelu_pair(__uint_as_float(r[j + 2]) + b0.z, __uint_as_float(r[j + 3]) + b0.w);
         v.z = conv_gelu_pair(__uint_as_float(r[j + 4]) + b1.x, __uint_as_float(r[j + 5]) + b1.y);
         v.w = conv_gelu_pair(__uint_as_float(r[j + 6]) + b1.z, __uint_as_float(r[j + 7]) + b1.w);
+        BHS_CHECK(lane * 64 + (((j >> 3) ^ wr_swz) << 4) + 16 <= EPI_STAGE_BYTES);
         *reinterpret_cast<uint4*>(staging + lane * 64 + (((j >> 3) ^ wr_swz) << 4)) = v;
       }
       __syncwarp();
@@ -311,8 +328,12 @@ __device__ __forceinline__ void epilogue_role(const StemProblem& p, const float*
       for (int pass = 0; pass < 4; ++pass) {
         const int rr = pass * 8 + rd_row;
         const uint4 v = *reinterpret_cast<const uint4*>(staging + rr * 64 + ((rd_piece ^ ((rr >> 1) & 3)) << 4));
-        if (row0 + rr < p.rows_out)
+        if (row0 + rr < p.rows_out) {
+          BHS_CHECK(rr * 64 + ((rd_piece ^ ((rr >> 1) & 3)) << 4) + 16 <= EPI_STAGE_BYTES && b < p.batches &&
+                    (static_cast<size_t>(b) * p.rows_out + row0 + rr) * p.n_out + nt * BN + c * 32 + rd_piece * 8 + 8 <=
+                        static_cast<size_t>(p.batches) * p.rows_out * p.n_out);
           *reinterpret_cast<uint4*>(oslab + static_cast<size_t>(rr) * p.n_out + c * 32 + rd_piece * 8) = v;
+        }
       }
     }
   }
@@ -562,6 +583,8 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
             { PROF_T0(); mbar_wait(wfull0 + 8 * ws, wph); PROF_ADD(3); }
             tc_fence_after();
             const uint32_t aaddr = sa + st.tap_buf[tap] * A0_BYTES + st.tap_shift[tap] * 128;
+            BHS_CHECK(aaddr + BLOCK_M * 128 <= sa + ASTAGE_BYTES && (st.tap_buf[tap] == 0 ? st.tap_shift[tap] * 128 + BLOCK_M * 128 <= A0_BYTES : st.tap_shift[tap] == 0));
+            BHS_CHECK(ksteps >= 1 && ksteps <= BLOCK_K / UMMA_K && ring_w + (ws + 1) * C::W_BYTES <= ring_a + C::SMEM_BYTES - 1024 + 0u);
             const uint64_t adesc = sw128_desc(aaddr);      // row-shifted start, base offset 0 (measured: see above)
             const uint64_t bdesc = sw128_desc(ring_w + ws * C::W_BYTES);
             for (int k = 0; k < ksteps; ++k)

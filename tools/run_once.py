@@ -15,13 +15,23 @@ ap.add_argument("--samples", type=int, default=524160)
 ap.add_argument("--mels", type=int, default=80)
 ap.add_argument("--variant", default=None)
 ap.add_argument("--no-static-mel", action="store_true")
+ap.add_argument("--static-mel", type=int, default=None, help="BHMEL_OPT_STATIC_MEL value (0..2)")
+ap.add_argument("--pset", default=None, choices=["P0", "P128", "P1", "T5"], help="a reference parameter set (overrides --mels)")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
-mel = MelSpectrogram("torchaudio", True, 16000, 1024, a.mels, 128, 20, 8000, "reflect").to(dev)
+PSETS = {"P0": (True, 80, 20, "reflect"), "P128": (True, 128, 20, "reflect"), "P1": (False, 388, 0, "constant"),
+         "T5": (False, 512, 0, "constant")}
+if a.pset:
+    log, n_mels, f_min, pad = PSETS[a.pset]
+    mel = MelSpectrogram("torchaudio", log, 16000, 1024, n_mels, 128, f_min, 8000, pad).to(dev)
+else:
+    mel = MelSpectrogram("torchaudio", True, 16000, 1024, a.mels, 128, 20, 8000, "reflect").to(dev)
 if a.variant:
     mel.set_kernel_variant(a.variant)
 if a.no_static_mel:
     mel.set_static_mel(False)
+if a.static_mel is not None:
+    mel.set_static_mel(a.static_mel)
 g = torch.Generator(device=dev).manual_seed(1234)
 x = torch.rand(a.batch, a.samples, device=dev, generator=g).mul_(2).sub_(1)
 torch.cuda.synchronize()
