@@ -77,9 +77,21 @@ class ConvStem(nn.Module):
             with torch.cuda.device(idx):
                 _stem_lib.check(lib.bhstem_create(self.conv1.in_channels, self.conv1.out_channels,
                                                   *[ctypes.cast(t.data_ptr(), fp) for t in host], ctypes.byref(out)))
+            if getattr(self, "_variant", 1) != 1:
+                _stem_lib.check(lib.bhstem_set_option(out.value, 1, self._variant))
             self._handles[idx] = out.value
             self._stamp[idx] = stamp
             return out.value
+
+    VARIANTS = {"tap_boxes": 0, "shared_taps": 1, "cta_pairs": 2}
+
+    def set_variant(self, name: str) -> None:
+        """Kernel schedule (A/B runs; same results within the bf16 tolerance): "shared_taps" (default),
+        "tap_boxes", "cta_pairs" (tcgen05 cta_group::2).  bhstem_set_option, include/bhstem.h."""
+        self._variant = self.VARIANTS[name]
+        lib = _stem_lib.lib()
+        for h in self._handles.values():
+            _stem_lib.check(lib.bhstem_set_option(h, 1, self._variant))
 
     def __del__(self):
         try:

@@ -170,7 +170,7 @@ struct bhmel_handle {
   int use_bulk = 1;
   int kernel_variant = BHMEL_KERNEL_WARP_SPECIALIZED;
   int baked_fb = 0;      // id of the baked table (bhmel_fb_baked.h) the filterbank equals bit for bit: 1 = P0, 2.. = all-static sets; 0 = none
-  int static_mel = 1;    // BHMEL_OPT_STATIC_MEL: 0 generic stage always, 1 the baked table's default static stage, 2 P0 takes its direct form too
+  int static_mel = 1;    // BHMEL_OPT_STATIC_MEL: 0 generic stage always, 1 the baked table's direct form, 2 P0 takes its hybrid form
   // bhmel_forward_host pipeline (lazily created)
   std::mutex host_mu;
   cudaStream_t hs[kHostSlots] = {nullptr, nullptr, nullptr};
@@ -352,12 +352,13 @@ int launch(bhmel_handle* h, const float* x, long long row_stride, long long row0
     const unsigned grid = static_cast<unsigned>(p.n_tiles < h->num_sms ? p.n_tiles : h->num_sms);
     // Which mel stage: 0 generic, 1 P0 hybrid, >= 2 a direct form (vector stores from registers: the
     // output rows must be 16-byte (float32) / 8-byte (bfloat16) aligned, else the generic stage runs).
+    // BHMEL_OPT_STATIC_MEL: 0 pair tables always; 1 (default) the baked table's direct form; 2 P0 takes its
+    // hybrid form instead (bit-identical to the pair tables, the round-1 default)
     int st = h->static_mel ? h->baked_fb : 0;
-    if (st == 1 && h->static_mel == 2) st = bhmel::kStaticP0Direct;
-    if (st >= 2) {   // direct forms store vectors
+    if (st == 1 && h->static_mel != 2) st = bhmel::kStaticP0Direct;
+    {   // direct forms: 16-byte (f32) / 8-byte (bf16) stores when every output row allows it, else element stores
       const uintptr_t align = out.bf16 ? 8 : 16;
-      const bool ok = (reinterpret_cast<uintptr_t>(y) % align) == 0 && p.y_frame_pitch % 4 == 0 && p.y_row_pitch % 4 == 0;
-      if (!ok) st = st == bhmel::kStaticP0Direct ? 1 : 0;
+      p.y_vec_ok = (reinterpret_cast<uintptr_t>(y) % align) == 0 && p.y_frame_pitch % 4 == 0 && p.y_row_pitch % 4 == 0;
     }
     constexpr size_t smem = sizeof(bhmel::ws::SmemWS);
     if (st == 1) {   // hybrid: the generic stage only sees the filters the generated code leaves

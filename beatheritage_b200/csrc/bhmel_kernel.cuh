@@ -101,6 +101,7 @@ struct KParams {
   int n_pairs;
   int y_bf16;              // 0: float32 output, 1: bfloat16 (round to nearest even)
   long long y_limit;       // one past the largest output element index the call may write (BH_CHECK only)
+  int y_vec_ok;            // direct mel stages: output rows are 16-byte (f32) / 8-byte (bf16) aligned -> vector stores
 };
 
 // Output element store: float32 or bfloat16, any frame / row pitch (N1: writes the mel channels

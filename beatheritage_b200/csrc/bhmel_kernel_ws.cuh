@@ -26,7 +26,7 @@ namespace bhmel {
 // filters] (row pitch kStagePitch floats: pitch / 4 odd, so the lane = frame 128-bit stores are conflict
 // free); four finished filters of this lane's frame go in with one store (mel_stage4), and a full block
 // is written out by the same warp as row segments of up to 128 contiguous bytes (mel_flush, one shared
-// loop) -- float32, or bfloat16 rounded to nearest even.
+// loop that also applies the log1p epilogue) -- float32, or bfloat16 rounded to nearest even.
 constexpr int kStageCols = 32;
 constexpr int kStagePitch = kStageCols + 4;
 __device__ __forceinline__ void mel_stage4(float* __restrict__ srow, int col, float a, float b, float c, float d) {
@@ -36,9 +36,9 @@ __device__ __forceinline__ void mel_stage4(float* __restrict__ srow, int col, fl
 // Writes the first `ncols` (multiple of 4) columns of the warp's staging block to rows 0..nf-1 of the
 // tile: lane -> 16-byte column group lane & 7 of rows (lane >> 3) + 4 i, so one instruction moves four
 // row segments of up to 128 contiguous bytes.
-template <bool kBf16, int kPitch = kStagePitch>
+template <bool kBf16, bool kLog, int kPitch = kStagePitch>
 __device__ __forceinline__ void mel_flush(const float* __restrict__ stage, void* __restrict__ ytile, long long fpitch,
-                                          int m0, int ncols, int nf, int lane, long long y_room = 0) {
+                                          int m0, int ncols, int nf, int lane, bool vec, long long y_room = 0) {
   BH_CHECK(ncols % 4 == 0 && ncols + 4 <= kPitch && nf >= 1 && nf <= 32);
   __syncwarp();
   const int c = 4 * (lane & 7);
@@ -48,17 +48,34 @@ __device__ __forceinline__ void mel_flush(const float* __restrict__ stage, void*
 #pragma unroll
     for (int i = 0; i < kTileF / 4; ++i, sp += 4 * kPitch, off += 4 * fpitch) {
       if ((lane >> 3) + 4 * i < nf) {
-        BH_CHECK(off >= 0 && off + 4 <= y_room && (kBf16 ? (reinterpret_cast<uintptr_t>(static_cast<__nv_bfloat16*>(ytile) + off) & 7) == 0
-                                                          : (reinterpret_cast<uintptr_t>(static_cast<float*>(ytile) + off) & 15) == 0));
-        const float4 v = *reinterpret_cast<const float4*>(sp);
+        BH_CHECK(off >= 0 && off + 4 <= y_room);
+        BH_CHECK(!vec || (kBf16 ? (reinterpret_cast<uintptr_t>(static_cast<__nv_bfloat16*>(ytile) + off) & 7) == 0
+                                : (reinterpret_cast<uintptr_t>(static_cast<float*>(ytile) + off) & 15) == 0));
+        float4 v = *reinterpret_cast<const float4*>(sp);
+        if constexpr (kLog) {
+          v.x = fast_log1p(v.x);
+          v.y = fast_log1p(v.y);
+          v.z = fast_log1p(v.z);
+          v.w = fast_log1p(v.w);
+        }
         if constexpr (kBf16) {
           const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-          uint2 q;
-          q.x = *reinterpret_cast<const unsigned*>(&lo);
-          q.y = *reinterpret_cast<const unsigned*>(&hi);
-          *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(ytile) + off) = q;
+          __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(ytile) + off;
+          if (vec) {
+            uint2 q;
+            q.x = *reinterpret_cast<const unsigned*>(&lo);
+            q.y = *reinterpret_cast<const unsigned*>(&hi);
+            *reinterpret_cast<uint2*>(yp) = q;
+          } else {   // rows not 8-byte aligned (odd channel offset): element stores, same values
+            yp[0] = lo.x; yp[1] = lo.y; yp[2] = hi.x; yp[3] = hi.y;
+          }
         } else {
-          *reinterpret_cast<float4*>(static_cast<float*>(ytile) + off) = v;
+          float* yp = static_cast<float*>(ytile) + off;
+          if (vec) {
+            *reinterpret_cast<float4*>(yp) = v;
+          } else {
+            yp[0] = v.x; yp[1] = v.y; yp[2] = v.z; yp[3] = v.w;
+          }
         }
       }
     }
@@ -347,9 +364,9 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
 #pragma unroll 1
         for (int part = 0; part < kParts; ++part) {
 #ifdef BHMEL_DEBUG_ONE_BLOCK   // timing experiment (wrong results): every mel warp runs warp 0's code -> 1/8 of the footprint
-          mel_direct<kStatic, kLog>(prow, stage + lane * kStagePitch, 0, part);
+          mel_direct<kStatic>(prow, stage + lane * kStagePitch, 0, part);
 #else
-          mel_direct<kStatic, kLog>(prow, stage + lane * kStagePitch, mw, part);
+          mel_direct<kStatic>(prow, stage + lane * kStagePitch, mw, part);
 #endif
           if (part == kParts - 1) {   // this warp no longer reads P[b]
             __syncwarp();
@@ -358,7 +375,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
           int m0, ncols;
           mel_direct_run<kStatic>(mw * kParts + part, m0, ncols);
           BH_CHECK(m0 + ncols <= p.n_mels && (stage - S.mel_stage()) + kTileF * kStagePitch <= kMelWarps * kTileF * kStagePitch);
-          mel_flush<kBf16>(stage, ytile, p.y_frame_pitch, m0, ncols, nf, lane, p.y_limit - ybase);
+          mel_flush<kBf16, kLog>(stage, ytile, p.y_frame_pitch, m0, ncols, nf, lane, p.y_vec_ok != 0, p.y_limit - ybase);
         }
       } else {
 #ifdef BHMEL_DEBUG_SKIP_MEL

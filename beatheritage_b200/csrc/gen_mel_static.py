@@ -171,8 +171,9 @@ def emit_table_direct(name, n_mels, ent):
     CHAIN1_MAX bins) or two (even / odd bins), in ascending bin order, so there are almost no adds left:
     the code of a part is its non-zeros as FMAs + one load per power block + one 128-bit store per four
     finished filters into the warp's PRIVATE staging block [32 frames][STAGE_COLS].  The kernel loops
-    over the parts and writes each staged block out with one shared, compact loop (mel_flush: row
-    segments of up to 128 contiguous bytes) -- no chunk loop over the whole role, no cross-warp
+    over the parts and writes each staged block out with one shared, compact loop (mel_flush: the
+    log1p epilogue and the output type conversion happen THERE, once, not per filter in the generated
+    code; row segments of up to 128 contiguous bytes) -- no chunk loop over the whole role, no cross-warp
     barriers.  kRun<name>[warp * parts + part] = {first filter, filters} of every part.  (Not
     bit-identical to the generic stage's four-chain order; tests hold it to the oracle and to the
     generic stage within a few ulp.)"""
@@ -185,8 +186,7 @@ def emit_table_direct(name, n_mels, ent):
     runs = []
     L = [f"// {name}: {n_mels} filters, {len(ent)} non-zero weights; direct form, warp runs {bounds}, {n_parts} part(s)",
          f"constexpr int kParts{name} = {n_parts};"]
-    body = ["template <bool kLog>",
-            f"__device__ __forceinline__ void mel_direct_{name}(const float4* __restrict__ prow, float* __restrict__ srow, int mw, int part) {{",
+    body = [f"__device__ __forceinline__ void mel_direct_{name}(const float4* __restrict__ prow, float* __restrict__ srow, int mw, int part) {{",
             f"  switch (mw * {n_parts} + part) {{"]
     for w in range(N_WARPS):
         for part in range(n_parts):
@@ -232,7 +232,7 @@ def emit_table_direct(name, n_mels, ent):
                                 live.add((f, ch))
                     if last_block.get(f) == g:
                         expr = " + ".join(f"a{f}_{ch}" for ch in (0, 1) if (f, ch) in live)
-                        body.append(f"{ind}const float v{f} = kLog ? fast_log1p({expr}) : ({expr});")
+                        body.append(f"{ind}const float v{f} = {expr};")     # the log epilogue is applied once, in mel_flush
                         done.add(f)
                 drain()
             assert state["next"] == hi
@@ -271,10 +271,10 @@ def main():
     for name in tables:
         L.append(f"  if constexpr (kStatic == {sel[name]}) {{ m0 = kRun{name}[idx][0]; ncols = kRun{name}[idx][1]; }}")
     L += ["}",
-          "template <int kStatic, bool kLog>",
+          "template <int kStatic>",
           "__device__ __forceinline__ void mel_direct(const float4* __restrict__ prow, float* __restrict__ srow, int mw, int part) {"]
     for name in tables:
-        L.append(f"  if constexpr (kStatic == {sel[name]}) mel_direct_{name}<kLog>(prow, srow, mw, part);")
+        L.append(f"  if constexpr (kStatic == {sel[name]}) mel_direct_{name}(prow, srow, mw, part);")
     L += ["}", "", "}  // namespace bhmel"]
     open(args.out, "w").write("\n".join(L) + "\n")
 

@@ -348,8 +348,8 @@ class MelSpectrogram(nn.Module):
 
     def set_static_mel(self, enabled) -> None:
         """Debug / A-B switch: False / 0 forces the generic mel stage even for the baked reference
-        filterbanks, True / 1 is the default, 2 also gives P0 its direct form (see BHMEL_OPT_STATIC_MEL
-        in include/bhmel.h)."""
+        filterbanks, True / 1 is the default (direct generated forms), 2 gives P0 its hybrid form, which
+        is bit-identical to the generic stage (see BHMEL_OPT_STATIC_MEL in include/bhmel.h)."""
         self._static_mel = int(enabled)
         for h in self._handles.values():
             _lib.check(_lib.lib().bhmel_set_option(h, _lib.OPT_STATIC_MEL, int(self._static_mel)))

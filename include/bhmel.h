@@ -190,11 +190,13 @@ int bhmel_forward_host(bhmel_handle* h, const float* x_host, int64_t B, int64_t 
  * filterbanks of every parameter set in the reference's configs (80 / 128 htk mels 20..8000 Hz,
  * 388 / 512 htk mels 0..8000 Hz at 16 kHz; ref: configs/model/whisper_small_v2.yaml:16-21,
  * configs/train/tiny_dist22.yaml:10-12, configs/model/default.yaml:18-27, configs/model/t5_small.yaml:9-10).
- * The 80-mel table takes a hybrid stage that is bit-identical to the generic one; the other three take
- * the "direct" form (one or two summation chains per filter, vector stores from registers; a few ulp
- * from the generic stage, same tolerance against the reference) when the output rows are 16-byte
- * (float32) / 8-byte (bfloat16) aligned.  0 forces the generic descriptor-driven stage; 2 also gives the
- * 80-mel table its direct form (A/B runs).  Any other filterbank always takes the generic stage. */
+ * They take the "direct" form (one or two summation chains per filter, results staged per warp and
+ * written as row segments -- 16-byte / 8-byte vector stores when the output rows are aligned that way,
+ * element stores otherwise, same values; a few ulp from the generic stage, same tolerance against the
+ * reference).
+ * 0 forces the generic descriptor-driven stage (pair tables); 2 gives the 80-mel table its "hybrid" form
+ * instead (half the mel warps on generated code, half on pair tables: bit-identical to the generic stage).
+ * Any other filterbank always takes the generic stage. */
 #define BHMEL_OPT_STATIC_MEL 3
 int bhmel_set_option(bhmel_handle* h, int32_t option, int64_t value);
 

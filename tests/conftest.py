@@ -106,7 +106,7 @@ def emu_lib():
             gather=None, rounds=False, static_mel=False):
         """gather = (first_offset, stride, W, window_len) treats x as a 1-D song.  rounds / static_mel pick
         the mel stage of the independent-warp kernel / the generated-code stage of a baked filterbank
-        (static_mel=True: the default form -- P0 hybrid, the others direct; static_mel=2: P0 direct too)."""
+        (static_mel=True: the direct form, as BHMEL_OPT_STATIC_MEL = 1; static_mel=2: P0's hybrid form)."""
         x = np.ascontiguousarray(x, np.float32)
         if gather is None:
             B, N = x.shape

@@ -50,10 +50,10 @@ extern "C" int bhmel_emu_forward(const float* x, long long B, long long N, long 
   PairTables pt = make_pairs(fb.data(), n_mels);
   RoundTables rt = make_rounds(fb.data(), n_mels);
   const bool use_rounds = (exact_log1p & 2) != 0;   // bit 1: independent-warp kernel's round tables
-  // bit 2: the warp-specialised kernel's hybrid mel stage for the baked P0 filterbank -- generated
-  // code for filters < kStaticP0Filters, pair tables of the remaining filters for the rest
+  // bit 2: the warp-specialised kernel's generated mel stage of a baked filterbank: the direct form, or
+  // (with bit 3) P0's hybrid form -- generated code for filters < kStaticP0Filters, pair tables for the rest
   const bool use_static = (exact_log1p & 4) != 0;
-  const bool p0_direct = (exact_log1p & 8) != 0;    // bit 3: P0 takes its direct form (BHMEL_OPT_STATIC_MEL = 2)
+  const bool p0_hybrid = (exact_log1p & 8) != 0;    // bit 3: P0 takes its hybrid form (BHMEL_OPT_STATIC_MEL = 2) instead of the direct one
   exact_log1p &= 1;
   PairTables pt_rem;
   int baked_id = 0;
@@ -71,7 +71,7 @@ extern "C" int bhmel_emu_forward(const float* x, long long B, long long N, long 
       if (same) baked_id = b.id;
     }
     if (!baked_id) return 2;   // not a baked table
-    if (baked_id == 1 && p0_direct) baked_id = kStaticP0Direct;
+    if (baked_id == 1 && !p0_hybrid) baked_id = kStaticP0Direct;
     if (baked_id == 1) pt_rem = make_pairs(fb.data(), n_mels, kStaticP0Filters);
   }
 
@@ -154,7 +154,7 @@ extern "C" int bhmel_emu_forward(const float* x, long long B, long long N, long 
             constexpr int kParts = mel_direct_parts<kS>();
             for (int mw = 0; mw < 8; ++mw)
               for (int part = 0; part < kParts; ++part) {
-                mel_direct<kS, false>(pr, srow, mw, part);
+                mel_direct<kS>(pr, srow, mw, part);
                 int m0, ncols;
                 mel_direct_run<kS>(mw * kParts + part, m0, ncols);
                 for (int j = 0; j < ncols; ++j) tmp[m0 + j] = srow[j];   // mel_flush

@@ -120,14 +120,14 @@ def test_static_mel_stage_is_bit_identical_to_the_generic_one(emu_lib, log):
     for x in (signals.noise(2, 9000, 11), signals.music(6000, seed=3)[None, :], 40.0 * signals.noise(1, 3000, 5),
               np.zeros((1, 2000), np.float32)):
         y_gen = emu_lib(x, 80, fb=fb, window=window, log=log)
-        y_st = emu_lib(x, 80, fb=fb, window=window, log=log, static_mel=True)
+        y_st = emu_lib(x, 80, fb=fb, window=window, log=log, static_mel=2)
         assert np.array_equal(y_st.view(np.uint32), y_gen.view(np.uint32))
 
 
 @pytest.mark.parametrize("pset,log,mode", [("P128", True, True), ("P1", False, True), ("T5", False, True), ("T5", True, True),
-                                           ("P0", True, 2), ("P0", False, 2)])
+                                           ("P0", True, True), ("P0", False, True)])
 def test_direct_mel_stages_agree_with_the_generic_one_and_the_oracle(emu_lib, pset, log, mode):
-    """The direct forms (P128 / P1 / T5 by default, P0 on request) sum every filter in one or two
+    """The direct forms (the default of every baked reference filterbank) sum every filter in one or two
     chains instead of four, so they are not bit-identical to the generic stage: they must agree with
     it to a few ulp, keep all-zero filters and silence exactly 0, and meet
     the fp64 oracle like every other path."""

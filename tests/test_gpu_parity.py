@@ -73,9 +73,9 @@ def test_golden_fixtures(mods, dev, name):
 @pytest.mark.parametrize("pset,shape", [("P0", (3, 40000)), ("P0", (2, 524160)), ("P0", (5, 513)), ("P0C", (2, 100)),
                                         ("P1", (2, 30000)), ("T5", (1, 20000)), ("P128", (3, 9999))])
 def test_kernel_variants_are_bit_identical(mods, dev, pset, shape):
-    """The three schedules (barrier, independent warps, warp-specialised with the generic or P0's hybrid
-    mel stage) run the same arithmetic bit for bit; the warp-specialised kernel's direct mel stages
-    (P128 / P1 / T5 by default) sum in a different order and stay within a few ulp."""
+    """The three schedules (barrier, independent warps, warp-specialised with the generic mel stage)
+    run the same arithmetic bit for bit; the warp-specialised kernel's direct mel stages (the default for
+    every baked reference filterbank) sum in a different order and stay within a few ulp."""
     m = mods[pset]
     x = signals.noise(shape[0], shape[1], 77 + shape[1])
     m.set_kernel_variant("barrier")
@@ -90,9 +90,7 @@ def test_kernel_variants_are_bit_identical(mods, dev, pset, shape):
     m.set_kernel_variant(DEFAULT_VARIANT)
     assert np.array_equal(y_iw, y_bar)
     assert np.array_equal(y_ws, y_bar)
-    if pset in ("P0", "P0C"):
-        assert np.array_equal(y_ws_default, y_bar)
-    elif PSET_ARGS[pset][0]:
+    if PSET_ARGS[pset][0]:
         assert np.abs(y_ws_default - y_bar).max() <= 2e-6
     else:
         assert np.all(np.abs(y_ws_default - y_bar) <= 4e-6 * np.abs(y_bar))
@@ -105,17 +103,24 @@ def test_kernel_variants_are_bit_identical(mods, dev, pset, shape):
 @pytest.mark.parametrize("log", [True, False])
 @pytest.mark.parametrize("shape", [(1, 513), (3, 40000), (2, 524160), (7, 4097)])
 def test_static_mel_stage_is_bit_identical_to_generic(dev, log, shape):
-    """P0's filterbank is recognised as the baked table and takes the generated mel stage
-    (BHMEL_OPT_STATIC_MEL, default on); forcing the generic stage must not change a single bit.
-    A filterbank that differs in one weight must fall back to the generic stage by itself."""
+    """P0's filterbank is recognised as the baked table.  Its HYBRID generated stage
+    (BHMEL_OPT_STATIC_MEL = 2) must not differ from the generic stage in a single bit; its default
+    direct form stays within a few ulp.  A filterbank that differs in one weight must fall back to
+    the generic stage by itself."""
     from beatheritage_b200 import MelSpectrogram
     m = MelSpectrogram("torchaudio", log, 16000, 1024, 80, 128, 20, 8000, "reflect").to(dev)
     x = signals.noise(shape[0], shape[1], 5 + shape[1])
+    y_direct = run(m, x, dev)
+    m.set_static_mel(2)
     y_static = run(m, x, dev)
     m.set_static_mel(False)
     y_generic = run(m, x, dev)
     m.set_static_mel(True)
     assert np.array_equal(y_static.view(np.uint32), y_generic.view(np.uint32))
+    if log:
+        assert np.abs(y_direct - y_generic).max() <= 2e-6
+    else:
+        assert np.all(np.abs(y_direct - y_generic) <= 4e-6 * np.abs(y_generic))
     window, fb = load_params("P0")
     ref = mel_oracle.mel_forward(x, fb=fb, window=window, pad_mode="reflect", log_scale=log, dtype=np.float64)
     assert parity_error(y_static, ref, log) < TARGET
@@ -167,26 +172,31 @@ def test_direct_mel_stages_agree_with_generic_and_oracle(dev, pset, args, shape)
     torch.cuda.synchronize()
     assert torch.equal(wide[..., :M].cpu(), torch.from_numpy(y_static).to(torch.bfloat16))
     assert bool((wide[..., M:] == 7.0).all())
-    # channel offset 2: rows are no longer 8-byte aligned -> generic stage, same values as its float32 run
-    wide2 = torch.zeros((x.shape[0], T, M + 8), dtype=torch.bfloat16, device=dev)
-    m.forward_into(xt, wide2, channel_offset=2)
-    torch.cuda.synchronize()
-    assert torch.equal(wide2[..., 2:M + 2].cpu(), torch.from_numpy(y_generic).to(torch.bfloat16))
+    # channel offsets 1 / 3: rows are no longer 8-byte aligned -> element stores, the very same values
+    for choff, dt in ((1, torch.bfloat16), (3, torch.float32)):
+        wide2 = torch.zeros((x.shape[0], T, M + 8), dtype=dt, device=dev)
+        m.forward_into(xt, wide2, channel_offset=choff)
+        torch.cuda.synchronize()
+        assert torch.equal(wide2[..., choff:M + choff].cpu(), torch.from_numpy(y_static).to(dt))
+        assert bool((wide2[..., :choff] == 0).all()) and bool((wide2[..., M + choff:] == 0).all())
 
 
-def test_p0_direct_form_on_request(dev):
-    """BHMEL_OPT_STATIC_MEL = 2: P0 through its direct form (A/B runs): same tolerance, silence exactly 0."""
+def test_p0_direct_and_hybrid_forms(dev):
+    """P0's default is its direct form; BHMEL_OPT_STATIC_MEL = 2 selects the hybrid form: same tolerance
+    against the oracle, silence exactly 0 in both."""
     from beatheritage_b200 import MelSpectrogram
     m = MelSpectrogram("torchaudio", True, 16000, 1024, 80, 128, 20, 8000, "reflect").to(dev)
     x = signals.noise(3, 70000, 21)
-    y_hybrid = run(m, x, dev)
-    m.set_static_mel(2)
     y_direct = run(m, x, dev)
+    m.set_static_mel(2)
+    y_hybrid = run(m, x, dev)
     window, fb = load_params("P0")
     ref = mel_oracle.mel_forward(x, fb=fb, window=window, dtype=np.float64)
-    assert parity_error(y_direct, ref, True) < TARGET
+    assert parity_error(y_direct, ref, True) < TARGET and parity_error(y_hybrid, ref, True) < TARGET
     assert np.abs(y_direct - y_hybrid).max() < 2e-6
-    assert np.all(run(m, np.zeros((1, 4096), np.float32), dev) == 0.0)
+    for mode in (1, 2):
+        m.set_static_mel(mode)
+        assert np.all(run(m, np.zeros((1, 4096), np.float32), dev) == 0.0)
 
 
 @pytest.mark.parametrize("offset", [0, 1, 2, 3])
@@ -216,10 +226,15 @@ def test_kernel_variants_gather_unaligned(mods, dev):
     outs = {}
     for variant in ("barrier", "warp", "ws"):
         m.set_kernel_variant(variant)
+        if variant == "ws":                     # pair tables: bit-identical to the other schedules
+            m.set_static_mel(False)
         outs[variant] = m.forward_gather(song[1:], 3, 52415, 9, 262144).cpu().numpy()
+        m.set_static_mel(True)
+    outs["ws_default"] = m.forward_gather(song[1:], 3, 52415, 9, 262144).cpu().numpy()   # direct mel stage
     m.set_kernel_variant(DEFAULT_VARIANT)
     assert np.array_equal(outs["warp"], outs["barrier"])
     assert np.array_equal(outs["ws"], outs["barrier"])
+    assert np.abs(outs["ws_default"] - outs["barrier"]).max() <= 2e-6
     window, fb = load_params("P0")
     seq = np.stack([np.pad(song[1:].cpu().numpy(), (0, 600000))[3 + w * 52415: 3 + w * 52415 + 262144] for w in range(9)])
     ref = mel_oracle.mel_forward(seq, fb=fb, window=window, dtype=np.float64)

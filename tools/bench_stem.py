@@ -33,6 +33,7 @@ def timed(fn, warm=5, reps=30):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--json")
+    ap.add_argument("--variant", default="shared_taps", choices=["shared_taps", "tap_boxes", "cta_pairs"])
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     peaks = {}
@@ -44,6 +45,7 @@ def main():
     torch.manual_seed(0)
     C, D, T = 464, 768, 4096
     stem = ConvStem(C, D).to(dev)
+    stem.set_variant(args.variant)
     ref = ConvStem(C, D).to(dev).to(torch.bfloat16)
     ref.load_state_dict(stem.state_dict())
     out = {"gpu": torch.cuda.get_device_name(0), "dims": {"c_in": C, "d_model": D, "frames": T}, "rows": []}

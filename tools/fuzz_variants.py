@@ -1,5 +1,5 @@
 """Randomised cross-check of the three kernel schedules (bit-identical by construction with the generic /
-hybrid mel stage; the warp-specialised kernel's direct mel stages -- 128 / 388 mels here -- are held to a few
+mel stage; the warp-specialised kernel's direct mel stages -- 80 / 128 / 388 mels here -- are held to a few
 ulp of them) over many
 shapes: ragged lengths, batch sizes around multiples of the SM count, both pad modes, several
 filterbanks, module and gather mode, aligned and unaligned rows.  Catches pipeline (mbarrier
@@ -29,7 +29,7 @@ for n_mels, pad, log, fmin in ((80, "reflect", True, 20), (80, "constant", True,
                                (388, "constant", False, 0), (33, "reflect", True, 0)):
     mods[(n_mels, pad)] = MelSpectrogram("torchaudio", log, 16000, 1024, n_mels, 128, fmin, 8000, pad).to(dev)
 keys = list(mods)
-DIRECT = {128: True, 388: False}      # n_mels whose default ws mel stage is a direct form -> log scale?
+DIRECT = {80: True, 128: True, 388: False}      # n_mels whose default ws mel stage is a direct form -> log scale?
 
 
 def close(y, ref, key, what):

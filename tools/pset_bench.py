@@ -18,7 +18,7 @@ from beatheritage_b200 import MelSpectrogram  # noqa: E402
 SETS = {   # name -> (ctor args, static mel allowed)
     "P0": (("torchaudio", True, 16000, 1024, 80, 128, 20, 8000, "reflect"), True),
     "P0_generic": (("torchaudio", True, 16000, 1024, 80, 128, 20, 8000, "reflect"), False),
-    "P0_direct": (("torchaudio", True, 16000, 1024, 80, 128, 20, 8000, "reflect"), 2),
+    "P0_hybrid": (("torchaudio", True, 16000, 1024, 80, 128, 20, 8000, "reflect"), 2),
     "M64": (("torchaudio", True, 16000, 1024, 64, 128, 0, 8000, "reflect"), True),
     "M64_pairs": (("torchaudio", True, 16000, 1024, 64, 128, 0, 8000, "reflect"), False),
     "P128": (("torchaudio", True, 16000, 1024, 128, 128, 20, 8000, "reflect"), True),
