@@ -77,7 +77,7 @@ class ConvStem(nn.Module):
             with torch.cuda.device(idx):
                 _stem_lib.check(lib.bhstem_create(self.conv1.in_channels, self.conv1.out_channels,
                                                   *[ctypes.cast(t.data_ptr(), fp) for t in host], ctypes.byref(out)))
-            if getattr(self, "_variant", 1) != 1:
+            if getattr(self, "_variant", 2) != 2:
                 _stem_lib.check(lib.bhstem_set_option(out.value, 1, self._variant))
             self._handles[idx] = out.value
             self._stamp[idx] = stamp
@@ -86,8 +86,8 @@ class ConvStem(nn.Module):
     VARIANTS = {"tap_boxes": 0, "shared_taps": 1, "cta_pairs": 2}
 
     def set_variant(self, name: str) -> None:
-        """Kernel schedule (A/B runs; same results within the bf16 tolerance): "shared_taps" (default),
-        "tap_boxes", "cta_pairs" (tcgen05 cta_group::2).  bhstem_set_option, include/bhstem.h."""
+        """Kernel schedule (A/B runs; same results within the bf16 tolerance): "cta_pairs" (default: tcgen05
+        cta_group::2 where d_model % 256 == 0), "shared_taps", "tap_boxes".  bhstem_set_option, include/bhstem.h."""
         self._variant = self.VARIANTS[name]
         lib = _stem_lib.lib()
         for h in self._handles.values():

@@ -12,13 +12,16 @@
 // activations through a [batch][T/2][2*D] view (two time steps per row): tap 0 is the odd half of
 // the previous row, taps 1 and 2 the even and odd halves of the current one.
 //
-// Three kernels share the tile shape (128 rows x BN channels), the epilogue and the barrier protocol:
-//   bhstem_conv_gelu_shared_kernel  DEFAULT.  One staged block of rows per 64-channel step feeds all taps
-//                                   through row-shifted descriptors; separate weight / activation rings.
+// Three kernels share the tile shape (128 rows x BN channels per CTA), the epilogue and the barrier protocol:
+//   bhstem_conv_gelu_pair_kernel    DEFAULT for d_model % 256 == 0 (BHSTEM_VARIANT_CTA_PAIRS): CTA pairs,
+//                                   tcgen05.mma.cta_group::2, each CTA stages its 128 activation rows and HALF
+//                                   of the 256-row weight tile, which halves the per-SM weight ingest that
+//                                   bounds the one-CTA kernels (conv1: 0.31 ms against 0.34 for 46 windows).
+//   bhstem_conv_gelu_shared_kernel  BHSTEM_VARIANT_SHARED_TAPS, and d_model % 256 != 0.  One staged block of rows
+//                                   per 64-channel step feeds all taps through row-shifted descriptors;
+//                                   separate weight / activation rings.
 //   bhstem_conv_gelu_kernel         BHSTEM_VARIANT_TAP_BOXES: one TMA box per (tap, channel step); the first
 //                                   working version, kept as the A/B baseline.
-//   bhstem_conv_gelu_pair_kernel    BHSTEM_VARIANT_CTA_PAIRS: CTA pairs, tcgen05.mma.cta_group::2, half a weight
-//                                   tile per CTA; correct, measured no faster.
 // One persistent CTA per SM, warp-specialised (default kernel: 352 threads):
 //   warp 0      weight producer       one thread: TMA box BN rows x 64 ch per (channel step, tap), 128-byte
 //                                      swizzle, 4-stage mbarrier ring
@@ -200,6 +203,28 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// The same MMA from the LOW words of its two shared-memory descriptors: for the 128-byte-swizzle K-major
+// operands of this file the high word is the constant 0x40004040 (SBO 1024 B, version 1, layout 2), so the
+// single-thread issue loop only carries 32-bit values and "+ 2 k" is one integer add.
+// One elected lane of a converged warp (the single-thread roles): lets ptxas prove that the tcgen05 /
+// TMA instructions below are issued by exactly one thread, instead of wrapping each of them in an
+// ELECT / BRA.U.ANY loop as it does under a generic `lane == 0` predicate.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+constexpr uint32_t SW128_DESC_HI = 0x40004040u;
+__device__ __forceinline__ uint32_t sw128_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | 0x10000u; }
+__device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %5};\nmov.b64 db, {%2, %5};\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(SW128_DESC_HI)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -520,7 +545,7 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
     // ===================================== TMA producers ====================================
     // Two independent single-thread producers: warp 0 feeds the weight ring, the last warp the
     // activation ring, so a full weight ring never delays the next activation block (and vice versa).
-    if (lane == 0 && warp == A_PRODUCER_WARP) {
+    if (warp == A_PRODUCER_WARP && elect_one()) {
       uint32_t as = 0, aph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int b = tile / tiles_per_batch, mt = (tile % tiles_per_batch) / p.n_tiles;
@@ -542,7 +567,7 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
           if (++as == A_STAGES) { as = 0; aph ^= 1; }
         }
       }
-    } else if (lane == 0) {
+    } else if (warp == 0 && elect_one()) {
       uint32_t ws = 0, wph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int nt = (tile % tiles_per_batch) % p.n_tiles;
@@ -566,10 +591,53 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
                                  (static_cast<uint32_t>(BLOCK_M >> 4) << 24);
       uint32_t as = 0, aph = 0, ws = 0, wph = 0, local = 0;
+      // Lean path (both reference convolutions: 3-4 MMA steps per tap stage): this ONE thread's instruction
+      // stream is a serial chain that has to stay ahead of the tensor pipe while it shares an issue
+      // scheduler with two epilogue warps, so every instruction counts (~90 per tap stage in the generic
+      // loop below, ~35 here, against 464 tensor cycles).  Only the LOW words of the descriptors are
+      // carried (the high word is a constant), a ring slot is "base + slot * step", an MMA step is
+      // "low word + 2 k", the 4th step is predicated, and elect_one() above lets ptxas issue the
+      // tcgen05 instructions without per-instruction election loops.
+      const bool fast = ks.base == 3 || (ks.base == 4 && ks.extra == 0);
+      if (fast) {
+        uint32_t a_tap_lo[3];
+#pragma unroll
+        for (int tap = 0; tap < 3; ++tap)
+          a_tap_lo[tap] = sw128_desc_lo(ring_a + st.tap_buf[tap] * A0_BYTES + st.tap_shift[tap] * 128);
+        const uint32_t b0_lo = sw128_desc_lo(ring_w);
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+          const uint32_t acc = local & 1, accphase = (local >> 1) & 1;
+          { PROF_T0(); mbar_wait(tempty0 + 8 * acc, accphase ^ 1); PROF_ADD(4); }
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * BN;
+          uint32_t accumulate = 0;                           // only the tile's very first MMA overwrites
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            const bool step4 = ks.base == 4 || kb < ks.extra;
+            { PROF_T0(); mbar_wait(afull0 + 8 * as, aph); PROF_ADD(2); }
+            const uint32_t a_off = as * (ASTAGE_BYTES >> 4);
+#pragma unroll
+            for (int tap = 0; tap < 3; ++tap) {
+              { PROF_T0(); mbar_wait(wfull0 + 8 * ws, wph); PROF_ADD(3); }
+              tc_fence_after();
+              const uint32_t al = a_tap_lo[tap] + a_off, bl = b0_lo + ws * (C::W_BYTES >> 4);
+              umma_bf16_lo(tmem_d, al, bl, idesc, accumulate);
+              accumulate = 1;
+              umma_bf16_lo(tmem_d, al + 2, bl + 2, idesc, 1u);
+              umma_bf16_lo(tmem_d, al + 4, bl + 4, idesc, 1u);
+              if (step4) umma_bf16_lo(tmem_d, al + 6, bl + 6, idesc, 1u);
+              umma_commit(wempty0 + 8 * ws);
+              if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
+            }
+            umma_commit(aempty0 + 8 * as);                   // all three taps have read the staged rows
+            if (++as == A_STAGES) { as = 0; aph ^= 1; }
+          }
+          umma_commit(tfull0 + 8 * acc);
+        }
+      } else
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
         const uint32_t acc = local & 1, accphase = (local >> 1) & 1;
         { PROF_T0(); mbar_wait(tempty0 + 8 * acc, accphase ^ 1); PROF_ADD(4); }
@@ -655,13 +723,22 @@ __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, 
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_bf16_pair_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %5};\nmov.b64 db, {%2, %5};\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(SW128_DESC_HI)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {     // arrives on `bar` in both CTAs of the pair
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
                "h"(static_cast<uint16_t>(3))
                : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS_SHARED, 1)
 bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                              const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias,
                              __nv_bfloat16* __restrict__ out, const StemProblem p, const SharedTaps st) {
@@ -707,14 +784,14 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_ns0));
 #endif
 
-  if (warp == 0) {
-    // ===================================== TMA producer (both CTAs) =========================
-    if (lane == 0) {
-      const uint32_t afull_leader = map_to_cta(afull0, 0), wfull_leader = map_to_cta(wfull0, 0);
-      uint32_t as = 0, aph = 0, ws = 0, wph = 0;
+  if (warp == 0 || warp == A_PRODUCER_WARP) {
+    // ===================================== TMA producers (both CTAs) ========================
+    // Independent single-thread producers for the activation ring (last warp) and the weight ring (warp 0).
+    if (warp == A_PRODUCER_WARP && elect_one()) {
+      const uint32_t afull_leader = map_to_cta(afull0, 0);
+      uint32_t as = 0, aph = 0;
       for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
-        const int b = tile / tiles_per_batch, rem = tile % tiles_per_batch;
-        const int mt = rem / p.n_tiles, nt = rem % p.n_tiles;
+        const int b = tile / tiles_per_batch, mt = (tile % tiles_per_batch) / p.n_tiles;
         const int my_row = mt * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           const int c0 = ks.first_channel(kb);
@@ -725,6 +802,15 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
           if (st.n_aloads == 2)
             tma_load_3d_pair(&map_a1, afull_leader + 8 * as, sa + A0_BYTES, st.a_col[1] + c0, my_row + st.a_row[1], b);
           if (++as == PAIR_A_STAGES) { as = 0; aph ^= 1; }
+        }
+      }
+    } else if (warp == 0 && elect_one()) {
+      const uint32_t wfull_leader = map_to_cta(wfull0, 0);
+      uint32_t ws = 0, wph = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        const int nt = (tile % tiles_per_batch) % p.n_tiles;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          const int c0 = ks.first_channel(kb);
           for (int tap = 0; tap < 3; ++tap) {
             { PROF_T0(); mbar_wait(wempty0 + 8 * ws, wph ^ 1); PROF_ADD(1); }
             if (leader) mbar_expect_tx(wfull0 + 8 * ws, 2 * PAIR_W_BYTES);    // both halves of the weight tile
@@ -737,11 +823,48 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer (leader CTA only) =====================
-    if (leader && lane == 0) {
+    if (leader && elect_one()) {
       // D = F32, A = B = BF16, K-major, N = 256, M = 256 across the pair
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(PAIR_BN >> 3) << 17) |
                                  (static_cast<uint32_t>(256 >> 4) << 24);
       uint32_t as = 0, aph = 0, ws = 0, wph = 0, local = 0;
+      // Lean path, as in the shared-tap kernel: descriptor low words, "base + slot * step", predicated 4th step.
+      const bool fast = ks.base == 3 || (ks.base == 4 && ks.extra == 0);
+      if (fast) {
+        uint32_t a_tap_lo[3];
+#pragma unroll
+        for (int tap = 0; tap < 3; ++tap)
+          a_tap_lo[tap] = sw128_desc_lo(ring_a + st.tap_buf[tap] * A0_BYTES + st.tap_shift[tap] * 128);
+        const uint32_t b0_lo = sw128_desc_lo(ring_w);
+        for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++local) {
+          const uint32_t acc = local & 1, accphase = (local >> 1) & 1;
+          { PROF_T0(); mbar_wait(tempty0 + 8 * acc, accphase ^ 1); PROF_ADD(4); }
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * PAIR_BN;
+          uint32_t accumulate = 0;
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            const bool step4 = ks.base == 4 || kb < ks.extra;
+            { PROF_T0(); mbar_wait(afull0 + 8 * as, aph); PROF_ADD(2); }
+            const uint32_t a_off = as * (PAIR_ASTAGE_BYTES >> 4);
+#pragma unroll
+            for (int tap = 0; tap < 3; ++tap) {
+              { PROF_T0(); mbar_wait(wfull0 + 8 * ws, wph); PROF_ADD(3); }
+              tc_fence_after();
+              const uint32_t al = a_tap_lo[tap] + a_off, bl = b0_lo + ws * (PAIR_W_BYTES >> 4);
+              umma_bf16_pair_lo(tmem_d, al, bl, idesc, accumulate);
+              accumulate = 1;
+              umma_bf16_pair_lo(tmem_d, al + 2, bl + 2, idesc, 1u);
+              umma_bf16_pair_lo(tmem_d, al + 4, bl + 4, idesc, 1u);
+              if (step4) umma_bf16_pair_lo(tmem_d, al + 6, bl + 6, idesc, 1u);
+              umma_commit_pair(wempty0 + 8 * ws);
+              if (++ws == PAIR_W_STAGES) { ws = 0; wph ^= 1; }
+            }
+            umma_commit_pair(aempty0 + 8 * as);
+            if (++as == PAIR_A_STAGES) { as = 0; aph ^= 1; }
+          }
+          umma_commit_pair(tfull0 + 8 * acc);
+        }
+      } else
       for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++local) {
         const uint32_t acc = local & 1, accphase = (local >> 1) & 1;
         { PROF_T0(); mbar_wait(tempty0 + 8 * acc, accphase ^ 1); PROF_ADD(4); }
@@ -773,7 +896,8 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
   }
 
 #ifdef BHSTEM_PROFILE
-  if (lane == 0 && warp == 0 && leader) { PROF_FLUSH(0); PROF_FLUSH(1); }
+  if (lane == 0 && warp == A_PRODUCER_WARP && leader) { PROF_FLUSH(0); }
+  if (lane == 0 && warp == 0 && leader) { PROF_FLUSH(1); }
   if (lane == 0 && warp == 1 && leader) {
     PROF_FLUSH(2); PROF_FLUSH(3); PROF_FLUSH(4);
     atomicAdd(&g_prof[6], static_cast<unsigned long long>(clock64() - prof_start));
@@ -844,7 +968,7 @@ struct bhstem_handle {
   EncodeTiledFn enc = nullptr;
   std::atomic<long long> launches{0};   // the only state forward calls mutate: handles may be shared by threads
   int variant = 1;      // 1: shared taps (row-shifted descriptors, default), 0: one TMA box per tap
-  int pairs = 0;        // 1: CTA-pair kernel (tcgen05 cta_group::2) when d_model % 256 == 0
+  int pairs = 1;        // 1 (default): CTA-pair kernel (tcgen05 cta_group::2) when d_model % 256 == 0 and the SM count is even
   int exp = 0;          // -DBHSTEM_PROFILE builds only: BHSTEM_EXP timing experiments (wrong results)
 };
 
@@ -915,7 +1039,7 @@ int launch_stage(bhstem_handle* h, int stage, const void* in, int64_t B, int64_t
       pp.m_tiles = (p.rows_out + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
       const long long pair_tiles = static_cast<long long>(pp.batches) * pp.m_tiles * pp.n_tiles;
       const int pgrid = 2 * static_cast<int>(pair_tiles < h->sms / 2 ? pair_tiles : h->sms / 2);
-      bhstem_conv_gelu_pair_kernel<<<pgrid, THREADS, PAIR_SMEM_BYTES, stream>>>(
+      bhstem_conv_gelu_pair_kernel<<<pgrid, THREADS_SHARED, PAIR_SMEM_BYTES, stream>>>(
           map_a0, map_a1, stage == 1 ? h->map_w1_half : h->map_w2_half, stage == 1 ? h->b1 : h->b2,
           static_cast<__nv_bfloat16*>(out), pp, st);
       const cudaError_t e = cudaGetLastError();
@@ -992,6 +1116,7 @@ int bhstem_create(int32_t c_in, int32_t d_model, const float* conv1_weight, cons
   h->d = d_model;
   h->bn = d_model % 256 == 0 ? 256 : 128;
   h->variant = 1;
+  h->pairs = 1;          // default: the CTA-pair kernel where it applies (d_model % 256 == 0, even SM count)
 #ifdef BHSTEM_PROFILE   // tools-only build: timing experiments that skip loads / stores (wrong results)
   if (const char* v = getenv("BHSTEM_EXP")) h->exp = atoi(v);
 #endif
@@ -1059,7 +1184,7 @@ int bhstem_set_option(bhstem_handle* h, int32_t option, int64_t value) {
   if (value != BHSTEM_VARIANT_TAP_BOXES && value != BHSTEM_VARIANT_SHARED_TAPS && value != BHSTEM_VARIANT_CTA_PAIRS)
     return fail(BHSTEM_EINVAL, "unknown kernel variant");
   h->variant = value == BHSTEM_VARIANT_TAP_BOXES ? 0 : 1;
-  h->pairs = value == BHSTEM_VARIANT_CTA_PAIRS;
+  h->pairs = value == BHSTEM_VARIANT_CTA_PAIRS;          // BHSTEM_VARIANT_SHARED_TAPS: one CTA per tile
   return BHSTEM_OK;
 }
 

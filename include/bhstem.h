@@ -71,8 +71,9 @@ int bhstem_forward_stage(bhstem_handle* h, int32_t stage, const void* in, int64_
  * within the bf16 tolerance).  The choice is explicit -- no environment variable is read by the library. */
 #define BHSTEM_OPT_VARIANT 1
 #define BHSTEM_VARIANT_TAP_BOXES 0    /* one TMA box per (tap, channel step) */
-#define BHSTEM_VARIANT_SHARED_TAPS 1  /* default: one staged block, three row-shifted descriptors */
-#define BHSTEM_VARIANT_CTA_PAIRS 2    /* tcgen05.mma.cta_group::2 (d_model % 256 == 0, even SM count) */
+#define BHSTEM_VARIANT_SHARED_TAPS 1  /* one CTA per tile: one staged block, three row-shifted descriptors */
+#define BHSTEM_VARIANT_CTA_PAIRS 2    /* default: tcgen05.mma.cta_group::2 CTA pairs where d_model % 256 == 0 and the SM
+                                         count is even (else the shared-tap kernel runs) */
 int bhstem_set_option(bhstem_handle* h, int32_t option, int64_t value);
 
 int bhstem_version(void);

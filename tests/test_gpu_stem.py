@@ -209,3 +209,21 @@ def test_c5_slice_song_to_stem_output_matches_the_reference_op_chain(dev):
     # (a flipped mel value reaches 3 x 768 hidden values and every output under them, so most outputs move
     # by an fp32 hair and many bf16 roundings flip: only the magnitude bound is meaningful here)
     assert_close(got, want, "song -> stem output (C5 slice)", max_frac=1.01)
+
+
+@pytest.mark.parametrize("B,T", [(2, 512), (1, 200), (3, 4096)])
+def test_kernel_variants_agree(dev, B, T):
+    """The CTA-pair kernel (default for d_model % 256 == 0: tcgen05.mma.cta_group::2, half a weight tile per
+    CTA), the one-CTA shared-tap kernel and the one-box-per-tap kernel accumulate the same products in
+    the same order: identical results, ragged row tiles included."""
+    stem = make_stem(464, 768, dev, seed=3)
+    x = make_input(B, T, 464, seed=B * 7 + T).to(dev)
+    outs = {}
+    for variant in ("cta_pairs", "shared_taps", "tap_boxes"):
+        stem.set_variant(variant)
+        outs[variant] = stem(x).clone()
+    torch.cuda.synchronize()
+    stem.set_variant("cta_pairs")
+    assert torch.equal(outs["cta_pairs"], outs["shared_taps"])
+    assert torch.equal(outs["tap_boxes"], outs["shared_taps"])
+    assert bool(torch.isfinite(outs["cta_pairs"].float()).all())

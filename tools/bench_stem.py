@@ -33,7 +33,7 @@ def timed(fn, warm=5, reps=30):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--json")
-    ap.add_argument("--variant", default="shared_taps", choices=["shared_taps", "tap_boxes", "cta_pairs"])
+    ap.add_argument("--variant", default="cta_pairs", choices=["shared_taps", "tap_boxes", "cta_pairs"])
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     peaks = {}
