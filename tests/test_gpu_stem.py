@@ -214,8 +214,9 @@ def test_c5_slice_song_to_stem_output_matches_the_reference_op_chain(dev):
 @pytest.mark.parametrize("B,T", [(2, 512), (1, 200), (3, 4096)])
 def test_kernel_variants_agree(dev, B, T):
     """The CTA-pair kernel (default for d_model % 256 == 0: tcgen05.mma.cta_group::2, half a weight tile per
-    CTA), the one-CTA shared-tap kernel and the one-box-per-tap kernel accumulate the same products in
-    the same order: identical results, ragged row tiles included."""
+    CTA) and the one-CTA shared-tap kernel accumulate the same products in the same order: identical
+    results, ragged row tiles included.  The one-box-per-tap kernel sums tap-major instead of channel-block
+    major, so it may flip a bf16 rounding here and there: the stem's usual tolerance."""
     stem = make_stem(464, 768, dev, seed=3)
     x = make_input(B, T, 464, seed=B * 7 + T).to(dev)
     outs = {}
@@ -225,5 +226,5 @@ def test_kernel_variants_agree(dev, B, T):
     torch.cuda.synchronize()
     stem.set_variant("cta_pairs")
     assert torch.equal(outs["cta_pairs"], outs["shared_taps"])
-    assert torch.equal(outs["tap_boxes"], outs["shared_taps"])
+    assert_close(outs["tap_boxes"], outs["shared_taps"], "tap_boxes vs shared_taps", max_frac=0.10)
     assert bool(torch.isfinite(outs["cta_pairs"].float()).all())
