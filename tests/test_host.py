@@ -365,3 +365,24 @@ def test_conv_stem_mirrors_the_encoders_parameters_and_has_no_cpu_path():
         stem(torch.zeros(1, 464, 64, dtype=torch.bfloat16))
     p = pickle.loads(pickle.dumps(stem))
     assert p._handles == {} and list(p.state_dict()) == list(stem.state_dict())
+
+
+def test_slaney_bank_matches_the_librosa_compatible_bank_of_transformers():
+    """N4, second independent pin of the Slaney / area-normalised bank nnAudio documents (`htk=False, norm=1`,
+    librosa's filterbank): `transformers.audio_utils.mel_filter_bank(norm="slaney", mel_scale="slaney")` -- the
+    librosa-compatible implementation Whisper's feature extractor uses -- agrees with
+    melscale_fbanks_slaney to float32 rounding for every n_mels of the reference configs.  (nnAudio itself
+    stays un-installable here: the row remains "parity unpinned".)"""
+    au = pytest.importorskip("transformers.audio_utils")
+    import warnings
+    from beatheritage_b200.spectrogram import melscale_fbanks_slaney
+    for n_mels in (80, 128, 388, 512):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            hf = au.mel_filter_bank(num_frequency_bins=513, num_mel_filters=n_mels, min_frequency=0.0, max_frequency=8000.0,
+                                    sampling_rate=16000, norm="slaney", mel_scale="slaney")
+        mine = melscale_fbanks_slaney(513, 0.0, 8000.0, n_mels, 16000).numpy()
+        assert hf.shape == mine.shape
+        assert np.abs(hf - mine).max() <= 4e-8 * max(1.0, np.abs(hf).max() / 0.1)
+        assert np.array_equal(hf != 0, mine != 0) or np.abs(hf[(hf != 0) != (mine != 0)]).max() < 1e-9
+
