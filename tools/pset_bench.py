@@ -23,6 +23,9 @@ SETS = {   # name -> (ctor args, static mel allowed)
     "M64_pairs": (("torchaudio", True, 16000, 1024, 64, 128, 0, 8000, "reflect"), False),
     "P128": (("torchaudio", True, 16000, 1024, 128, 128, 20, 8000, "reflect"), True),
     "P1": (("torchaudio", False, 16000, 1024, 388, 128, 0, 8000, "constant"), True),
+    "P1_generic": (("torchaudio", False, 16000, 1024, 388, 128, 0, 8000, "constant"), False),
+    "T5_generic": (("torchaudio", False, 16000, 1024, 512, 128, 0, 8000, "constant"), False),
+    "P128_generic": (("torchaudio", True, 16000, 1024, 128, 128, 20, 8000, "reflect"), False),
     "T5": (("torchaudio", False, 16000, 1024, 512, 128, 0, 8000, "constant"), True),
 }
 
