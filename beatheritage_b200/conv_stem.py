@@ -116,15 +116,22 @@ class ConvStem(nn.Module):
             raise RuntimeError("the number of frames T must be even")
 
     @torch.no_grad()
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, hidden: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
         """x [B, T, C_in] bf16 channels last -> [B, T/2, D] bf16
-        == gelu(conv2(gelu(conv1(x.swapaxes(1, 2))))).permute(0, 2, 1)."""
+        == gelu(conv2(gelu(conv1(x.swapaxes(1, 2))))).permute(0, 2, 1).
+        `hidden` [B, T, D] and `out` [B, T/2, D] (bf16, contiguous, same device) may be passed in to keep
+        the two allocations out of a serving loop."""
         self._check(x)
         x = x.contiguous()
         B, T, _ = x.shape
         D = self.conv1.out_channels
-        hidden = torch.empty((B, T, D), dtype=torch.bfloat16, device=x.device)
-        y = torch.empty((B, T // 2, D), dtype=torch.bfloat16, device=x.device)
+        for name, buf, shape in (("hidden", hidden, (B, T, D)), ("out", out, (B, T // 2, D))):
+            if buf is not None and not (tuple(buf.shape) == shape and buf.dtype == torch.bfloat16 and buf.is_contiguous()
+                                        and buf.device == x.device):
+                raise RuntimeError(f"{name} must be a contiguous bfloat16 tensor {shape} on {x.device}")
+        if hidden is None:
+            hidden = torch.empty((B, T, D), dtype=torch.bfloat16, device=x.device)
+        y = out if out is not None else torch.empty((B, T // 2, D), dtype=torch.bfloat16, device=x.device)
         h = self._handle_for(x.device)
         with torch.cuda.device(x.device):
             stream = torch.cuda.current_stream(x.device).cuda_stream
