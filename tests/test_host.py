@@ -386,3 +386,24 @@ def test_slaney_bank_matches_the_librosa_compatible_bank_of_transformers():
         assert np.abs(hf - mine).max() <= 4e-8 * max(1.0, np.abs(hf).max() / 0.1)
         assert np.array_equal(hf != 0, mine != 0) or np.abs(hf[(hf != 0) != (mine != 0)]).max() < 1e-9
 
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (CPU only): one JSON line with the contract's keys; it runs the reference's
+    own module when oracle/_ref holds the copy build() makes, else the torch port, and says which."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "log-mel audio-sec/sec" and line["unit"] == "audio-s/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["gpu_launches"] == 0
+    assert line["e2e"] == {"value": line["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = line["cpu_baseline"]
+    have_copy = os.path.exists(os.path.join(root, "oracle", "_ref", "spectrogram.py"))
+    assert cb["kind"] == ("reference" if have_copy else "port") and cb["cores"] >= 1 and cb["value"] == line["value"]
+    assert "workload" in line["config"]
