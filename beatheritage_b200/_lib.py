@@ -15,6 +15,7 @@ PAD_CONSTANT, PAD_REFLECT = 0, 1
 OPT_BULK_COPY = 1
 OPT_KERNEL = 2
 OPT_STATIC_MEL = 3
+OPT_PDL = 4
 KERNEL_BARRIER, KERNEL_INDEPENDENT_WARPS, KERNEL_WARP_SPECIALIZED = 0, 1, 2
 OK, EINVAL, ECUDA, ESHAPE, EDEVICE = 0, 1, 2, 3, 4
 

@@ -79,6 +79,8 @@ class ConvStem(nn.Module):
                                                   *[ctypes.cast(t.data_ptr(), fp) for t in host], ctypes.byref(out)))
             if getattr(self, "_variant", 2) != 2:
                 _stem_lib.check(lib.bhstem_set_option(out.value, 1, self._variant))
+            if not getattr(self, "_pdl", True):
+                _stem_lib.check(lib.bhstem_set_option(out.value, 2, 0))
             self._handles[idx] = out.value
             self._stamp[idx] = stamp
             return out.value
@@ -92,6 +94,14 @@ class ConvStem(nn.Module):
         lib = _stem_lib.lib()
         for h in self._handles.values():
             _stem_lib.check(lib.bhstem_set_option(h, 1, self._variant))
+
+    def set_pdl(self, on: bool) -> None:
+        """Programmatic dependent launch (default on): a kernel's prologue overlaps the previous kernel's tail;
+        all global accesses still wait for that kernel.  BHSTEM_OPT_PDL, include/bhstem.h."""
+        self._pdl = bool(on)
+        lib = _stem_lib.lib()
+        for h in self._handles.values():
+            _stem_lib.check(lib.bhstem_set_option(h, 2, int(self._pdl)))
 
     def __del__(self):
         try:

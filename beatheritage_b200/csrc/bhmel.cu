@@ -170,6 +170,7 @@ struct bhmel_handle {
   int use_bulk = 1;
   int kernel_variant = BHMEL_KERNEL_WARP_SPECIALIZED;
   int baked_fb = 0;      // id of the baked table (bhmel_fb_baked.h) the filterbank equals bit for bit: 1 = P0, 2.. = all-static sets; 0 = none
+  int pdl = 1;           // BHMEL_OPT_PDL: launch the warp-specialised kernel with programmatic stream serialisation
   int static_mel = 1;    // BHMEL_OPT_STATIC_MEL: 0 generic stage always, 1 the baked table's direct form, 2 P0 takes its hybrid form
   // bhmel_forward_host pipeline (lazily created)
   std::mutex host_mu;
@@ -370,7 +371,20 @@ int launch(bhmel_handle* h, const float* x, long long row_stride, long long row0
       p.n_pairs = 0;
       p.n_weights = 0;
     }
-#define BHMEL_WS_LAUNCH(LOG, ST, BF) bhmel::ws::bhmel_logmel_ws_kernel<LOG, ST, BF><<<grid, bhmel::ws::kThreadsW, smem, stream>>>(p)
+    // Programmatic stream serialisation: the kernel's prologue (table staging, barrier init) may overlap the
+    // tail of the previous kernel in the stream; its mel / producer role waits (griddepcontrol.wait) before the
+    // first sample is read or the first output written.
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(bhmel::ws::kThreadsW);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute pdl_attr[1];
+    pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = pdl_attr;
+    cfg.numAttrs = h->pdl ? 1 : 0;
+#define BHMEL_WS_LAUNCH(LOG, ST, BF) BH_CUDA(cudaLaunchKernelEx(&cfg, bhmel::ws::bhmel_logmel_ws_kernel<LOG, ST, BF>, p))
 #define BHMEL_WS_DIRECT(ST)                                        \
   case ST:                                                         \
     if (p.log_scale) {                                             \
@@ -602,6 +616,10 @@ int bhmel_set_option(bhmel_handle* h, int32_t option, int64_t value) {
     case BHMEL_OPT_STATIC_MEL:
       if (value < 0 || value > 2) return fail(BHMEL_EINVAL, "BHMEL_OPT_STATIC_MEL takes 0, 1 or 2");
       h->static_mel = static_cast<int>(value);
+      return BHMEL_OK;
+    case BHMEL_OPT_PDL:
+      if (value != 0 && value != 1) return fail(BHMEL_EINVAL, "BHMEL_OPT_PDL takes 0 or 1");
+      h->pdl = static_cast<int>(value);
       return BHMEL_OK;
     default:
       return fail(BHMEL_EINVAL, "unknown option " + std::to_string(option));

@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
   constexpr bool kDirect = kStatic >= 2;
   static_assert(kDirect || !kBf16, "kBf16 only selects the store type of the direct forms");
   const bool fw_in_smem = p.n_weights <= kFwCap;   // the host guarantees this for kStatic != 0
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel's CTAs may take this SM as soon as we exit
   if (fw_in_smem)
     for (int i = tid; i < p.n_weights; i += kThreadsW) S.fw[i] = p.weights[i];
   for (int i = tid; i < p.n_pairs; i += kThreadsW) S.pairs[i] = reinterpret_cast<const int4*>(p.pairs)[i];
@@ -326,6 +327,10 @@ __global__ void __launch_bounds__(kThreadsW, 1) bhmel_logmel_ws_kernel(const __g
   } else {
     // ======================= producer + mel + store role =======================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(kMelRegs));
+    // Programmatic dependent launch (launch(), BHMEL_OPT_PDL): this grid may have become resident while the
+    // previous kernel in the stream was draining.  Everything above touches only the handle's constant tables;
+    // the samples are read and the output written by this role alone, after the previous grid has completed.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int mt = tid - kFftWarps * 32;
     const int mw = warp - kFftWarps;
     {

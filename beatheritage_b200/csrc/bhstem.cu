@@ -137,6 +137,12 @@ __device__ __forceinline__ uint32_t cluster_rank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Programmatic dependent launch: when the host launches with programmatic stream serialisation, the next
+// kernel's CTAs may become resident (barrier init, TMEM allocation, descriptor prefetch) while this grid drains.
+// Every global access of a kernel comes after pdl_wait(), which returns once the previous grid in the stream has
+// completed and its writes are visible; without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 #ifdef BHSTEM_PROFILE
 // -DBHSTEM_PROFILE (tools only): cycles each role spends waiting on its barriers, summed over CTAs.
@@ -400,6 +406,8 @@ bhstem_conv_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int tiles_per_batch = p.m_tiles * p.n_tiles;
   const int num_tiles = p.batches * tiles_per_batch;
@@ -529,6 +537,8 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int tiles_per_batch = p.m_tiles * p.n_tiles;
   const int num_tiles = p.batches * tiles_per_batch;
@@ -771,6 +781,8 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
   cluster_sync_all();       // both CTAs' barriers are initialised before anyone signals across
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int tiles_per_batch = p.m_tiles * p.n_tiles;       // m_tiles counts 256-row tiles here
   const int num_tiles = p.batches * tiles_per_batch;
@@ -968,6 +980,7 @@ struct bhstem_handle {
   EncodeTiledFn enc = nullptr;
   std::atomic<long long> launches{0};   // the only state forward calls mutate: handles may be shared by threads
   int variant = 1;      // 1: shared taps (row-shifted descriptors, default), 0: one TMA box per tap
+  int pdl = 1;          // 1 (default): launch with programmatic stream serialisation (prologue overlaps the previous grid's tail)
   int pairs = 1;        // 1 (default): CTA-pair kernel (tcgen05 cta_group::2) when d_model % 256 == 0 and the SM count is even
   int exp = 0;          // -DBHSTEM_PROFILE builds only: BHSTEM_EXP timing experiments (wrong results)
 };
@@ -982,6 +995,23 @@ std::vector<__nv_bfloat16> pack_weight(const float* w, int d, int c) {
       for (int tap = 0; tap < 3; ++tap)
         out[(static_cast<size_t>(tap) * d + n) * c + ci] = __float2bfloat16_rn(w[(static_cast<size_t>(n) * c + ci) * 3 + tap]);
   return out;
+}
+
+// One launch, optionally with programmatic stream serialisation (see pdl_wait above).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_kernel(bool pdl, void (*kernel)(KArgs...), int grid, int threads, size_t smem, cudaStream_t stream,
+                          Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(static_cast<unsigned>(threads));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 template <int BN>
@@ -1039,27 +1069,28 @@ int launch_stage(bhstem_handle* h, int stage, const void* in, int64_t B, int64_t
       pp.m_tiles = (p.rows_out + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
       const long long pair_tiles = static_cast<long long>(pp.batches) * pp.m_tiles * pp.n_tiles;
       const int pgrid = 2 * static_cast<int>(pair_tiles < h->sms / 2 ? pair_tiles : h->sms / 2);
-      bhstem_conv_gelu_pair_kernel<<<pgrid, THREADS_SHARED, PAIR_SMEM_BYTES, stream>>>(
-          map_a0, map_a1, stage == 1 ? h->map_w1_half : h->map_w2_half, stage == 1 ? h->b1 : h->b2,
-          static_cast<__nv_bfloat16*>(out), pp, st);
-      const cudaError_t e = cudaGetLastError();
+      const cudaError_t e = launch_kernel(h->pdl != 0, bhstem_conv_gelu_pair_kernel, pgrid, THREADS_SHARED, PAIR_SMEM_BYTES,
+                                          stream, map_a0, map_a1, stage == 1 ? h->map_w1_half : h->map_w2_half,
+                                          static_cast<const float*>(stage == 1 ? h->b1 : h->b2),
+                                          static_cast<__nv_bfloat16*>(out), pp, st);
       if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
       ++h->launches;
       return BHSTEM_OK;
     }
     auto kernel = bhstem_conv_gelu_shared_kernel<BN>;
-    kernel<<<grid, THREADS_SHARED, CfgShared<BN>::SMEM_BYTES, stream>>>(map_a0, map_a1, stage == 1 ? h->map_w1 : h->map_w2,
-                                                                 stage == 1 ? h->b1 : h->b2,
-                                                                 static_cast<__nv_bfloat16*>(out), p, st);
-    const cudaError_t e = cudaGetLastError();
+    const cudaError_t e = launch_kernel(h->pdl != 0, kernel, grid, THREADS_SHARED, CfgShared<BN>::SMEM_BYTES, stream, map_a0,
+                                        map_a1, stage == 1 ? h->map_w1 : h->map_w2,
+                                        static_cast<const float*>(stage == 1 ? h->b1 : h->b2),
+                                        static_cast<__nv_bfloat16*>(out), p, st);
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     ++h->launches;
     return BHSTEM_OK;
   }
   auto kernel = bhstem_conv_gelu_kernel<BN>;
-  kernel<<<grid, THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(map_a, stage == 1 ? h->map_w1 : h->map_w2,
-                                                         stage == 1 ? h->b1 : h->b2, static_cast<__nv_bfloat16*>(out), p);
-  const cudaError_t e = cudaGetLastError();
+  const cudaError_t e = launch_kernel(h->pdl != 0, kernel, grid, THREADS, Cfg<BN>::SMEM_BYTES, stream, map_a,
+                                      stage == 1 ? h->map_w1 : h->map_w2,
+                                      static_cast<const float*>(stage == 1 ? h->b1 : h->b2),
+                                      static_cast<__nv_bfloat16*>(out), p);
   if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
   ++h->launches;
   return BHSTEM_OK;
@@ -1180,6 +1211,11 @@ void bhstem_destroy(bhstem_handle* h) {
 
 int bhstem_set_option(bhstem_handle* h, int32_t option, int64_t value) {
   if (!h) return fail(BHSTEM_EINVAL, "null handle");
+  if (option == BHSTEM_OPT_PDL) {
+    if (value != 0 && value != 1) return fail(BHSTEM_EINVAL, "BHSTEM_OPT_PDL takes 0 or 1");
+    h->pdl = static_cast<int>(value);
+    return BHSTEM_OK;
+  }
   if (option != BHSTEM_OPT_VARIANT) return fail(BHSTEM_EINVAL, "unknown option");
   if (value != BHSTEM_VARIANT_TAP_BOXES && value != BHSTEM_VARIANT_SHARED_TAPS && value != BHSTEM_VARIANT_CTA_PAIRS)
     return fail(BHSTEM_EINVAL, "unknown kernel variant");

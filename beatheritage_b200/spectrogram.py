@@ -313,6 +313,8 @@ class MelSpectrogram(nn.Module):
                     _lib.check(lib.bhmel_set_option(h, _lib.OPT_KERNEL, self._variant))
                     if int(getattr(self, "_static_mel", 1)) != 1:
                         _lib.check(lib.bhmel_set_option(h, _lib.OPT_STATIC_MEL, int(self._static_mel)))
+                    if not getattr(self, "_pdl", True):
+                        _lib.check(lib.bhmel_set_option(h, _lib.OPT_PDL, 0))
                 else:   # buffers were reloaded / edited: refresh the device tables
                     _lib.check(lib.bhmel_set_fb(h, ctypes.cast(fb.data_ptr(), fp)))
                     _lib.check(lib.bhmel_set_window(h, ctypes.cast(win.data_ptr(), fp)))
@@ -353,6 +355,13 @@ class MelSpectrogram(nn.Module):
         self._static_mel = int(enabled)
         for h in self._handles.values():
             _lib.check(_lib.lib().bhmel_set_option(h, _lib.OPT_STATIC_MEL, int(self._static_mel)))
+
+    def set_pdl(self, enabled: bool) -> None:
+        """A-B switch: programmatic dependent launch of the fused kernel (default on; BHMEL_OPT_PDL in
+        include/bhmel.h).  Results and stream-order semantics do not depend on it."""
+        self._pdl = bool(enabled)
+        for h in self._handles.values():
+            _lib.check(_lib.lib().bhmel_set_option(h, _lib.OPT_PDL, int(self._pdl)))
 
     # -- forward -----------------------------------------------------------------------
     def _check_input(self, samples: torch.Tensor) -> torch.Tensor:

@@ -198,6 +198,11 @@ int bhmel_forward_host(bhmel_handle* h, const float* x_host, int64_t B, int64_t 
  * instead (half the mel warps on generated code, half on pair tables: bit-identical to the generic stage).
  * Any other filterbank always takes the generic stage. */
 #define BHMEL_OPT_STATIC_MEL 3
+/* BHMEL_OPT_PDL: 1 (default) launches the warp-specialised kernel with programmatic stream serialisation, so
+ * its prologue (constant-table staging, barrier init) overlaps the tail of the previous kernel in the stream.
+ * The kernel reads no sample and writes no output before that kernel has completed (griddepcontrol.wait);
+ * results and stream-order semantics are unchanged.  0: plain stream order. */
+#define BHMEL_OPT_PDL 4
 int bhmel_set_option(bhmel_handle* h, int32_t option, int64_t value);
 
 /* Host-buffer entry with typed input / output (next rows N1 + N2 of SURVEY.md 8f).

@@ -74,6 +74,10 @@ int bhstem_forward_stage(bhstem_handle* h, int32_t stage, const void* in, int64_
 #define BHSTEM_VARIANT_SHARED_TAPS 1  /* one CTA per tile: one staged block, three row-shifted descriptors */
 #define BHSTEM_VARIANT_CTA_PAIRS 2    /* default: tcgen05.mma.cta_group::2 CTA pairs where d_model % 256 == 0 and the SM
                                          count is even (else the shared-tap kernel runs) */
+/* 1 (default): kernels are launched with programmatic stream serialisation, so a kernel's prologue (barrier
+ * init, TMEM allocation) overlaps the tail of the previous kernel in the stream; every global access still
+ * waits for that kernel to complete (griddepcontrol.wait).  0: plain stream order. */
+#define BHSTEM_OPT_PDL 2
 int bhstem_set_option(bhstem_handle* h, int32_t option, int64_t value);
 
 int bhstem_version(void);

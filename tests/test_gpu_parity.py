@@ -758,3 +758,42 @@ def test_torch_compile_does_not_graph_break(mods, dev):
     except Exception as e:   # inductor needs a working host compiler/triton; not the subject here
         pytest.skip(f"torch.compile unavailable in this environment: {type(e).__name__}")
     assert torch.allclose(out, w(x), atol=1e-6)
+
+
+def test_programmatic_dependent_launch_keeps_stream_order(mods, dev):
+    """BHMEL_OPT_PDL (default on): the warp-specialised kernel may become resident while the previous kernel
+    in the stream drains, but reads no sample and writes no output before that kernel has completed.  Chains
+    of adjacent launches with read-after-write (the next input is made from this output by the previous
+    launch's own output buffer), write-after-write (one output buffer) and write-after-read hazards give the
+    same bits with and without it."""
+    m = mods["P0"]
+    B, N = 3, 66000
+    T = N // 128 + 1
+    x0 = torch.from_numpy(signals.noise(B, N, 4242)).to(dev)
+    out = torch.empty(B, T, 80, device=dev)
+
+    def chain():
+        x = x0.clone()
+        got = []
+        for i in range(6):
+            m.forward_into(x, out)                                   # same output buffer every time
+            got.append(out.clone())
+            # adjacent launch reads what the previous one wrote: rebuild an input from the output in place
+            x.view(-1)[: out.numel()].copy_(out.view(-1)).mul_(0.1).sub_(0.3)
+            m.forward_into(x, out)
+            got.append(out.clone())
+        # and with nothing between the launches at all
+        for i in range(6):
+            m.forward_into(x0 if i % 2 == 0 else x, out)
+        got.append(out.clone())
+        torch.cuda.synchronize()
+        return got
+
+    with_pdl = chain()
+    m.set_pdl(False)
+    try:
+        without = chain()
+    finally:
+        m.set_pdl(True)
+    for a, b in zip(with_pdl, without):
+        assert torch.equal(a, b)

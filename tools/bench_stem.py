@@ -34,6 +34,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--json")
     ap.add_argument("--variant", default="cta_pairs", choices=["shared_taps", "tap_boxes", "cta_pairs"])
+    ap.add_argument("--no-pdl", action="store_true", help="plain stream order instead of programmatic dependent launch")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     peaks = {}
@@ -46,6 +47,8 @@ def main():
     C, D, T = 464, 768, 4096
     stem = ConvStem(C, D).to(dev)
     stem.set_variant(args.variant)
+    if args.no_pdl:
+        stem.set_pdl(False)
     ref = ConvStem(C, D).to(dev).to(torch.bfloat16)
     ref.load_state_dict(stem.state_dict())
     out = {"gpu": torch.cuda.get_device_name(0), "dims": {"c_in": C, "d_model": D, "frames": T}, "rows": []}
