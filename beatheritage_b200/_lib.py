@@ -84,6 +84,7 @@ SIGNATURES = {
     "bhmel_forward_gather_pcm16": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
     "bhmel_forward_host": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _vp]),
     "bhmel_forward_host_ex": (ctypes.c_int, [_vp, ctypes.POINTER(BhmelHostIO), _i64, _i64, _i64]),
+    "bhmel_host_chunk_plan": (_i64, [_i64, _i64, _i32, ctypes.POINTER(_i64), _i64]),
     "bhmel_set_option": (ctypes.c_int, [_vp, _i32, _i64]),
     "bhmel_version": (ctypes.c_int, []),
     "bhmel_last_error": (ctypes.c_char_p, []),

@@ -33,7 +33,19 @@ int fail(int code, const std::string& msg) {
       return fail(BHMEL_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));         \
   } while (0)
 
-constexpr int kHostSlots = 3;
+#ifndef BHMEL_HOST_SLOTS
+#define BHMEL_HOST_SLOTS 3
+#endif
+#ifndef BHMEL_HOST_CHUNK_MB
+#define BHMEL_HOST_CHUNK_MB 16
+#endif
+#ifndef BHMEL_HOST_CHUNK_MB_PCM
+#define BHMEL_HOST_CHUNK_MB_PCM 32
+#endif
+#ifndef BHMEL_HOST_TAPER
+#define BHMEL_HOST_TAPER 1
+#endif
+constexpr int kHostSlots = BHMEL_HOST_SLOTS;
 
 }  // namespace
 
@@ -174,10 +186,10 @@ struct bhmel_handle {
   int static_mel = 1;    // BHMEL_OPT_STATIC_MEL: 0 generic stage always, 1 the baked table's direct form, 2 P0 takes its hybrid form
   // bhmel_forward_host pipeline (lazily created)
   std::mutex host_mu;
-  cudaStream_t hs[kHostSlots] = {nullptr, nullptr, nullptr};
-  float* d_in[kHostSlots] = {nullptr, nullptr, nullptr};
-  float* d_out[kHostSlots] = {nullptr, nullptr, nullptr};
-  int16_t* d_pcm[kHostSlots] = {nullptr, nullptr, nullptr};
+  cudaStream_t hs[kHostSlots] = {};
+  float* d_in[kHostSlots] = {};
+  float* d_out[kHostSlots] = {};
+  int16_t* d_pcm[kHostSlots] = {};
   float* d_scales = nullptr;
   size_t cap_in = 0, cap_out = 0, cap_pcm = 0, cap_scales = 0;
   // bhmel_forward_encoder_input / bhmel_forward_gather_pcm16 scratch (lazily created, only when the caller passes none)
@@ -744,6 +756,32 @@ int bhmel_forward_gather_pcm16(bhmel_handle* h, const int16_t* song_dev, int64_t
   return launch(h, scratch, stride, first_offset, n_song, W, window_len, OutSpec{y, 0, 0, 0}, s);
 }
 
+// Row chunks of one bhmel_forward_host_ex call.  ~16 MB of fp32 / ~32 MB of int16 source per chunk (8 / 32
+// model-context windows) keeps both copy engines busy; the first and last chunks are tapered (1/8, 1/4, 1/2 of a
+// chunk) because nothing overlaps the very first host->device copy and the very last device->host copy of a call
+// (measured on B200 with tools/host_chunk_probe.py: fp32 12 / 16 / 20 / 24 / 32 MB chunks 10.63 / 10.44-10.51 /
+// 10.53 / 10.57 / 10.77-11.0 ms per 256 windows, int16 16 / 32 / 40 / 48 / 64 MB 5.77 / 5.60 / 5.60 / 5.90 / 6.26 ms;
+// the taper is worth 0.3 % / 1.2 %).
+static std::vector<int64_t> host_chunk_rows(int64_t B, size_t row_src, bool pcm) {
+  int64_t rows = static_cast<int64_t>((static_cast<size_t>(pcm ? BHMEL_HOST_CHUNK_MB_PCM : BHMEL_HOST_CHUNK_MB) << 20) / row_src);
+  if (rows < 1) rows = 1;
+  if (rows > B) rows = B;
+  if (rows * 2 > B && B >= 2 * kHostSlots) rows = (B + 2 * kHostSlots - 1) / (2 * kHostSlots);
+  std::vector<int64_t> chunk_rows;
+  int64_t head[3], n_head = 0, taper_total = 0;
+  if (BHMEL_HOST_TAPER && B >= 6 * rows)
+    for (int64_t r = rows >= 8 ? rows / 8 : 1; r < rows && n_head < 3; r *= 2) { head[n_head++] = r; taper_total += r; }
+  for (int64_t i = 0; i < n_head; ++i) chunk_rows.push_back(head[i]);
+  int64_t middle = B - 2 * taper_total;
+  while (middle > 0) {
+    const int64_t r = middle < rows ? middle : rows;
+    chunk_rows.push_back(r);
+    middle -= r;
+  }
+  for (int64_t i = n_head - 1; i >= 0; --i) chunk_rows.push_back(head[i]);
+  return chunk_rows;
+}
+
 int bhmel_forward_host_ex(bhmel_handle* h, const bhmel_host_io* io, int64_t B, int64_t N, int64_t x_row_stride) {
   if (!h) return fail(BHMEL_EINVAL, "null handle");
   if (!io || !io->x_host || !io->y_host) return fail(BHMEL_EINVAL, "null data pointer");
@@ -760,11 +798,9 @@ int bhmel_forward_host_ex(bhmel_handle* h, const bhmel_host_io* io, int64_t B, i
   const size_t row_f32 = static_cast<size_t>(N) * sizeof(float);
   const size_t row_src = static_cast<size_t>(N) * (pcm ? sizeof(int16_t) : sizeof(float));
   const size_t row_out = static_cast<size_t>(T) * h->prm.n_mels * (bf16 ? 2 : 4);
-  // ~32 MB of fp32 input per chunk keeps three chunks in flight (H2D / kernel / D2H) with small tails.
-  int64_t rows = static_cast<int64_t>((32u << 20) / row_f32);
-  if (rows < 1) rows = 1;
-  if (rows > B) rows = B;
-  if (rows * 2 > B && B >= 2 * kHostSlots) rows = (B + 2 * kHostSlots - 1) / (2 * kHostSlots);
+  const std::vector<int64_t> chunk_rows = host_chunk_rows(B, row_src, pcm);
+  int64_t rows = 1;
+  for (int64_t r : chunk_rows) rows = r > rows ? r : rows;
   const size_t need_in = static_cast<size_t>(rows) * row_f32;
   const size_t need_out = static_cast<size_t>(rows) * static_cast<size_t>(T) * h->prm.n_mels * 4;
   const size_t need_pcm = pcm ? static_cast<size_t>(rows) * N * sizeof(int16_t) : 0;
@@ -803,32 +839,53 @@ int bhmel_forward_host_ex(bhmel_handle* h, const bhmel_host_io* io, int64_t B, i
     BH_CUDA(cudaMemcpy(h->d_scales, io->scales, static_cast<size_t>(B) * sizeof(float), cudaMemcpyHostToDevice));
     d_scales = h->d_scales;
   }
-  int slot = 0;
-  for (int64_t b0 = 0; b0 < B; b0 += rows, slot = (slot + 1) % kHostSlots) {
-    const int64_t nb = (B - b0) < rows ? (B - b0) : rows;
-    cudaStream_t s = h->hs[slot];
-    if (pcm) {
-      const int16_t* src = static_cast<const int16_t*>(io->x_host) + b0 * x_row_stride;
-      BH_CUDA(cudaMemcpy2DAsync(h->d_pcm[slot], row_src, src, static_cast<size_t>(x_row_stride) * sizeof(int16_t),
-                                row_src, static_cast<size_t>(nb), cudaMemcpyHostToDevice, s));
-      const long long total = static_cast<long long>(nb) * N;
-      const unsigned blocks = static_cast<unsigned>(h->num_sms * 8);
-      bhmel_pcm16_to_f32_kernel<<<blocks, 256, 0, s>>>(h->d_pcm[slot], h->d_in[slot],
-                                                       d_scales ? d_scales + b0 : nullptr, N, total);
-      BH_CUDA(cudaGetLastError());
-      h->launches.fetch_add(1, std::memory_order_relaxed);
-    } else {
-      const float* src = static_cast<const float*>(io->x_host) + b0 * x_row_stride;
-      BH_CUDA(cudaMemcpy2DAsync(h->d_in[slot], row_f32, src, static_cast<size_t>(x_row_stride) * sizeof(float),
-                                row_f32, static_cast<size_t>(nb), cudaMemcpyHostToDevice, s));
+  // Every exit below this point first drains the private streams: the caller owns the host buffers again the
+  // moment this function returns, with or without an error.
+  auto enqueue = [&]() -> int {
+    int slot = 0;
+    int64_t b0 = 0;
+    for (size_t c = 0; c < chunk_rows.size(); b0 += chunk_rows[c], ++c, slot = (slot + 1) % kHostSlots) {
+      const int64_t nb = chunk_rows[c];
+      cudaStream_t s = h->hs[slot];
+      if (pcm) {
+        const int16_t* src = static_cast<const int16_t*>(io->x_host) + b0 * x_row_stride;
+        BH_CUDA(cudaMemcpy2DAsync(h->d_pcm[slot], row_src, src, static_cast<size_t>(x_row_stride) * sizeof(int16_t),
+                                  row_src, static_cast<size_t>(nb), cudaMemcpyHostToDevice, s));
+        const long long total = static_cast<long long>(nb) * N;
+        const unsigned blocks = static_cast<unsigned>(h->num_sms * 8);
+        bhmel_pcm16_to_f32_kernel<<<blocks, 256, 0, s>>>(h->d_pcm[slot], h->d_in[slot],
+                                                         d_scales ? d_scales + b0 : nullptr, N, total);
+        BH_CUDA(cudaGetLastError());
+        h->launches.fetch_add(1, std::memory_order_relaxed);
+      } else {
+        const float* src = static_cast<const float*>(io->x_host) + b0 * x_row_stride;
+        BH_CUDA(cudaMemcpy2DAsync(h->d_in[slot], row_f32, src, static_cast<size_t>(x_row_stride) * sizeof(float),
+                                  row_f32, static_cast<size_t>(nb), cudaMemcpyHostToDevice, s));
+      }
+      if (int rc = launch(h, h->d_in[slot], N, 0, LLONG_MAX, nb, N, OutSpec{h->d_out[slot], bf16 ? 1 : 0, 0, 0}, s))
+        return rc;
+      BH_CUDA(cudaMemcpyAsync(static_cast<char*>(io->y_host) + static_cast<size_t>(b0) * row_out, h->d_out[slot],
+                              static_cast<size_t>(nb) * row_out, cudaMemcpyDeviceToHost, s));
     }
-    if (int rc = launch(h, h->d_in[slot], N, 0, LLONG_MAX, nb, N, OutSpec{h->d_out[slot], bf16 ? 1 : 0, 0, 0}, s))
-      return rc;
-    BH_CUDA(cudaMemcpyAsync(static_cast<char*>(io->y_host) + static_cast<size_t>(b0) * row_out, h->d_out[slot],
-                            static_cast<size_t>(nb) * row_out, cudaMemcpyDeviceToHost, s));
+    return BHMEL_OK;
+  };
+  const int rc = enqueue();
+  cudaError_t sync_err = cudaSuccess;
+  for (int i = 0; i < kHostSlots; ++i) {
+    const cudaError_t e = cudaStreamSynchronize(h->hs[i]);
+    if (e != cudaSuccess && sync_err == cudaSuccess) sync_err = e;
   }
-  for (int i = 0; i < kHostSlots; ++i) BH_CUDA(cudaStreamSynchronize(h->hs[i]));
+  if (rc != BHMEL_OK) return rc;      // bhmel_last_error() already holds the first failure
+  if (sync_err != cudaSuccess) return fail(BHMEL_ECUDA, std::string("bhmel_forward_host: ") + cudaGetErrorString(sync_err));
   return BHMEL_OK;
+}
+
+int64_t bhmel_host_chunk_plan(int64_t B, int64_t N, int32_t x_dtype, int64_t* rows_out, int64_t cap) {
+  if (B <= 0 || N <= 0 || (x_dtype != BHMEL_IN_F32 && x_dtype != BHMEL_IN_PCM16)) return 0;
+  const bool pcm = x_dtype == BHMEL_IN_PCM16;
+  const std::vector<int64_t> c = host_chunk_rows(B, static_cast<size_t>(N) * (pcm ? sizeof(int16_t) : sizeof(float)), pcm);
+  for (size_t i = 0; i < c.size() && rows_out && static_cast<int64_t>(i) < cap; ++i) rows_out[i] = c[i];
+  return static_cast<int64_t>(c.size());
 }
 
 int bhmel_forward_host(bhmel_handle* h, const float* x_host, int64_t B, int64_t N, int64_t x_row_stride,

@@ -356,6 +356,16 @@ class MelSpectrogram(nn.Module):
         for h in self._handles.values():
             _lib.check(_lib.lib().bhmel_set_option(h, _lib.OPT_STATIC_MEL, int(self._static_mel)))
 
+    @staticmethod
+    def host_chunk_plan(batch: int, n_samples: int, pcm16: bool = False) -> list:
+        """Rows per chunk of one forward_host call (bhmel_host_chunk_plan, include/bhmel.h): what a benchmark
+        needs to time plain copies in the entry's own pattern."""
+        lib = _lib.lib()
+        n = int(lib.bhmel_host_chunk_plan(batch, n_samples, _lib.IN_PCM16 if pcm16 else _lib.IN_F32, None, 0))
+        buf = (ctypes.c_int64 * max(n, 1))()
+        lib.bhmel_host_chunk_plan(batch, n_samples, _lib.IN_PCM16 if pcm16 else _lib.IN_F32, buf, n)
+        return [int(buf[i]) for i in range(n)]
+
     def set_pdl(self, enabled: bool) -> None:
         """A-B switch: programmatic dependent launch of the fused kernel (default on; BHMEL_OPT_PDL in
         include/bhmel.h).  Results and stream-order semantics do not depend on it."""

@@ -363,16 +363,19 @@ def run_ours(args):
     del host_in
 
     # ---- plain-copy ceiling of this host for the SAME bytes: every rank at once, the host entry's own pattern
-    #      (row chunks of ~32 MB round-robin over 3 streams, one cudaMemcpyAsync H2D and one D2H per chunk,
-    #      no kernel in between), pinned buffers.  e2e can at best equal this figure.
-    def copy_ceiling(h_in, h_out, d_in, d_out, n_steps):
+    #      (bhmel_host_chunk_plan's row chunks round-robin over 3 streams, one cudaMemcpyAsync H2D and one D2H
+    #      per chunk, no kernel in between), pinned buffers.  e2e can at best equal this figure.
+    def copy_ceiling(h_in, h_out, d_in, d_out, n_steps, pcm16=False):
         streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
-        rows = max(1, min(BATCH, (32 << 20) // (WINDOW * 4)))       # bhmel_forward_host_ex: ~32 MB of fp32 rows per chunk
+        plan = MelSpectrogram.host_chunk_plan(BATCH, WINDOW, pcm16=pcm16)
+        assert sum(plan) == BATCH
         def one_step():
-            for k, b0 in enumerate(range(0, BATCH, rows)):
+            b0 = 0
+            for k, rows in enumerate(plan):
                 with torch.cuda.stream(streams[k % 3]):
                     d_in[b0:b0 + rows].copy_(h_in[b0:b0 + rows], non_blocking=True)
                     h_out[b0:b0 + rows].copy_(d_out[b0:b0 + rows], non_blocking=True)
+                b0 += rows
         one_step()
         barrier()
         t0 = time.perf_counter()
@@ -404,7 +407,7 @@ def run_ours(args):
     typed_t, typed_audio = reduce_over_ranks(time.perf_counter() - t0, n_typed * BATCH * WINDOW / SR)
     d_pcm = torch.empty(BATCH, WINDOW, dtype=torch.int16, device=dev)
     d_out16 = torch.empty(BATCH, FRAMES, N_MELS, dtype=torch.bfloat16, device=dev)
-    cc16_t, cc16_audio = copy_ceiling(pcm, out16, d_pcm, d_out16, max(3, n_typed // 2))
+    cc16_t, cc16_audio = copy_ceiling(pcm, out16, d_pcm, d_out16, max(3, n_typed // 2), pcm16=True)
     e2e_typed = {"value": typed_audio / typed_t, "unit": UNIT, "input": "int16 PCM + per-row scale",
                  "output": "bfloat16", "h2d_bytes_per_step": BATCH * WINDOW * 2,
                  "d2h_bytes_per_step": BATCH * FRAMES * N_MELS * 2, "n_gpus_measured": world,

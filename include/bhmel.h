@@ -169,6 +169,14 @@ int bhmel_forward_gather_pcm16(bhmel_handle* h, const int16_t* song_dev, int64_t
 int bhmel_forward_host(bhmel_handle* h, const float* x_host, int64_t B, int64_t N,
                        int64_t x_row_stride, float* y_host);
 
+/* The row chunks bhmel_forward_host / bhmel_forward_host_ex split a [B][N] batch into (x_dtype BHMEL_IN_F32 or
+ * BHMEL_IN_PCM16): chunk i covers rows_out[i] consecutive rows; chunks go round-robin over the handle's private
+ * streams, each as one host->device copy, the kernel(s), one device->host copy.  Returns the number of chunks
+ * (0 for invalid arguments) and fills at most `cap` entries; rows_out may be NULL.  Pure host arithmetic -- it
+ * exists so that a benchmark can time plain copies in exactly the pattern the entry uses (bench.py,
+ * e2e.plain_copy_ceiling). */
+int64_t bhmel_host_chunk_plan(int64_t B, int64_t N, int32_t x_dtype, int64_t* rows_out, int64_t cap);
+
 /* Tuning / debugging switches (per handle).  BHMEL_OPT_BULK_COPY: 1 (default) stages aligned
  * interior tiles with the TMA bulk copy, 0 forces the per-element cp.async path everywhere. */
 #define BHMEL_OPT_BULK_COPY 1

@@ -70,6 +70,28 @@ def test_num_frames(lib):
     assert lib.bhmel_num_frames(None, 513) == 5
 
 
+def test_host_chunk_plan_covers_the_batch_exactly_once(lib):
+    """bhmel_host_chunk_plan is pure host arithmetic: the chunks of a host-buffer call tile the batch, the taper
+    at both ends is symmetric, no chunk is larger than the steady-state one, invalid arguments give 0."""
+    from beatheritage_b200 import MelSpectrogram
+    for pcm in (False, True):
+        for B in (1, 2, 3, 5, 6, 7, 8, 15, 16, 46, 47, 48, 49, 100, 255, 256, 257, 1090, 24576):
+            for N in (513, 160000, 524160, 524161, 5_000_000):
+                plan = MelSpectrogram.host_chunk_plan(B, N, pcm16=pcm)
+                assert sum(plan) == B and min(plan) >= 1
+                big = max(plan)
+                if len(plan) > 8:
+                    k = next(i for i, r in enumerate(plan) if r == big)
+                    assert plan[:k] == plan[::-1][:k]                   # symmetric taper
+                    assert all(plan[i] < plan[i + 1] for i in range(k))
+    assert lib.bhmel_host_chunk_plan(0, 100, 0, None, 0) == 0
+    assert lib.bhmel_host_chunk_plan(4, 0, 0, None, 0) == 0
+    assert lib.bhmel_host_chunk_plan(4, 100, 7, None, 0) == 0
+    # the 256-window bench batch: 8 fp32 / 32 int16 windows per steady-state chunk
+    assert max(MelSpectrogram.host_chunk_plan(256, 524160)) == 8
+    assert max(MelSpectrogram.host_chunk_plan(256, 524160, pcm16=True)) == 32
+
+
 def test_sass_is_sm100_and_uses_tma_bulk_copy():
     """The built library must carry sm_100a SASS with the TMA bulk copy (UBLKCP) in it."""
     import shutil

@@ -445,6 +445,29 @@ def test_forward_host_pcm16_and_bf16(mods, dev):
     assert parity_error(y[:2].numpy(), ref, True) < TARGET
 
 
+def test_forward_host_tapered_chunk_plan(mods, dev):
+    """Batches large enough for the host entry's tapered chunk schedule (1/8, 1/4, 1/2 chunks at both ends,
+    bhmel_host_chunk_plan): every row lands where the device-resident forward puts it, f32 and int16 ingest."""
+    from beatheritage_b200 import MelSpectrogram
+    m = mods["P0"]
+    B, N = 53, 524161
+    plan = MelSpectrogram.host_chunk_plan(B, N)
+    assert plan[:3] == [1, 2, 4] and plan[-3:] == [4, 2, 1] and sum(plan) == B
+    g = torch.Generator().manual_seed(17)
+    x = (torch.rand(B, N, generator=g) * 2 - 1).pin_memory()
+    y_dev = m(x.to(dev)).cpu()
+    assert torch.equal(m.forward_host(x), y_dev)
+    del x, y_dev
+    B, N = 27, 4_000_003
+    plan = MelSpectrogram.host_chunk_plan(B, N, pcm16=True)
+    assert plan[0] < max(plan) and plan[-1] < max(plan) and sum(plan) == B
+    pcm = torch.randint(-30000, 30000, (B, N), dtype=torch.int16, generator=g)
+    scales = torch.full((B,), 1.0 / 30000.0)
+    y_ref = m((pcm.to(torch.float32) * scales[:, None]).to(dev)).to(torch.bfloat16).cpu()
+    y = m.forward_host(pcm.pin_memory(), scales=scales, out_dtype=torch.bfloat16)
+    assert torch.equal(y, y_ref)
+
+
 def test_properties_at_full_size(mods, dev):
     """Size-independent properties on a [64, 524160] batch (no oracle needed at this size):
     batch independence, determinism, power scaling (non-log set), zero rows, time shift."""
