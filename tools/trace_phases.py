@@ -26,9 +26,11 @@ from beatheritage_b200 import MelSpectrogram, _lib  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "trace.json"))
 ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--static-mel", type=int, default=1, help="BHMEL_OPT_STATIC_MEL (0: generic mel stage)")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 mel = MelSpectrogram("torchaudio", True, 16000, 1024, 80, 128, 20, 8000, "reflect").to(dev)
+mel.set_static_mel(args.static_mel)
 x = torch.rand(args.batch, 524160, device=dev) * 2 - 1
 for _ in range(3):
     y = mel(x)
