@@ -541,7 +541,7 @@ def run_ours(args):
                          "note": "fp32 CUDA-core FFT: the FP32 issue rate, not HBM, bounds this kernel (DESIGN.md)",
                          "static_from": "profiles/traffic.json (one ncu --set full capture of this kernel, not live): "
                                         "traffic, ncu_issue_slots_busy_pct, ncu_warp_instructions_per_launch",
-                         "ncu_capture": ncu_facts.get("capture"),
+                         "ncu_capture": (f"{ncu_facts.get('kernel')} -- profiles/{ncu_facts.get('source')}" if ncu_facts else None),
                          "ncu_issue_slots_busy_pct": ncu_facts.get("issue_slots_busy_pct"),
                          "ncu_warp_instructions_per_launch": ncu_facts.get("warp_instructions_per_launch")},
             "cpu_baseline": cpu,
