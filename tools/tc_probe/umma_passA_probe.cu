@@ -172,8 +172,10 @@ __device__ void teardown(Smem& S, int tid) {
 
 // ------------------------------------------------------------------ T1 / T3: MMA rate, optional LDS stream
 // amode 0: A = overlapped MN-major SW64 span; 1: A = K-major SW128 block.  lds_warps: how many of warps 1-7 stream LDS.128.
-template <int N>
-__global__ void __launch_bounds__(kThreads, 1) k_mma_rate(Args a, int amode, int lds_warps, int slot) {
+// bmode 0: B = the small K-major DFT block; 1 (T5): B = the overlapped MN-major SW64 span (N = 32 b x N/32 frames,
+// the transposed formulation: DFT matrix on the M side, samples on the N side), A K-major; M = 128 or 64.
+template <int N, int M = 128>
+__global__ void __launch_bounds__(kThreads, 1) k_mma_rate(Args a, int amode, int lds_warps, int slot, int bmode = 0) {
   extern __shared__ __align__(1024) unsigned char raw[];
   Smem& S = *reinterpret_cast<Smem*>(raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mma_rate(Args a, int amode, int
   float sink = 0.f;
   __syncthreads();
   if (tid == 0) {
-    const uint32_t idesc = make_idesc(128, N, amode == 0 ? 1 : 0, 0);
+    const uint32_t idesc = make_idesc(M, N, amode == 0 ? 1 : 0, bmode);
     const uint32_t xa = smem_u32(S.xh), ka = smem_u32(S.kmaj), wa = smem_u32(S.W);
     const long long t0 = clock64();
     for (int i = 0; i < burst; ++i) {
@@ -192,7 +194,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_mma_rate(Args a, int amode, int
                                      : make_desc(ka + (i & 3) * 32, 16, 1024, 2);
       // B: N rows x 16 k, K-major no swizzle, [n/8][k/8][8][8]: LBO = 128 (k chunk), SBO = 512 (n group).
       // For N > 96 the operand runs past the 6 KB of W into the T ring: garbage values, same traffic.
-      const uint64_t bd = make_desc(wa + (i & 1) * 256, 128, 512, 0);
+      const uint64_t bd = bmode == 0 ? make_desc(wa + (i & 1) * 256, 128, 512, 0)
+                                     : make_desc(xa + (i & 7) * 1024, 256, 512, 4);
       umma_f16(taddr, ad, bd, idesc, 1u);
     }
     umma_commit(smem_u32(&S.done));
@@ -446,11 +449,13 @@ int main(int argc, char** argv) {
 
 #define SET_SMEM(k) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)))
   SET_SMEM(k_mma_rate<32>); SET_SMEM(k_mma_rate<64>); SET_SMEM(k_mma_rate<128>); SET_SMEM(k_mma_rate<256>);
+  SET_SMEM((k_mma_rate<256, 64>)); SET_SMEM((k_mma_rate<128, 64>)); SET_SMEM((k_mma_rate<64, 64>));
   SET_SMEM(k_tmem_rate);
   SET_SMEM((k_pass_a<0, 0>)); SET_SMEM((k_pass_a<0, 1>)); SET_SMEM((k_pass_a<1, 0>)); SET_SMEM((k_pass_a<1, 1>));
 
   long long cyc[64 * 4 / 4 * 4];
   auto fetch = [&]() {
+    CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(cyc, d_cyc, 64 * 8, cudaMemcpyDeviceToHost));
   };
@@ -468,6 +473,23 @@ int main(int argc, char** argv) {
       printf("T1 %s A, M=128 N=%3d K=16 f16 SS: %.1f cycles / MMA (tensor floor %d, operand bytes %d -> %.1f at 128 B/clk)\n",
              amode == 0 ? "MN-major SW64 overlapped" : "K-major SW128          ", Ns[i], cyc[i * 4] / 512.0, Ns[i] / 2,
              4096 + Ns[i] * 32, (4096 + Ns[i] * 32) / 128.0);
+  }
+  // ---- T5: the transposed formulation (DFT matrix = A, K-major; samples = B through the overlapped MN-major span)
+  {
+    k_mma_rate<256, 128><<<sms, kThreads, smem>>>(b, 1, 0, 0, 1);
+    k_mma_rate<128, 128><<<sms, kThreads, smem>>>(b, 1, 0, 1, 1);
+    k_mma_rate<256, 64><<<sms, kThreads, smem>>>(b, 1, 0, 2, 1);
+    k_mma_rate<128, 64><<<sms, kThreads, smem>>>(b, 1, 0, 3, 1);
+    fetch();
+    const int Ns[4] = {256, 128, 256, 128}, Ms[4] = {128, 128, 64, 64};
+    for (int i = 0; i < 4; ++i)
+      printf("T5 A = K-major SW128 DFT block, B = MN-major SW64 overlapped span, M=%3d N=%3d K=16 f16 SS: %.1f cycles / MMA "
+             "(tensor floor %d; %d frames per MMA)\n", Ms[i], Ns[i], cyc[i * 4] / 512.0, Ns[i] / 2 * Ms[i] / 128, Ns[i] / 32);
+    k_mma_rate<256, 128><<<sms, kThreads, smem>>>(b, 1, 7, 0, 1);
+    k_mma_rate<256, 64><<<sms, kThreads, smem>>>(b, 1, 7, 1, 1);
+    fetch();
+    printf("T5 the same next to 7 LDS warps: M=128 N=256 %.1f cycles / MMA, M=64 N=256 %.1f (LDS warp: %.2f / %.2f cycles per LDS.128)\n",
+           cyc[0] / 512.0, cyc[4] / 512.0, cyc[1] / (512.0 * 16), cyc[5] / (512.0 * 16));
   }
   // ---- T3
   for (int lw = 0; lw <= 7; lw += (lw == 0 ? 1 : 3)) {
