@@ -263,3 +263,47 @@ def test_programmatic_dependent_launch_keeps_stream_order(dev):
     torch.cuda.synchronize()
     for y in ys[1:]:
         assert torch.equal(y, ys[0])
+
+
+def test_cuda_graph_capture_of_the_serving_chain(dev):
+    """The serving loop of one model-context window -- frontend + encoder-input assembly + conv stem, four
+    launches, two of them programmatic dependents -- captured ONCE in a CUDA graph and replayed on new audio in
+    the same buffers gives the bits of the eager calls: the C ABI makes no allocation, no synchronisation and
+    no host-side state change per call, so it is capturable as it stands."""
+    from beatheritage_b200 import MelSpectrogram
+    from tests.golden import signals
+    mel = MelSpectrogram("torchaudio", True, 16000, 1024, 80, 128, 20, 8000, "reflect").to(dev)
+    stem = make_stem(464, 768, dev, seed=5)
+    torch.manual_seed(2)
+    cond = torch.randn(1, 384, device=dev)
+    x = torch.zeros(1, 524160, device=dev)
+    songs = [torch.from_numpy(signals.music(524160, seed=s).reshape(1, 524160)).to(dev) for s in (21, 22, 23)]
+    hidden = torch.empty(1, 4096, 768, dtype=torch.bfloat16, device=dev)
+    out = torch.empty(1, 2048, 768, dtype=torch.bfloat16, device=dev)
+
+    def chain():
+        enc_in = mel.forward_encoder_input(x, [cond], dtype=torch.bfloat16, channels_first=False)
+        return stem(enc_in, hidden=hidden, out=out)
+
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):                 # handles, scratch and lazy state exist before the capture
+        x.copy_(songs[0])
+        for _ in range(3):
+            chain()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    before = (mel.launch_count(), stem.launch_count())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        y = chain()
+    assert y.data_ptr() == out.data_ptr()
+    for song in songs:
+        x.copy_(song)
+        graph.replay()
+        replayed = out.clone()
+        eager = chain().clone()
+        torch.cuda.synchronize()
+        assert torch.equal(replayed, eager)
+        assert bool(torch.isfinite(replayed.float()).all()) and float(replayed.float().abs().max()) > 0
+    assert mel.launch_count() > before[0] and stem.launch_count() > before[1]

@@ -251,7 +251,27 @@ def run_c5(ctx):
                 fr_btc = mel.forward_encoder_input(xd, [cvec], channels_first=False)
                 fr_bct = fr_btc.swapaxes(1, 2).contiguous()
                 a, b = ref_ops().float(), ours().float()
+                # the same chain captured once in a CUDA graph (the serving loop: no host work per call)
+                graph_ms = None
+                try:
+                    side = torch.cuda.Stream(device=dev)
+                    side.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(side):
+                        for _ in range(3):
+                            ours()
+                    torch.cuda.current_stream(dev).wait_stream(side)
+                    torch.cuda.synchronize()
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        g_out = ours()
+                    graph.replay()
+                    torch.cuda.synchronize()
+                    if torch.equal(g_out.float(), b):
+                        graph_ms = timed(graph.replay, 50)
+                except Exception as e:  # noqa: BLE001
+                    graph_ms = f"unavailable: {type(e).__name__}: {e}"
                 stem_res[mode] = {
+                    "ours_frontend_to_stem_cuda_graph_ms": graph_ms,
                     "reference_ops_frontend_to_stem_ms": timed(ref_ops, 20),
                     "ours_frontend_to_stem_ms": timed(ours, 20),
                     "stem_only_torch_cudnn_ms": timed(lambda: ref_stem_only(fr_bct), 20),
