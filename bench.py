@@ -377,13 +377,18 @@ def run_ours(args):
                     h_out[b0:b0 + rows].copy_(d_out[b0:b0 + rows], non_blocking=True)
                 b0 += rows
         one_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(n_steps):
-            one_step()
-        torch.cuda.synchronize(dev)
-        dt = time.perf_counter() - t0
-        return reduce_over_ranks(dt, n_steps * BATCH * WINDOW / SR)
+        best = None
+        for _ in range(3):          # a ceiling: the best of three rounds (host-memory traffic of the box varies)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_steps):
+                one_step()
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+            t, audio = reduce_over_ranks(dt, n_steps * BATCH * WINDOW / SR)
+            if best is None or audio / t > best[1] / best[0]:
+                best = (t, audio)
+        return best
 
     d_out32 = torch.empty(BATCH, FRAMES, N_MELS, dtype=torch.float32, device=dev)
     host_in1 = torch.empty(BATCH, WINDOW, dtype=torch.float32, pin_memory=True)
@@ -532,7 +537,7 @@ def run_ours(args):
                     "plain_copy_ceiling": copy_ceiling_f32,
                     "plain_copy_ceiling_is": f"the same {BATCH * WINDOW * 4 + BATCH * FRAMES * N_MELS * 4} bytes per step per rank as plain pinned "
                                              f"cudaMemcpyAsync H2D + D2H in the host entry's chunk pattern, no kernel, all {world} rank(s) at once, "
-                                             "expressed in audio-s/s",
+                                             "best of 3 rounds, expressed in audio-s/s",
                     "fraction_of_plain_copy_ceiling": (e2e_audio / e2e_t) / copy_ceiling_f32},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
