@@ -820,3 +820,48 @@ def test_programmatic_dependent_launch_keeps_stream_order(mods, dev):
         m.set_pdl(True)
     for a, b in zip(with_pdl, without):
         assert torch.equal(a, b)
+
+
+def test_non_finite_and_extreme_samples(mods, dev):
+    """What a NaN / Inf / huge sample does (the reference just propagates IEEE arithmetic through stft, the
+    filterbank matmul and log1p): every frame whose 1024-sample span holds the bad sample is non-finite in the
+    reference and here; frames that do not touch it keep their oracle values.  Two frames share one complex
+    FFT here, so a bad frame's partner frame (the one just before or after the affected run) may turn
+    non-finite as well -- at most one extra frame at each end, documented in INTEGRATION.md.  Samples so large
+    that the power overflows give +inf on both sides (log1p(inf) = inf), never NaN."""
+    import warnings
+    m = mods["P0"]
+    N = 40000
+    T = N // 128 + 1
+    window, fb = load_params("P0")
+    for bad, pos in ((np.nan, 20000), (np.inf, 13), (-np.inf, 39990), (np.nan, 128 * 100 + 512)):
+        x = signals.noise(2, N, 5).copy()
+        x[1, pos] = bad
+        with warnings.catch_warnings(), np.errstate(all="ignore"):
+            warnings.simplefilter("ignore")
+            ref = mel_oracle.mel_forward(x, fb=fb, window=window, dtype=np.float64)
+        got = run(m, x, dev)
+        assert np.isfinite(got[0]).all() and parity_error(got[:1], ref[:1], True) < TARGET      # the clean row
+        ref_bad = ~np.isfinite(ref[1]).all(axis=1)            # frames the reference poisons
+        got_bad = ~np.isfinite(got[1]).all(axis=1)
+        assert ref_bad.sum() >= 4
+        assert np.all(got_bad[ref_bad]), "a frame the reference poisons is finite here"
+        # every mel of a poisoned frame is non-finite on both sides
+        assert (~np.isfinite(got[1][ref_bad])).all() and (~np.isfinite(ref[1][ref_bad])).all()
+        extra = np.flatnonzero(got_bad & ~ref_bad)
+        first, last = np.flatnonzero(ref_bad)[[0, -1]]
+        assert len(extra) <= 2 and all(t in (first - 1, last + 1) for t in extra), extra
+        ok = ~got_bad
+        assert parity_error(got[1][ok][None], ref[1][ok][None], True) < TARGET
+    # overflow: a mel value beyond float32 is +inf (log1p(inf) = inf), never NaN; values short of the limit stay finite
+    x = signals.noise(1, N, 6).copy()
+    x[0, 20000] = 3e19
+    got = run(m, x, dev)
+    with np.errstate(all="ignore"):
+        lin64 = np.expm1(mel_oracle.mel_forward(x, fb=fb, window=window, dtype=np.float64))
+    over = lin64[0] > 4 * float(np.finfo(np.float32).max)           # clearly past the float32 range
+    under = lin64[0] < 0.25 * float(np.finfo(np.float32).max)
+    assert over.sum() > 100 and not np.isnan(got).any()
+    assert np.isposinf(got[0][over]).all()
+    assert np.isfinite(got[0][under]).all()
+    assert T == got.shape[1]
