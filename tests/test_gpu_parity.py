@@ -865,3 +865,29 @@ def test_non_finite_and_extreme_samples(mods, dev):
     assert np.isposinf(got[0][over]).all()
     assert np.isfinite(got[0][under]).all()
     assert T == got.shape[1]
+
+
+def test_one_call_larger_than_int32_element_counts(mods, dev):
+    """Maximum sizes: ONE call over 7 000 model-context windows -- 3.67e9 input samples and 2.29e9 output
+    values, both past 2^31 (the input also past 2^32 bytes by a wide margin) -- must index with 64 bits
+    everywhere.  Rows on both sides of the 2^31-element boundaries (input row 4097, output row 6553), the
+    first and the last row equal the same rows computed alone."""
+    free, _ = torch.cuda.mem_get_info(dev)
+    B, N = 7000, 524160
+    need = B * N * 4 + B * 4096 * 80 * 4
+    if free < need * 1.15:
+        pytest.skip(f"needs {need / 2**30:.1f} GiB of device memory")
+    m = mods["P0"]
+    g = torch.Generator(device=dev).manual_seed(99)
+    x = torch.empty(B, N, device=dev)
+    for b0 in range(0, B, 500):                         # filled in slices: torch's RNG kernels index with 32 bits
+        x[b0:b0 + 500].uniform_(-1, 1, generator=g)
+    y = m(x)
+    torch.cuda.synchronize()
+    assert y.shape == (B, 4096, 80) and y.numel() > 2 ** 31 and x.numel() > 2 ** 31
+    for r in (0, 1, 4095, 4096, 4097, 4098, 6552, 6553, 6554, B - 2, B - 1):
+        alone = m(x[r:r + 1].clone())
+        assert torch.equal(y[r], alone[0]), f"row {r}"
+    assert bool(torch.isfinite(y[::97]).all())
+    del x, y
+    torch.cuda.empty_cache()

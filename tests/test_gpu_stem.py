@@ -307,3 +307,29 @@ def test_cuda_graph_capture_of_the_serving_chain(dev):
         assert torch.equal(replayed, eager)
         assert bool(torch.isfinite(replayed.float()).all()) and float(replayed.float().abs().max()) > 0
     assert mel.launch_count() > before[0] and stem.launch_count() > before[1]
+
+
+def test_one_call_larger_than_int32_element_counts(dev):
+    """Maximum sizes: 700 windows in one call -- the hidden activations are 2.2e9 bf16 values (past 2^31
+    elements, 4.4 GB), the input 1.33e9, the output 1.1e9 -- rows around the boundary and at both ends equal the
+    same windows computed alone (the CTA-pair kernel is deterministic and batch-independent)."""
+    B, T, C, D = 700, 4096, 464, 768
+    need = 2 * (B * T * C + B * T * D + B * (T // 2) * D)
+    free, _ = torch.cuda.mem_get_info(dev)
+    if free < need * 1.2:
+        pytest.skip(f"needs {need / 2**30:.1f} GiB of device memory")
+    stem = make_stem(C, D, dev, seed=8)
+    g = torch.Generator(device=dev).manual_seed(5)
+    x = torch.empty(B, T, C, dtype=torch.bfloat16, device=dev)
+    for b0 in range(0, B, 100):
+        x[b0:b0 + 100] = (torch.randn(min(100, B - b0), T, C, device=dev, generator=g) * 1.5).to(torch.bfloat16)
+    hidden = torch.empty(B, T, D, dtype=torch.bfloat16, device=dev)
+    assert hidden.numel() > 2 ** 31
+    y = stem(x, hidden=hidden)
+    torch.cuda.synchronize()
+    for r in (0, 1, 340, 341, 342, 682, 683, B - 1):       # 2^31 / (4096 * 768) = 682.67: hidden row 682 straddles it
+        alone = stem(x[r:r + 1].contiguous())
+        assert torch.equal(y[r], alone[0]), f"window {r}"
+    assert bool(torch.isfinite(y[::53].float()).all())
+    del x, y, hidden
+    torch.cuda.empty_cache()
