@@ -66,6 +66,17 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// kind::tf32 (A = B = TF32, D = F32): the shape of the dense mel projection (stage 3), K = 8 per instruction
+__device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -222,6 +233,35 @@ __global__ void __launch_bounds__(kThreads, 1) k_mma_rate(Args a, int amode, int
     if (tid == 32) a.cycles[slot * 4 + 1] = t_lds;
     if (sink == 12345.678f) a.cycles[63] = 1;
   }
+  teardown(S, tid);
+}
+
+// ------------------------------------------------------------------ T6: the dense mel projection's MMA (stage 3)
+// A = 128 frames x 8 power bins (K-major SW128, as a [frames][bins] power tile would be staged), B = N mel filters x 8
+// bins (K-major), kind::tf32.  Timing only (operands are whatever the buffers hold).
+template <int N>
+__global__ void __launch_bounds__(kThreads, 1) k_mel_mma_rate(Args a, int slot) {
+  extern __shared__ __align__(1024) unsigned char raw[];
+  Smem& S = *reinterpret_cast<Smem*>(raw);
+  const int tid = threadIdx.x;
+  setup(S, a, tid);
+  const uint32_t taddr = S.tmem_base;
+  long long t_mma = 0;
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_tf32(128, N);
+    const uint32_t ka = smem_u32(S.kmaj), wa = smem_u32(S.W);
+    const long long t0 = clock64();
+    for (int i = 0; i < a.reps; ++i) {
+      const uint64_t ad = make_desc(ka + (i & 3) * 32, 16, 1024, 2);
+      const uint64_t bd = make_desc(wa + (i & 1) * 256, 128, 512, 0);
+      umma_tf32(taddr, ad, bd, idesc, 1u);
+    }
+    umma_commit(smem_u32(&S.done));
+    mbar_wait(smem_u32(&S.done), 0);
+    t_mma = clock64() - t0;
+  }
+  if (blockIdx.x == 0 && tid == 0) a.cycles[slot * 4 + 0] = t_mma;
   teardown(S, tid);
 }
 
@@ -450,6 +490,7 @@ int main(int argc, char** argv) {
 #define SET_SMEM(k) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)))
   SET_SMEM(k_mma_rate<32>); SET_SMEM(k_mma_rate<64>); SET_SMEM(k_mma_rate<128>); SET_SMEM(k_mma_rate<256>);
   SET_SMEM((k_mma_rate<256, 64>)); SET_SMEM((k_mma_rate<128, 64>)); SET_SMEM((k_mma_rate<64, 64>));
+  SET_SMEM(k_mel_mma_rate<80>); SET_SMEM(k_mel_mma_rate<128>); SET_SMEM(k_mel_mma_rate<256>);
   SET_SMEM(k_tmem_rate);
   SET_SMEM((k_pass_a<0, 0>)); SET_SMEM((k_pass_a<0, 1>)); SET_SMEM((k_pass_a<1, 0>)); SET_SMEM((k_pass_a<1, 1>));
 
@@ -490,6 +531,19 @@ int main(int argc, char** argv) {
     fetch();
     printf("T5 the same next to 7 LDS warps: M=128 N=256 %.1f cycles / MMA, M=64 N=256 %.1f (LDS warp: %.2f / %.2f cycles per LDS.128)\n",
            cyc[0] / 512.0, cyc[4] / 512.0, cyc[1] / (512.0 * 16), cyc[5] / (512.0 * 16));
+  }
+  // ---- T6: dense mel projection on the tensor pipe (north_star stage 3): [128 frames x 520 bins] x [520 x n_mels], TF32
+  {
+    k_mel_mma_rate<80><<<sms, kThreads, smem>>>(b, 0);
+    k_mel_mma_rate<128><<<sms, kThreads, smem>>>(b, 1);
+    k_mel_mma_rate<256><<<sms, kThreads, smem>>>(b, 2);
+    fetch();
+    const int Ns[3] = {80, 128, 256};
+    for (int i = 0; i < 3; ++i) {
+      const double c = cyc[i * 4] / 512.0;
+      printf("T6 kind::tf32 SS, M=128 (frames) N=%3d (mels) K=8 (bins), A K-major SW128: %.1f cycles / MMA -> dense mel GEMM = 65 K-steps "
+             "x 3 (hi/lo split) = %.0f cycles / 128 frames = %.1f cycles / frame / SM\n", Ns[i], c, 65 * 3 * c, 65 * 3 * c / 128.0);
+    }
   }
   // ---- T3
   for (int lw = 0; lw <= 7; lw += (lw == 0 ? 1 : 3)) {
