@@ -46,6 +46,22 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+def fp32_roof(frames_per_s: float, clocks: dict) -> dict:
+    """Achieved algorithmic fp32 throughput of the frontend against the CUDA-core FMA peak of the device at the SM
+    clock sampled under load (148 SMs x 128 lanes x 2 flop; SURVEY.md 8d's second roofline)."""
+    flop_per_frame = 30.5e3
+    try:
+        import torch
+        sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    except Exception:
+        sms = 148
+    mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
+    peak = sms * 128 * 2 * mhz * 1e6 / 1e12
+    achieved = frames_per_s * flop_per_frame / 1e12
+    return {"achieved_tflops": achieved, "peak_tflops": peak, "frac": achieved / peak, "flop_per_frame": flop_per_frame,
+            "sm_mhz": mhz, "sms": sms}
+
+
 def reduce_over_ranks(elapsed: float, units: float):
     """(max over ranks of elapsed, sum over ranks of units).  Works for gloo (CPU) and nccl."""
     import torch
@@ -547,6 +563,10 @@ def run_ours(args):
                          "static_from": "profiles/traffic.json (one ncu --set full capture of this kernel, not live): "
                                         "traffic, ncu_issue_slots_busy_pct, ncu_warp_instructions_per_launch",
                          "ncu_capture": (f"{ncu_facts.get('kernel')} -- profiles/{ncu_facts.get('source')}" if ncu_facts else None),
+                         # the roof that actually binds: ~30.5 kflop of fp32 CUDA-core work per frame
+                         # (real 1024-point FFT 25.6 k, window 1.0 k, power 1.5 k, banded mel 2.0 k, log1p 0.3 k)
+                         # against the FMA peak of the SMs at the clock sampled during the timed region
+                         "fp32": fp32_roof(BATCH * FRAMES / (t_max / args.steps), clock_summary),
                          "ncu_issue_slots_busy_pct": ncu_facts.get("issue_slots_busy_pct"),
                          "ncu_warp_instructions_per_launch": ncu_facts.get("warp_instructions_per_launch")},
             "cpu_baseline": cpu,
