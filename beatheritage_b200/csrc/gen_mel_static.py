@@ -22,6 +22,9 @@ N_WARPS = 8         # warps of the mel role
 M_CHUNK = 96        # filters per output chunk (kMelChunk of bhmel_tables.h)
 STAGE_COLS = 32     # direct form: filters per private staging block (kStageCols of bhmel_kernel_ws.cuh)
 CHAIN1_MAX = 6      # direct form: bands up to this many bins accumulate in one chain, longer ones in two
+PACKED = True       # direct form: a filter's fully covered 4-bin block runs as LDCU.128 (four weights from constant
+                    # memory into uniform registers) + two FFMA2 (packed fp32 pairs: even bin -> chain 0, odd bin ->
+                    # chain 1) instead of four immediate FFMAs: 48 instead of 64 bytes of code, same arithmetic
 STATIC_WARPS = 4    # P0: of which this many run generated code; the rest run the generic stage on the
                     # remaining (highest, widest) filters.  All-static (8) is 28 KB of code and falls
                     # out of the instruction cache next to the FFT role.
@@ -184,6 +187,7 @@ def emit_table_direct(name, n_mels, ent):
     bounds = partition4(filters, N_WARPS)
     n_parts = max((bounds[w + 1] - bounds[w] + STAGE_COLS - 1) // STAGE_COLS for w in range(N_WARPS))
     runs = []
+    wtab = []           # packed form: four weight bit patterns per fully covered (filter, block)
     L = [f"// {name}: {n_mels} filters, {len(ent)} non-zero weights; direct form, warp runs {bounds}, {n_parts} part(s)",
          f"constexpr int kParts{name} = {n_parts};"]
     body = [f"__device__ __forceinline__ void mel_direct_{name}(const float4* __restrict__ prow, float* __restrict__ srow, int mw, int part) {{",
@@ -219,6 +223,22 @@ def emit_table_direct(name, n_mels, ent):
             for g in blocks:
                 body.append(f"{ind}x = prow[{g}];")
                 for f in range(lo, hi):
+                    if PACKED and nch[f] == 2 and all(4 * g + c in filters[f] for c in range(4)):
+                        idx = len(wtab) // 4
+                        wtab += [filters[f][4 * g + c] for c in range(4)]
+                        if (f, 0) not in live and (f, 1) not in live:
+                            body.append(f"{ind}float a{f}_0, a{f}_1; mel_mul2x2(a{f}_0, a{f}_1, x, kWpk{name}[{idx}]);")
+                        else:
+                            for ch in (0, 1):
+                                if (f, ch) not in live:
+                                    body.append(f"{ind}float a{f}_{ch} = 0.f;")
+                            body.append(f"{ind}mel_fma2x2(a{f}_0, a{f}_1, x, kWpk{name}[{idx}]);")
+                        live.add((f, 0))
+                        live.add((f, 1))
+                        if last_block.get(f) == g:
+                            body.append(f"{ind}const float v{f} = a{f}_0 + a{f}_1;")
+                            done.add(f)
+                        continue
                     for c in range(4):
                         k = 4 * g + c
                         if k in filters[f]:
@@ -240,6 +260,16 @@ def emit_table_direct(name, n_mels, ent):
     body += ["    default: break;", "  }", "}", ""]
     L.append(f"static __constant__ unsigned short kRun{name}[{N_WARPS * n_parts}][2] = {{" +
              ", ".join(f"{{{a}, {b}}}" for a, b in runs) + "};")
+    if wtab:
+        import struct
+        vals = [struct.unpack("<f", struct.pack("<I", b))[0] for b in wtab]
+        for b, v in zip(wtab, vals):      # nine significant digits round-trip a float32
+            assert struct.unpack("<I", struct.pack("<f", float(f"{v:.9e}")))[0] == b
+        L.append(f"// {len(wtab) // 4} fully covered blocks run packed ({len(wtab)} of the {len(ent)} weights)")
+        L.append(f"static __constant__ float4 kWpk{name}[{len(wtab) // 4}] = {{")
+        for i in range(0, len(vals), 4):
+            L.append("  {" + ", ".join(f"{v:.9e}f" for v in vals[i:i + 4]) + "},")
+        L.append("};")
     return L + body
 
 
@@ -253,6 +283,39 @@ def main():
     N_WARPS, STATIC_WARPS = args.warps, args.static_warps
     tables = read_baked(os.path.join(HERE, "bhmel_fb_baked.h"))
     L = ["// mel_static_gen.h -- generated by gen_mel_static.py; do not edit.", "#pragma once", "", "namespace bhmel {", ""]
+    L += [
+        "// One fully covered 4-bin block of a two-chain filter: chain 0 += x.x w.x, chain 1 += x.y w.y, then chain 0 += x.z w.z,",
+        "// chain 1 += x.w w.w -- four IEEE fp32 FMAs.  On the device they are two packed fma.rn.f32x2 (SASS FFMA2) whose weight",
+        "// pairs sit in uniform registers loaded by ONE LDCU.128 from constant memory; the host (lane emulator) runs the same",
+        "// four fmaf.  mel_mul2x2 starts both chains (first pair multiplied, not accumulated).",
+        "#ifdef __CUDA_ARCH__",
+        "__device__ __forceinline__ unsigned long long mel_pk(float lo, float hi) {",
+        "  unsigned long long r;",
+        "  asm(\"mov.b64 %0, {%1, %2};\" : \"=l\"(r) : \"f\"(lo), \"f\"(hi));",
+        "  return r;",
+        "}",
+        "__device__ __forceinline__ void mel_fma2x2(float& a0, float& a1, const float4& x, const float4& w) {",
+        "  unsigned long long a = mel_pk(a0, a1);",
+        "  asm(\"fma.rn.f32x2 %0, %1, %2, %0;\" : \"+l\"(a) : \"l\"(mel_pk(x.x, x.y)), \"l\"(mel_pk(w.x, w.y)));",
+        "  asm(\"fma.rn.f32x2 %0, %1, %2, %0;\" : \"+l\"(a) : \"l\"(mel_pk(x.z, x.w)), \"l\"(mel_pk(w.z, w.w)));",
+        "  asm(\"mov.b64 {%0, %1}, %2;\" : \"=f\"(a0), \"=f\"(a1) : \"l\"(a));",
+        "}",
+        "__device__ __forceinline__ void mel_mul2x2(float& a0, float& a1, const float4& x, const float4& w) {",
+        "  unsigned long long a;",
+        "  asm(\"mul.rn.f32x2 %0, %1, %2;\" : \"=l\"(a) : \"l\"(mel_pk(x.x, x.y)), \"l\"(mel_pk(w.x, w.y)));",
+        "  asm(\"fma.rn.f32x2 %0, %1, %2, %0;\" : \"+l\"(a) : \"l\"(mel_pk(x.z, x.w)), \"l\"(mel_pk(w.z, w.w)));",
+        "  asm(\"mov.b64 {%0, %1}, %2;\" : \"=f\"(a0), \"=f\"(a1) : \"l\"(a));",
+        "}",
+        "#else",
+        "inline void mel_fma2x2(float& a0, float& a1, const float4& x, const float4& w) {",
+        "  a0 = fmaf(x.x, w.x, a0); a1 = fmaf(x.y, w.y, a1); a0 = fmaf(x.z, w.z, a0); a1 = fmaf(x.w, w.w, a1);",
+        "}",
+        "inline void mel_mul2x2(float& a0, float& a1, const float4& x, const float4& w) {",
+        "  a0 = x.x * w.x; a1 = x.y * w.y; a0 = fmaf(x.z, w.z, a0); a1 = fmaf(x.w, w.w, a1);",
+        "}",
+        "#endif",
+        "",
+    ] if PACKED else []
     for name, (ident, n_mels, ent) in tables.items():
         if name == "P0":
             L += emit_table(name, n_mels, ent)

@@ -231,7 +231,16 @@ def test_static_mel_generator_covers_each_weight_once(tmp_path):
         all_bits = sorted(int(b) for b in t[fb != 0])
         # direct form (every set): every non-zero weight once, every aligned group of four filters stored once
         body = re.search(rf"void mel_direct_{name}\(.*?\n}}\n", txt, re.S).group(0)
-        assert sorted(int(h, 16) for h in re.findall(r"__uint_as_float\(0x([0-9a-f]+)u\)", body)) == all_bits, name
+        got_bits = [int(h, 16) for h in re.findall(r"__uint_as_float\(0x([0-9a-f]+)u\)", body)]
+        # fully covered blocks run packed: four weights from the constant table kWpk<name>, every entry used once
+        tab = re.search(rf"kWpk{name}\[(\d+)\] = \{{(.*?)\n\}};", txt, re.S)
+        if tab:
+            vals = np.array([float(v.rstrip("f")) for v in re.findall(r"[-+0-9.e]+f", tab.group(2))], dtype=np.float32)
+            assert len(vals) == 4 * int(tab.group(1))
+            used = sorted(int(i) for i in re.findall(rf"kWpk{name}\[(\d+)\]\);", body))
+            assert used == list(range(int(tab.group(1))))
+            got_bits += [int(b) for b in vals.view(np.uint32)]
+        assert sorted(got_bits) == all_bits, name
         staged = re.findall(r"mel_stage4\(srow, (\d+), v(\d+), v(\d+), v(\d+), v(\d+)\);", body)
         assert sorted(int(g[1]) for g in staged) == list(range(0, n_mels, 4))            # every aligned group of four, once
         assert all([int(g[1]) + j for j in range(4)] == [int(v) for v in g[1:]] and int(g[0]) % 4 == 0 and int(g[0]) < 32
