@@ -21,6 +21,8 @@ SIGNATURES = {
     "bhstem_destroy": (None, [_vp]),
     "bhstem_forward": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "bhstem_forward_stage": (ctypes.c_int, [_vp, _i32, _vp, _i64, _i64, _vp, _vp]),
+    "bhstem_prepare_split": (ctypes.c_int, [_vp, _i32]),
+    "bhstem_forward_split": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "bhstem_set_option": (ctypes.c_int, [_vp, _i32, _i64]),
     "bhstem_version": (ctypes.c_int, []),
     "bhstem_last_error": (ctypes.c_char_p, []),

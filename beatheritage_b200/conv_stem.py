@@ -39,6 +39,7 @@ class ConvStem(nn.Module):
         self._handles: dict[int, int] = {}
         self._stamp: dict[int, tuple] = {}
         self._retired: list[int] = []     # handles of superseded parameters: freed with the module, never earlier
+        self._split: dict[int, tuple] = {}  # device -> (handle, n_var) prepared for forward_split
 
     @classmethod
     def from_encoder(cls, encoder: nn.Module) -> "ConvStem":
@@ -49,7 +50,7 @@ class ConvStem(nn.Module):
 
     def __getstate__(self):
         state = self.__dict__.copy()
-        state["_handles"], state["_stamp"], state["_retired"] = {}, {}, []
+        state["_handles"], state["_stamp"], state["_retired"], state["_split"] = {}, {}, [], {}
         return state
 
     def _param_stamp(self) -> tuple:
@@ -83,7 +84,22 @@ class ConvStem(nn.Module):
                 _stem_lib.check(lib.bhstem_set_option(out.value, 2, 0))
             self._handles[idx] = out.value
             self._stamp[idx] = stamp
+            self._split.pop(idx, None)
             return out.value
+
+    def _split_handle_for(self, device: torch.device, n_var: int) -> int:
+        """The handle with its time-varying conv1 channels repacked (bhstem_prepare_split, once per handle)."""
+        h = self._handle_for(device)
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        with _handle_lock:
+            done = self._split.get(idx)
+            if done is not None and done != (h, n_var):
+                raise RuntimeError(f"this ConvStem already runs split with {done[1]} time-varying channels")
+            if done is None:
+                with torch.cuda.device(idx):
+                    _stem_lib.check(_stem_lib.lib().bhstem_prepare_split(h, n_var))
+                self._split[idx] = (h, n_var)
+        return h
 
     VARIANTS = {"tap_boxes": 0, "shared_taps": 1, "cta_pairs": 2}
 
@@ -146,6 +162,48 @@ class ConvStem(nn.Module):
         with torch.cuda.device(x.device):
             stream = torch.cuda.current_stream(x.device).cuda_stream
             _stem_lib.check(_stem_lib.lib().bhstem_forward(h, x.data_ptr(), B, T, hidden.data_ptr(), y.data_ptr(), stream))
+        return y
+
+    @torch.no_grad()
+    def forward_split(self, frames: torch.Tensor, cond: torch.Tensor, hidden: torch.Tensor | None = None,
+                      out: torch.Tensor | None = None) -> torch.Tensor:
+        """The stem on the reference's encoder input WITHOUT building it: `frames` [B, T, n_mels] bf16 (what
+        `MelSpectrogram.forward_into` writes into a dense bf16 buffer) and `cond` [B, C_in - n_mels] bf16, the
+        concatenated conditioning embeddings of each window, which the reference repeats over the T frames
+        (modeling_mapperatorinator.py:368-370) before conv1 (modeling_ropewhisper.py:1206).  Equals
+
+            x = torch.cat([frames, cond.unsqueeze(1).expand(-1, T, -1)], dim=-1)
+            self(x)
+
+        up to the fp32 summation order inside conv1: the time-constant channels are folded into a per-window
+        bias (three small sums per output channel), conv1 multiplies n_mels instead of C_in channels.
+        bhstem_forward_split, include/bhstem.h."""
+        C, D = self.conv1.in_channels, self.conv1.out_channels
+        if frames.dim() != 3 or cond.dim() != 2 or frames.shape[0] != cond.shape[0] or frames.shape[2] + cond.shape[1] != C:
+            raise RuntimeError(f"expected frames [B, T, n] and cond [B, {C} - n], got {tuple(frames.shape)} and {tuple(cond.shape)}")
+        if not (frames.is_cuda and cond.is_cuda and frames.device == cond.device):
+            raise RuntimeError("beatheritage_b200.ConvStem has no CPU path: move the batch to a CUDA (sm_100) device")
+        if frames.dtype != torch.bfloat16 or cond.dtype != torch.bfloat16:
+            raise RuntimeError("ConvStem computes in bfloat16 (the reference model's inference dtype): pass bfloat16 tensors")
+        B, T, n_var = frames.shape
+        if T < 2 or T % 2:
+            raise RuntimeError("the number of frames T must be even")
+        if n_var % 8 or n_var < 8 or cond.shape[1] < 8:
+            raise RuntimeError("the number of time-varying channels must be a multiple of 8 below C_in")
+        frames, cond = frames.contiguous(), cond.contiguous()
+        for name, buf, shape in (("hidden", hidden, (B, T, D)), ("out", out, (B, T // 2, D))):
+            if buf is not None and not (tuple(buf.shape) == shape and buf.dtype == torch.bfloat16 and buf.is_contiguous()
+                                        and buf.device == frames.device):
+                raise RuntimeError(f"{name} must be a contiguous bfloat16 tensor {shape} on {frames.device}")
+        if hidden is None:
+            hidden = torch.empty((B, T, D), dtype=torch.bfloat16, device=frames.device)
+        y = out if out is not None else torch.empty((B, T // 2, D), dtype=torch.bfloat16, device=frames.device)
+        bias3 = torch.empty((B, 3, D), dtype=torch.float32, device=frames.device)
+        h = self._split_handle_for(frames.device, n_var)
+        with torch.cuda.device(frames.device):
+            stream = torch.cuda.current_stream(frames.device).cuda_stream
+            _stem_lib.check(_stem_lib.lib().bhstem_forward_split(h, frames.data_ptr(), cond.data_ptr(), B, T,
+                                                                 bias3.data_ptr(), hidden.data_ptr(), y.data_ptr(), stream))
         return y
 
     @torch.no_grad()

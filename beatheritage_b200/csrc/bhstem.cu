@@ -91,6 +91,10 @@ struct StemProblem {
   int32_t tap_col[3];      // column offset of each tap inside a row of the A view
   int32_t tap_row[3];      // row offset of each tap
   int32_t exp;             // -DBHSTEM_PROFILE builds only (always 0 otherwise): 1 no W loads, 2 no epilogue math / stores, 4 no A loads
+  // Bias addressing (elements).  Plain stages: both 0, one bias row [n_out] for everything.  Split conv1
+  // (bhstem_forward_split): the bias is [batch][3][n_out] -- interior rows, the first row, the last row --
+  // because the folded time-constant channels see the zero padding at the two ends of a window.
+  int32_t bias_batch_stride, bias_edge_stride;
 };
 
 // The C channels of a tap are n16 = ceil(C / 16) MMA steps dealt EVENLY over k_blocks = ceil(n16 / 4)
@@ -317,7 +321,10 @@ __device__ __forceinline__ void epilogue_role(const StemProblem& p, const float*
     const uint32_t as = local & 1, aphase = (local >> 1) & 1;
     const int row0 = mt * tile_rows + row_off + quarter * 32;          // first row of this warp's 32-row slab
     __nv_bfloat16* oslab = out + (static_cast<size_t>(b) * p.rows_out + row0) * p.n_out + nt * BN;
-    const float* brow = bias + nt * BN;
+    const int my_row = row0 + lane;                        // the output row (time step) this lane owns
+    const int edge = my_row == 0 ? 1 : (my_row == p.rows_out - 1 ? 2 : 0);
+    const float* brow = bias + static_cast<size_t>(b) * p.bias_batch_stride + edge * p.bias_edge_stride + nt * BN;
+    BHS_CHECK(p.bias_edge_stride == 0 || (p.bias_batch_stride == 3 * p.bias_edge_stride && p.bias_edge_stride == p.n_out));
 #ifdef BHSTEM_PROFILE
     { const long long t0p = clock64(); mbar_wait(tfull0 + 8 * as, aphase); if (warp == 2 && lane == 0) atomicAdd(&g_prof[5], static_cast<unsigned long long>(clock64() - t0p)); }
 #else
@@ -931,6 +938,61 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
   }
 }
 
+// ------------------------------------------------------------------------------------------ split conv1: folded bias
+// The reference's encoder input is [mel | cond] where the conditioning channels are one vector per window
+// broadcast over its T frames (modeling_mapperatorinator.py:368-370: c.unsqueeze(1).expand(-1, T, -1)).  A
+// convolution is linear in its input channels, so those channels contribute, at every frame,
+//     S_tap[b][n] = sum_c W[tap][n][n_var + c] * cond[b][c]
+// for each tap whose frame exists: all three inside a window, taps 1 and 2 at its first frame (tap 0 reads the
+// zero padding), taps 0 and 1 at its last.  This kernel evaluates the three sums once per (window, output
+// channel) -- the same bf16 x bf16 products the full convolution would add, accumulated in fp32 -- and writes
+//     bias3[b][0][n] = bias[n] + S0 + S1 + S2     interior frames
+//     bias3[b][1][n] = bias[n] + S1 + S2          frame 0
+//     bias3[b][2][n] = bias[n] + S0 + S1          frame T-1
+// which the conv1 epilogue adds to the accumulator of the n_var time-varying channels: 3 * n_var instead of
+// 3 * C products per output element (80 of 464 channels at the reference's dims: 5.8x fewer), and the
+// [B][T][C] encoder input is never materialised.
+// One warp per output channel, 8 channels per CTA, blockIdx.y strides over the windows; 16-byte loads.
+constexpr int BIAS_WARPS = 8;
+__global__ void __launch_bounds__(BIAS_WARPS * 32)
+bhstem_cond_bias_kernel(const __nv_bfloat16* __restrict__ w /* [3][D][C] */, const float* __restrict__ bias,
+                        const __nv_bfloat16* __restrict__ cond /* [B][C - n_var] */, float* __restrict__ bias3,
+                        int batches, int d, int c, int n_var) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * BIAS_WARPS + warp;
+  if (n >= d) return;
+  const int n_cond = c - n_var, vecs = n_cond >> 3;       // n_var % 8 == 0 and C % 8 == 0: whole 16-byte pieces
+  const float bn = bias[n];
+  for (int b = blockIdx.y; b < batches; b += gridDim.y) {
+    float s[3] = {0.f, 0.f, 0.f};
+    const uint4* xrow = reinterpret_cast<const uint4*>(cond + static_cast<size_t>(b) * n_cond);
+    for (int v = lane; v < vecs; v += 32) {
+      const uint4 xv = __ldg(xrow + v);
+      const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+      for (int tap = 0; tap < 3; ++tap) {
+        const uint4 wv = __ldg(reinterpret_cast<const uint4*>(w + (static_cast<size_t>(tap) * d + n) * c + n_var) + v);
+        const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                      // bf16 -> fp32 is a shift; the products are exact in fp32
+          s[tap] = fmaf(__uint_as_float(ww[i] << 16), __uint_as_float(xw[i] << 16), s[tap]);
+          s[tap] = fmaf(__uint_as_float(ww[i] & 0xffff0000u), __uint_as_float(xw[i] & 0xffff0000u), s[tap]);
+        }
+      }
+    }
+#pragma unroll
+    for (int tap = 0; tap < 3; ++tap)
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) s[tap] += __shfl_xor_sync(0xffffffffu, s[tap], off);
+    if (lane == 0) {
+      float* o = bias3 + static_cast<size_t>(b) * 3 * d + n;
+      o[0] = bn + ((s[0] + s[1]) + s[2]);
+      o[d] = bn + (s[1] + s[2]);
+      o[2 * d] = bn + (s[0] + s[1]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host
 thread_local std::string g_err;
 int fail(int code, const std::string& msg) {
@@ -977,6 +1039,10 @@ struct bhstem_handle {
   float *b1 = nullptr, *b2 = nullptr;
   CUtensorMap map_w1, map_w2;
   CUtensorMap map_w1_half, map_w2_half;   // 128-row boxes for the CTA-pair kernel (bn == 256 only)
+  // split conv1 (bhstem_prepare_split): the first n_var input channels of conv1 repacked [3][D][n_var]
+  int32_t n_var = 0;
+  __nv_bfloat16* w1v = nullptr;
+  CUtensorMap map_w1v, map_w1v_half;
   EncodeTiledFn enc = nullptr;
   std::atomic<long long> launches{0};   // the only state forward calls mutate: handles may be shared by threads
   int variant = 1;      // 1: shared taps (row-shifted descriptors, default), 0: one TMA box per tap
@@ -1014,9 +1080,19 @@ cudaError_t launch_kernel(bool pdl, void (*kernel)(KArgs...), int grid, int thre
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// What a launch multiplies with: the packed weights (full and 128-row-box maps), their channel count, and the
+// bias with its addressing (StemProblem::bias_*_stride).
+struct StageSel {
+  int c;
+  const CUtensorMap *map_w, *map_w_half;
+  const float* bias;
+  int32_t bias_batch_stride, bias_edge_stride;
+};
+
 template <int BN>
-int launch_stage(bhstem_handle* h, int stage, const void* in, int64_t B, int64_t T, void* out, cudaStream_t stream) {
-  const int c = stage == 1 ? h->c_in : h->d;
+int launch_stage(bhstem_handle* h, int stage, const StageSel& sel, const void* in, int64_t B, int64_t T, void* out,
+                 cudaStream_t stream) {
+  const int c = sel.c;
   StemProblem p{};
   CUtensorMap map_a;
   int rc;
@@ -1041,6 +1117,8 @@ int launch_stage(bhstem_handle* h, int stage, const void* in, int64_t B, int64_t
   p.c_in = c;
   p.k_blocks = (c + BLOCK_K - 1) / BLOCK_K;
   p.exp = h->exp;
+  p.bias_batch_stride = sel.bias_batch_stride;
+  p.bias_edge_stride = sel.bias_edge_stride;
   const long long tiles = static_cast<long long>(p.batches) * p.m_tiles * p.n_tiles;
   const int grid = static_cast<int>(tiles < h->sms ? tiles : h->sms);
   if (h->variant == 1) {
@@ -1070,8 +1148,7 @@ int launch_stage(bhstem_handle* h, int stage, const void* in, int64_t B, int64_t
       const long long pair_tiles = static_cast<long long>(pp.batches) * pp.m_tiles * pp.n_tiles;
       const int pgrid = 2 * static_cast<int>(pair_tiles < h->sms / 2 ? pair_tiles : h->sms / 2);
       const cudaError_t e = launch_kernel(h->pdl != 0, bhstem_conv_gelu_pair_kernel, pgrid, THREADS_SHARED, PAIR_SMEM_BYTES,
-                                          stream, map_a0, map_a1, stage == 1 ? h->map_w1_half : h->map_w2_half,
-                                          static_cast<const float*>(stage == 1 ? h->b1 : h->b2),
+                                          stream, map_a0, map_a1, *sel.map_w_half, sel.bias,
                                           static_cast<__nv_bfloat16*>(out), pp, st);
       if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
       ++h->launches;
@@ -1079,17 +1156,14 @@ int launch_stage(bhstem_handle* h, int stage, const void* in, int64_t B, int64_t
     }
     auto kernel = bhstem_conv_gelu_shared_kernel<BN>;
     const cudaError_t e = launch_kernel(h->pdl != 0, kernel, grid, THREADS_SHARED, CfgShared<BN>::SMEM_BYTES, stream, map_a0,
-                                        map_a1, stage == 1 ? h->map_w1 : h->map_w2,
-                                        static_cast<const float*>(stage == 1 ? h->b1 : h->b2),
+                                        map_a1, *sel.map_w, sel.bias,
                                         static_cast<__nv_bfloat16*>(out), p, st);
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     ++h->launches;
     return BHSTEM_OK;
   }
   auto kernel = bhstem_conv_gelu_kernel<BN>;
-  const cudaError_t e = launch_kernel(h->pdl != 0, kernel, grid, THREADS, Cfg<BN>::SMEM_BYTES, stream, map_a,
-                                      stage == 1 ? h->map_w1 : h->map_w2,
-                                      static_cast<const float*>(stage == 1 ? h->b1 : h->b2),
+  const cudaError_t e = launch_kernel(h->pdl != 0, kernel, grid, THREADS, Cfg<BN>::SMEM_BYTES, stream, map_a, *sel.map_w, sel.bias,
                                       static_cast<__nv_bfloat16*>(out), p);
   if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
   ++h->launches;
@@ -1206,6 +1280,7 @@ void bhstem_destroy(bhstem_handle* h) {
   cudaFree(h->w2);
   cudaFree(h->b1);
   cudaFree(h->b2);
+  cudaFree(h->w1v);
   delete h;
 }
 
@@ -1229,12 +1304,64 @@ int bhstem_forward_stage(bhstem_handle* h, int32_t stage, const void* in, int64_
   if (rc != BHSTEM_OK) return rc;
   if (stage != 1 && stage != 2) return fail(BHSTEM_EINVAL, "stage must be 1 or 2");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return h->bn == 256 ? launch_stage<256>(h, stage, in, B, T, out, s) : launch_stage<128>(h, stage, in, B, T, out, s);
+  const StageSel sel = stage == 1 ? StageSel{h->c_in, &h->map_w1, &h->map_w1_half, h->b1, 0, 0}
+                                  : StageSel{h->d, &h->map_w2, &h->map_w2_half, h->b2, 0, 0};
+  return h->bn == 256 ? launch_stage<256>(h, stage, sel, in, B, T, out, s) : launch_stage<128>(h, stage, sel, in, B, T, out, s);
 }
 
 int bhstem_forward(bhstem_handle* h, const void* x, int64_t B, int64_t T, void* hidden, void* y, void* stream) {
   if (!hidden) return fail(BHSTEM_EINVAL, "null argument");
   int rc = bhstem_forward_stage(h, 1, x, B, T, hidden, stream);
+  if (rc == BHSTEM_OK) rc = bhstem_forward_stage(h, 2, hidden, B, T, y, stream);
+  return rc;
+}
+
+int bhstem_prepare_split(bhstem_handle* h, int32_t n_var) {
+  if (!h) return fail(BHSTEM_EINVAL, "null handle");
+  if (n_var < 8 || n_var % 8 || n_var >= h->c_in)
+    return fail(BHSTEM_EINVAL, "n_var must be a positive multiple of 8 below c_in");
+  int dev = -1;
+  cudaGetDevice(&dev);
+  if (dev != h->device) return fail(BHSTEM_EDEVICE, "handle was created on another device than the current one");
+  if (h->n_var == n_var) return BHSTEM_OK;
+  if (h->n_var != 0) return fail(BHSTEM_EINVAL, "this handle is already prepared for another n_var");
+  __nv_bfloat16* w = nullptr;
+  const size_t rows = static_cast<size_t>(3) * h->d;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&w), rows * n_var * 2);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+  // channels 0 .. n_var-1 of every [tap][n] row of the packed conv1 weights
+  e = cudaMemcpy2D(w, static_cast<size_t>(n_var) * 2, h->w1, static_cast<size_t>(h->c_in) * 2, static_cast<size_t>(n_var) * 2,
+                   rows, cudaMemcpyDeviceToDevice);
+  if (e != cudaSuccess) { cudaFree(w); return cuda_fail(e, "repacking the time-varying conv1 channels"); }
+  int rc = make_map(h->enc, &h->map_w1v, w, n_var, h->d, 3, static_cast<uint64_t>(n_var) * 2,
+                    static_cast<uint64_t>(h->d) * n_var * 2, h->bn);
+  if (rc == BHSTEM_OK && h->bn == 256)
+    rc = make_map(h->enc, &h->map_w1v_half, w, n_var, h->d, 3, static_cast<uint64_t>(n_var) * 2,
+                  static_cast<uint64_t>(h->d) * n_var * 2, 128);
+  if (rc != BHSTEM_OK) { cudaFree(w); return rc; }
+  h->w1v = w;
+  h->n_var = n_var;
+  return BHSTEM_OK;
+}
+
+int bhstem_forward_split(bhstem_handle* h, const void* x_var, const void* cond, int64_t B, int64_t T, float* bias3,
+                         void* hidden, void* y, void* stream) {
+  int rc = check_call(h, x_var, B, T, y);
+  if (rc != BHSTEM_OK) return rc;
+  if (!cond || !bias3 || !hidden) return fail(BHSTEM_EINVAL, "null argument");
+  if (h->n_var == 0) return fail(BHSTEM_EINVAL, "call bhstem_prepare_split first");
+  if ((reinterpret_cast<uintptr_t>(cond) & 15) || (reinterpret_cast<uintptr_t>(bias3) & 15) ||
+      (reinterpret_cast<uintptr_t>(hidden) & 15))
+    return fail(BHSTEM_EINVAL, "buffers must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int by = static_cast<int>(B < 16 ? B : 16);
+  bhstem_cond_bias_kernel<<<dim3((h->d + BIAS_WARPS - 1) / BIAS_WARPS, by), BIAS_WARPS * 32, 0, s>>>(
+      h->w1, h->b1, static_cast<const __nv_bfloat16*>(cond), bias3, static_cast<int>(B), h->d, h->c_in, h->n_var);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+  ++h->launches;
+  const StageSel sel{h->n_var, &h->map_w1v, &h->map_w1v_half, bias3, 3 * h->d, h->d};
+  rc = h->bn == 256 ? launch_stage<256>(h, 1, sel, x_var, B, T, hidden, s) : launch_stage<128>(h, 1, sel, x_var, B, T, hidden, s);
   if (rc == BHSTEM_OK) rc = bhstem_forward_stage(h, 2, hidden, B, T, y, stream);
   return rc;
 }

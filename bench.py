@@ -496,10 +496,22 @@ def run_ours(args):
                 ms_all = timed(lambda: stem(mel.forward_encoder_input(xw, [cond], dtype=torch.bfloat16,
                                                                       channels_first=False)), 20)
                 flop = 2.0 * nw * FRAMES * 768 * 3 * (N_MELS + 384) + 2.0 * nw * (FRAMES // 2) * 768 * 3 * 768
+                # split conv1 (bhstem_forward_split): the 384 time-constant channels folded into a per-window
+                # bias, the [nw, 4096, 464] encoder input never built; same outputs within the bf16 tolerance
+                frames16 = torch.empty(nw, FRAMES, N_MELS, dtype=torch.bfloat16, device=dev)
+                mel.forward_into(xw, frames16)
+                cond16 = cond.to(torch.bfloat16)
+                ms_split = timed(lambda: stem.forward_split(frames16, cond16, hidden=hid, out=yst), 20)
+                ms_split_all = timed(lambda: stem.forward_split(mel.forward_into(xw, frames16), cond16, hidden=hid,
+                                                                out=yst), 20)
+                flop_split = 2.0 * nw * FRAMES * 768 * 3 * N_MELS + 2.0 * nw * (FRAMES // 2) * 768 * 3 * 768
                 stem_rows[f"{nw}_windows"] = {
                     "stem_ms": ms_stem, "stem_tflops": flop / ms_stem / 1e9,
                     "stem_frac_of_measured_bf16_peak": flop / ms_stem / 1e9 / bf16_peak,
-                    "frontend_plus_assembly_plus_stem_ms": ms_all}
+                    "frontend_plus_assembly_plus_stem_ms": ms_all,
+                    "split_stem_ms": ms_split, "split_stem_executed_tflops": flop_split / ms_split / 1e9,
+                    "split_stem_speedup": ms_stem / ms_split,
+                    "frontend_plus_split_stem_ms": ms_split_all}
             extra["conv_stem_n3"] = {"dims": "464 -> 768 channels, 4096 -> 2048 frames, bf16, fp32 accumulate",
                                      "kernel": "bhstem_conv_gelu_pair_kernel (tcgen05 cta_group::2 / TMEM / TMA)",
                                      "launches": stem.launch_count(), **stem_rows}

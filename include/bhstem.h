@@ -67,6 +67,34 @@ int bhstem_forward(bhstem_handle* h, const void* x, int64_t B, int64_t T, void* 
 int bhstem_forward_stage(bhstem_handle* h, int32_t stage, const void* in, int64_t B, int64_t T, void* out,
                          void* stream);
 
+/* Split conv1 (SURVEY.md 8f N1 + N3 fused: the encoder input is never materialised).
+ *
+ * The reference feeds conv1 the concatenation [mel | cond] where the conditioning embeddings are ONE vector per
+ * window repeated over its T frames (ref: osuT5/osuT5/model/modeling_mapperatorinator.py:368-370,
+ * `c.unsqueeze(1).expand((-1, frames.shape[1], -1))`, then swapaxes :375-376 and the encoder's conv1,
+ * modeling_ropewhisper.py:1206).  A convolution is linear in its input channels, so the time-constant channels
+ * contribute the same three per-tap sums S_tap[b][n] = sum_c W[n][n_var + c][tap] * cond[b][c] at every frame
+ * (two of them at a window's first and last frame, where one tap reads the zero padding).  bhstem_forward_split
+ * evaluates those sums once per (window, output channel) -- the same bf16 x bf16 products, accumulated in fp32 --
+ * adds them to the bias, and runs the tcgen05 implicit GEMM over the n_var time-varying channels only:
+ *     3 * n_var instead of 3 * c_in products per output element (80 of 464 channels at the reference's dims)
+ * with the same epilogue (fp32 accumulator + bias -> bf16 -> GELU -> bf16).  Results equal bhstem_forward on the
+ * materialised [B][T][c_in] input up to the fp32 summation order (same tolerance as against the reference's
+ * cuDNN convolution; tests/test_gpu_stem.py).
+ *
+ * bhstem_prepare_split: once per handle, before the first bhstem_forward_split (allocates the repacked
+ * [3][D][n_var] weights; synchronous; not to be raced with launches on the same handle).  n_var % 8 == 0,
+ * 8 <= n_var < c_in. */
+int bhstem_prepare_split(bhstem_handle* h, int32_t n_var);
+/* x_var   DEVICE bf16 [B][T][n_var], channels last, contiguous: the time-varying channels (the log-mel frames,
+ *         e.g. written by bhmel_forward_ex with BHMEL_OUT_BF16)
+ * cond    DEVICE bf16 [B][c_in - n_var]: the concatenated conditioning embeddings of each window
+ * bias3   DEVICE float32 [B][3][D] scratch owned by the caller (interior / first-frame / last-frame bias)
+ * hidden  DEVICE bf16 [B][T][D] scratch, y DEVICE bf16 [B][T/2][D] as for bhstem_forward.
+ * Three kernel launches on `stream` (folded bias, conv1, conv2). */
+int bhstem_forward_split(bhstem_handle* h, const void* x_var, const void* cond, int64_t B, int64_t T, float* bias3,
+                         void* hidden, void* y, void* stream);
+
 /* Kernel schedule of this handle (A/B experiments and wider models; all variants give the same results
  * within the bf16 tolerance).  The choice is explicit -- no environment variable is read by the library. */
 #define BHSTEM_OPT_VARIANT 1

@@ -333,3 +333,117 @@ def test_one_call_larger_than_int32_element_counts(dev):
     assert bool(torch.isfinite(y[::53].float()).all())
     del x, y, hidden
     torch.cuda.empty_cache()
+
+
+# ------------------------------------------------------------------ split conv1 (bhstem_forward_split)
+def _cat_input(frames, cond):
+    """The reference's concatenation (modeling_mapperatorinator.py:368-370)."""
+    return torch.cat([frames, cond.unsqueeze(1).expand(-1, frames.shape[1], -1)], dim=-1)
+
+
+@pytest.mark.parametrize("B,T,c_in,d,n_var", [
+    (2, 256, 464, 768, 80),        # the reference's dims: 80 mel + 3 x 128 conditioning channels
+    (1, 200, 464, 768, 80),        # ragged row tile: the last frame sits inside a partial tile
+    (3, 258, 464, 768, 80),        # the last frame alone in its CTA-pair tile
+    (3, 64, 80, 384, 16),          # BN = 128 kernel, one 16-channel block
+    (1, 2, 16, 128, 8),            # smallest: every frame is an edge frame
+    (2, 130, 208, 256, 128),       # 128 varying channels: two full 64-channel blocks (lean issue path)
+])
+def test_split_conv1_matches_the_oracle_on_the_concatenated_input(dev, B, T, c_in, d, n_var):
+    stem = make_stem(c_in, d, dev, seed=c_in + d + 1)
+    x = make_input(B, T, c_in, seed=T + 1)
+    frames, cond = x[:, :, :n_var].contiguous(), x[:, 0, n_var:].contiguous()
+    full = _cat_input(frames, cond)
+    want_y, want_h = conv_stem_oracle.conv_stem(full, stem.conv1.weight, stem.conv1.bias, stem.conv2.weight,
+                                                stem.conv2.bias, return_hidden=True)
+    hidden = torch.empty(B, T, d, dtype=torch.bfloat16, device=dev)
+    before = stem.launch_count()
+    y = stem.forward_split(frames.to(dev), cond.to(dev), hidden=hidden)
+    torch.cuda.synchronize()
+    assert stem.launch_count() == before + 3
+    assert y.shape == (B, T // 2, d) and y.dtype == torch.bfloat16 and y.is_contiguous()
+    assert_close(hidden, want_h, "gelu(split conv1)")
+    # the two edge frames see one tap of zero padding each: check them on their own as well
+    assert_close(hidden[:, 0], want_h[:, 0], "gelu(split conv1), first frame", 0.05)
+    assert_close(hidden[:, T - 1], want_h[:, T - 1], "gelu(split conv1), last frame", 0.05)
+    assert_close(y, want_y, "split stem", 0.10)
+    # and against this library's own convolution over the materialised input
+    hidden_full = stem.forward_stage(1, full.to(dev))
+    assert_close(hidden, hidden_full, "split conv1 vs conv1 over the concatenated input")
+    assert "libbhstem.so" in open("/proc/self/maps").read()
+
+
+def test_split_conv1_edge_frames_drop_exactly_one_tap(dev):
+    """Zero frames isolate the folded bias: interior frames carry bias + S0 + S1 + S2, frame 0 loses tap 0,
+    frame T-1 loses tap 2 (the zero padding).  Checked against fp64 sums of the same bf16 products."""
+    stem = make_stem(464, 768, dev, seed=21)
+    B, T, n_var = 2, 384, 80
+    cond = make_input(B, 1, 464 - n_var, seed=22)[:, 0].contiguous()
+    hidden = torch.empty(B, T, 768, dtype=torch.bfloat16, device=dev)
+    stem.forward_split(torch.zeros(B, T, n_var, dtype=torch.bfloat16, device=dev), cond.to(dev), hidden=hidden)
+    w = stem.conv1.weight.detach().cpu().double()[:, n_var:, :]               # [D, n_cond, 3]
+    s = torch.einsum("nct,bc->btn", w, cond.double())                          # [B, 3, D]
+    bias = stem.conv1.bias.detach().cpu().double()
+    gelu = lambda v: torch.nn.functional.gelu(v.to(torch.bfloat16).float()).to(torch.bfloat16)
+    want_mid = gelu((bias + s.sum(1)).float())
+    want_first = gelu((bias + s[:, 1] + s[:, 2]).float())
+    want_last = gelu((bias + s[:, 0] + s[:, 1]).float())
+    got = hidden.cpu()
+    assert_close(got[:, 0], want_first, "first frame", 0.05)
+    assert_close(got[:, T - 1], want_last, "last frame", 0.05)
+    for t in (1, 2, 127, 128, 255, 256, T - 2):
+        assert_close(got[:, t], want_mid, f"interior frame {t}", 0.05)
+    assert torch.equal(got[:, 1], got[:, 200]) and torch.equal(got[:, 1], got[:, T - 2])
+    assert float((want_first.float() - want_mid.float()).abs().max()) > 0.05   # the edges really differ
+
+
+def test_split_stem_on_the_frontend_output_matches_the_materialised_chain(dev):
+    """C5 slice at full context: frontend (bf16 frames, dense) -> split stem against frontend -> encoder
+    input [B, 4096, 464] -> stem, 6 windows."""
+    from beatheritage_b200 import MelSpectrogram
+    mel = MelSpectrogram("torchaudio", True, 16000, 1024, 80, 128, 20, 8000, "reflect").to(dev)
+    stem = make_stem(464, 768, dev, seed=31)
+    g = torch.Generator().manual_seed(32)
+    samples = (torch.rand(6, 524160, generator=g) * 2 - 1).to(dev)
+    conds = [(torch.randn(6, 128, generator=g) * 0.5).to(dev) for _ in range(3)]
+    enc_in = mel.forward_encoder_input(samples, conds, dtype=torch.bfloat16)
+    want = stem(enc_in)
+    frames = torch.empty(6, 4096, 80, dtype=torch.bfloat16, device=dev)
+    mel.forward_into(samples, frames)
+    assert torch.equal(frames, enc_in[:, :, :80])
+    cond = torch.cat([c.to(torch.bfloat16) for c in conds], dim=1)
+    got = stem.forward_split(frames, cond)
+    torch.cuda.synchronize()
+    assert_close(got, want, "split stem vs stem over the encoder input", 0.10)
+    one = conv_stem_oracle.conv_stem(enc_in[2:3].cpu(), stem.conv1.weight, stem.conv1.bias, stem.conv2.weight,
+                                     stem.conv2.bias)
+    assert_close(got[2:3], one, "split stem vs oracle, window 2", 0.10)
+
+
+def test_split_errors(dev):
+    import ctypes
+    from beatheritage_b200 import _stem_lib
+    stem = make_stem(464, 768, dev, seed=41)
+    frames = torch.zeros(1, 64, 80, dtype=torch.bfloat16, device=dev)
+    cond = torch.zeros(1, 384, dtype=torch.bfloat16, device=dev)
+    with pytest.raises(RuntimeError):
+        stem.forward_split(frames, cond[:, :380])                       # channel counts do not add up
+    with pytest.raises(RuntimeError):
+        stem.forward_split(frames.float(), cond)
+    with pytest.raises(RuntimeError):
+        stem.forward_split(frames[:, :63], cond)                        # odd T
+    with pytest.raises(RuntimeError):
+        stem.forward_split(frames.cpu(), cond.cpu())
+    lib = _stem_lib.lib()
+    h = stem._handle_for(dev)
+    buf = torch.empty(1 << 20, dtype=torch.uint8, device=dev)
+    rc = lib.bhstem_forward_split(h, frames.data_ptr(), cond.data_ptr(), 1, 64, buf.data_ptr(), buf.data_ptr(),
+                                  buf.data_ptr(), None)
+    assert rc == 1 and b"prepare_split" in lib.bhstem_last_error()     # not prepared yet
+    assert lib.bhstem_prepare_split(h, 84) == 1 and lib.bhstem_prepare_split(h, 464) == 1
+    stem.forward_split(frames, cond)
+    assert lib.bhstem_prepare_split(h, 80) == 0                         # idempotent
+    assert lib.bhstem_prepare_split(h, 88) == 1                         # but one n_var per handle
+    with pytest.raises(RuntimeError):
+        stem.forward_split(torch.zeros(1, 64, 88, dtype=torch.bfloat16, device=dev),
+                           torch.zeros(1, 376, dtype=torch.bfloat16, device=dev))
