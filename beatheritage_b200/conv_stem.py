@@ -80,6 +80,8 @@ class ConvStem(nn.Module):
                                                   *[ctypes.cast(t.data_ptr(), fp) for t in host], ctypes.byref(out)))
             if getattr(self, "_variant", 2) != 2:
                 _stem_lib.check(lib.bhstem_set_option(out.value, 1, self._variant))
+            if getattr(self, "_epi", None) is not None:
+                _stem_lib.check(lib.bhstem_set_option(out.value, 3, self._epi))
             if not getattr(self, "_pdl", True):
                 _stem_lib.check(lib.bhstem_set_option(out.value, 2, 0))
             self._handles[idx] = out.value
@@ -110,6 +112,14 @@ class ConvStem(nn.Module):
         lib = _stem_lib.lib()
         for h in self._handles.values():
             _stem_lib.check(lib.bhstem_set_option(h, 1, self._variant))
+
+    def set_epilogue_warps(self, conv1: int = 8, conv2: int = 8, split_conv1: int = 16) -> None:
+        """Epilogue warps of the CTA-pair kernel per stage, 8 or 16 each (A/B runs; same bits).
+        BHSTEM_OPT_EPILOGUE_WARPS, include/bhstem.h."""
+        self._epi = conv1 | (conv2 << 8) | (split_conv1 << 16)
+        lib = _stem_lib.lib()
+        for h in self._handles.values():
+            _stem_lib.check(lib.bhstem_set_option(h, 3, self._epi))
 
     def set_pdl(self, on: bool) -> None:
         """Programmatic dependent launch (default on): a kernel's prologue overlaps the previous kernel's tail;

@@ -128,6 +128,16 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {     // barrier in any CTA of the cluster
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
+// Hand-back of a TMEM accumulator stage: what has to be ordered before the arrival are this warp's tcgen05.ld
+// reads, and those are complete (tcgen05.wait::ld) and fenced (tcgen05.fence::before_thread_sync) already.  A
+// .release arrival at cluster scope additionally waits for every earlier global store of the thread to drain
+// (MEMBAR.ALL.CTA + ERRBAR in SASS: 9 % of the split conv1's stall samples sat there) -- relaxed does not.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t cta_addr, uint32_t rank) {   // shared::cta -> shared::cluster
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
@@ -180,6 +190,23 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {    
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
+}
+// The same wait for roles whose wake-up latency is covered by a ring or by the second accumulator stage (TMA
+// producers waiting for a free slot, epilogue warps waiting for an accumulator): sleeps between polls, so a
+// waiting warp does not take issue slots from the epilogue warps on its scheduler (the tight poll loops were
+// 28 % of the split conv1's executed instructions).  The MMA issuer waits this way for a free accumulator
+// stage (a long wait exactly when the epilogue is the bound) and keeps the tight loop for its operands.
+__device__ __noinline__ void mbar_wait_sleep_slow(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  unsigned ns = 32;
+  while (!mbar_try(bar, parity)) {
+    __nanosleep(ns);
+    if (ns < 256) ns *= 2;                                  // long waits poll rarely: a poll is ~8 issue slots
+    if (clock64() - t0 > SPIN_LIMIT_CYCLES) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  if (!mbar_try(bar, parity)) mbar_wait_sleep_slow(bar, parity);
 }
 
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
@@ -284,11 +311,78 @@ __device__ __forceinline__ float gelu_of_bf16(const float x) {
 }
 // Two accumulators at a time: + bias, ONE packed conversion to bf16 (the conv's output), GELU on the two
 // bf16 values, one packed conversion of the results.
-__device__ __forceinline__ uint32_t conv_gelu_pair(const float a, const float b) {
+//
+// The two GELUs run on packed fp32 pairs (fma / mul.rn.f32x2 -> SASS FFMA2 / FMUL2): every multiply-add of
+// gelu_of_bf16 above, in the same order with the same roundings, so the results are bit-identical to two
+// scalar evaluations -- but one issue slot per pair instead of two.  The epilogue is issue-bound wherever it
+// is the bound (the split conv1: 74 % issue-active with the FMA pipe at 46 %), and the packed form holds the
+// FMA pipe exactly as long as the two scalar instructions it replaces.  |x| and the final sign are integer
+// operations on the halves (no operand modifiers on packed instructions): h + |h| erf|x| is evaluated as
+// h + h * (erf|x| with x's sign), the same product and the same single rounding.
+#ifndef BHSTEM_SCALAR_GELU
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t bc2(float v) { return pk2(v, v); }
+#endif
+
+__device__ __forceinline__ uint32_t conv_gelu_pair(const float acc_a, const float acc_b, const float bias_a, const float bias_b) {
+#if defined(BHSTEM_SCALAR_GELU) || defined(BHSTEM_ERFF) || defined(BHSTEM_TIMING_NO_GELU)
+  const float a = acc_a + bias_a, b = acc_b + bias_b;
+#else
+  float a, b;
+  {
+    uint64_t sum;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(sum) : "l"(pk2(acc_a, acc_b)), "l"(pk2(bias_a, bias_b)));
+    unpk2(sum, a, b);
+  }
+#endif
   const __nv_bfloat162 c = __floats2bfloat162_rn(a, b);
   const uint32_t bits = *reinterpret_cast<const uint32_t*>(&c);
+#if defined(BHSTEM_SCALAR_GELU) || defined(BHSTEM_ERFF) || defined(BHSTEM_TIMING_NO_GELU)
   const float xa = __uint_as_float(bits << 16), xb = __uint_as_float(bits & 0xffff0000u);
   const __nv_bfloat162 y = __floats2bfloat162_rn(gelu_of_bf16(xa), gelu_of_bf16(xb));
+#else
+  const uint32_t ia = bits << 16, ib = bits & 0xffff0000u;
+  const uint64_t x = pk2(__uint_as_float(ia), __uint_as_float(ib));
+  const uint64_t u = pk2(__uint_as_float(ia & 0x7fffffffu), __uint_as_float(ib & 0x7fffffffu));
+  float da, db, ta, tb, ea, eb;
+  unpk2(fma2(bc2(0.3275911f * 0.70710678118654752440f), u, bc2(1.0f)), da, db);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ta) : "f"(da));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(tb) : "f"(db));
+  float qa, qb;
+  unpk2(mul2(mul2(u, u), bc2(-0.5f * 1.4426950408889634f)), qa, qb);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(qa));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(qb));
+  const uint64_t t = pk2(ta, tb), e = pk2(ea, eb);
+  // the polynomial with every coefficient negated: each step is the exact negation of the scalar one
+  uint64_t npoly = fma2(t, bc2(-1.061405429f), bc2(1.453152027f));
+  npoly = fma2(npoly, t, bc2(-1.421413741f));
+  npoly = fma2(npoly, t, bc2(0.284496736f));
+  npoly = fma2(npoly, t, bc2(-0.254829592f));
+  float fa, fb;
+  unpk2(fma2(mul2(npoly, t), e, bc2(1.0f)), fa, fb);                         // erf|x| = 1 - (poly t) e
+  // erf|x| carrying x's sign
+  const uint64_t s = pk2(__uint_as_float(__float_as_uint(fa) ^ (ia & 0x80000000u)),
+                         __uint_as_float(__float_as_uint(fb) ^ (ib & 0x80000000u)));
+  const uint64_t h = mul2(x, bc2(0.5f));
+  float ya, yb;
+  unpk2(fma2(h, s, h), ya, yb);
+  const __nv_bfloat162 y = __floats2bfloat162_rn(ya, yb);
+#endif
   return *reinterpret_cast<const uint32_t*>(&y);
 }
 
@@ -300,20 +394,37 @@ __device__ __forceinline__ uint32_t conv_gelu_pair(const float a, const float b)
 // leaves as 64-byte row segments, 8 rows per store instruction.
 constexpr int EPI_STAGE_BYTES = 32 * 64;
 
-template <int BN>
+template <int BN, int EW = EPI_WARPS>
 __device__ __forceinline__ void epilogue_role(const StemProblem& p, const float* __restrict__ bias,
                                               __nv_bfloat16* __restrict__ out, uint32_t tmem_base, uint32_t tfull0,
                                               uint32_t tempty0, int warp, int lane, uint8_t* staging_all,
-                                              int tile0 = blockIdx.x, int tile_step = gridDim.x, int tile_rows = BLOCK_M,
+                                              float* bias_stage_all, int tile0 = blockIdx.x, int tile_step = gridDim.x, int tile_rows = BLOCK_M,
                                               int row_off = 0, bool tempty_is_cluster_addr = false) {
   const int tiles_per_batch = p.m_tiles * p.n_tiles;
   const int num_tiles = p.batches * tiles_per_batch;
   const int quarter = warp & 3;                            // TMEM lanes this warp may touch: 32 * (warp % 4) ...
-  const int half = (warp - 2) >> 2;                        // which half of the tile's columns (warps 2-5 / 6-9)
-  constexpr int CHUNKS = BN / 64;                          // 32-column chunks per warp
+  const int half = (warp - 2) >> 2;                        // which share of the tile's columns (warps 2-5 / 6-9 / ...)
+  constexpr int CHUNKS = BN / 32 / (EW / 4);               // 32-column chunks per warp (EW / 4 warps per lane quarter)
+  static_assert(EW % 4 == 0 && (BN / 32) % (EW / 4) == 0, "epilogue warps must divide the tile's column chunks");
   uint8_t* staging = staging_all + (warp - 2) * EPI_STAGE_BYTES;
   const int wr_swz = (lane >> 1) & 3;                      // my row's XOR phase when writing
   const int rd_row = lane >> 2, rd_piece = lane & 3;       // read-back: 4 lanes per row, 8 rows per pass
+  // The bias of this warp's CHUNKS * 32 columns is read once per tile, one tile AHEAD (coalesced, into CHUNKS
+  // registers per lane), and turned round through a per-warp shared-memory block at the top of the tile, so the
+  // chunk loop reads it as broadcast 16-byte pieces without waiting for L2 (the per-chunk global loads this
+  // replaces: 8.5 % of the split conv1's stall samples).  A warp that holds a window's first / last frame
+  // (split conv1 only) stages those two bias rows as well, and the lane on that frame reads its own copy.
+  float* bst = bias_stage_all + (warp - 2) * (3 * CHUNKS * 32);   // [interior | first frame | last frame]
+  auto interior_bias = [&](int t) {
+    const int tb = t / tiles_per_batch, tnt = (t % tiles_per_batch) % p.n_tiles;
+    return bias + static_cast<size_t>(tb) * p.bias_batch_stride + tnt * BN + half * (CHUNKS * 32);
+  };
+  float bias_next[CHUNKS];
+  if (tile0 < num_tiles) {
+    const float* src = interior_bias(tile0);
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) bias_next[i] = __ldg(src + i * 32 + lane);
+  }
   uint32_t local = 0;
   for (int tile = tile0; tile < num_tiles; tile += tile_step, ++local) {
     const int b = tile / tiles_per_batch, rem = tile % tiles_per_batch;
@@ -323,12 +434,32 @@ __device__ __forceinline__ void epilogue_role(const StemProblem& p, const float*
     __nv_bfloat16* oslab = out + (static_cast<size_t>(b) * p.rows_out + row0) * p.n_out + nt * BN;
     const int my_row = row0 + lane;                        // the output row (time step) this lane owns
     const int edge = my_row == 0 ? 1 : (my_row == p.rows_out - 1 ? 2 : 0);
-    const float* brow = bias + static_cast<size_t>(b) * p.bias_batch_stride + edge * p.bias_edge_stride + nt * BN;
     BHS_CHECK(p.bias_edge_stride == 0 || (p.bias_batch_stride == 3 * p.bias_edge_stride && p.bias_edge_stride == p.n_out));
+    __syncwarp();                                          // the previous tile's bias is no longer read
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) bst[i * 32 + lane] = bias_next[i];
+    __syncwarp();
+    if (tile + tile_step < num_tiles) {
+      const float* src = interior_bias(tile + tile_step);
+#pragma unroll
+      for (int i = 0; i < CHUNKS; ++i) bias_next[i] = __ldg(src + i * 32 + lane);
+    }
+    // split conv1: a lane on a window's first / last frame reads the bias row of that frame
+    const bool is_edge = edge != 0 && p.bias_edge_stride != 0;
+    if (__any_sync(0xffffffffu, is_edge)) {
+      const float* erow = bias + static_cast<size_t>(b) * p.bias_batch_stride + nt * BN + half * (CHUNKS * 32);
+#pragma unroll
+      for (int i = 0; i < CHUNKS; ++i) {
+        bst[(CHUNKS + i) * 32 + lane] = __ldg(erow + p.bias_edge_stride + i * 32 + lane);
+        bst[(2 * CHUNKS + i) * 32 + lane] = __ldg(erow + 2 * p.bias_edge_stride + i * 32 + lane);
+      }
+      __syncwarp();
+    }
+    const float* bl = bst + (is_edge ? edge * (CHUNKS * 32) : 0);
 #ifdef BHSTEM_PROFILE
-    { const long long t0p = clock64(); mbar_wait(tfull0 + 8 * as, aphase); if (warp == 2 && lane == 0) atomicAdd(&g_prof[5], static_cast<unsigned long long>(clock64() - t0p)); }
+    { const long long t0p = clock64(); mbar_wait_sleep(tfull0 + 8 * as, aphase); if (warp == 2 && lane == 0) atomicAdd(&g_prof[5], static_cast<unsigned long long>(clock64() - t0p)); }
 #else
-    mbar_wait(tfull0 + 8 * as, aphase);
+    mbar_wait_sleep(tfull0 + 8 * as, aphase);
 #endif
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
@@ -342,8 +473,8 @@ __device__ __forceinline__ void epilogue_role(const StemProblem& p, const float*
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (tempty_is_cluster_addr) mbar_arrive_cluster(tempty0 + 8 * as);
-          else mbar_arrive(tempty0 + 8 * as);
+          if (tempty_is_cluster_addr) mbar_arrive_cluster_relaxed(tempty0 + 8 * as);
+          else mbar_arrive_relaxed(tempty0 + 8 * as);
         }
       }
 #ifdef BHSTEM_PROFILE
@@ -351,13 +482,13 @@ __device__ __forceinline__ void epilogue_role(const StemProblem& p, const float*
 #endif
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(brow + c * 32 + j));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(brow + c * 32 + j + 4));
+        const float4 b0 = *reinterpret_cast<const float4*>(bl + (c - half * CHUNKS) * 32 + j);
+        const float4 b1 = *reinterpret_cast<const float4*>(bl + (c - half * CHUNKS) * 32 + j + 4);
         uint4 v;
-        v.x = conv_gelu_pair(__uint_as_float(r[j + 0]) + b0.x, __uint_as_float(r[j + 1]) + b0.y);
-        v.y = conv_gelu_pair(__uint_as_float(r[j + 2]) + b0.z, __uint_as_float(r[j + 3]) + b0.w);
-        v.z = conv_gelu_pair(__uint_as_float(r[j + 4]) + b1.x, __uint_as_float(r[j + 5]) + b1.y);
-        v.w = conv_gelu_pair(__uint_as_float(r[j + 6]) + b1.z, __uint_as_float(r[j + 7]) + b1.w);
+        v.x = conv_gelu_pair(__uint_as_float(r[j + 0]), __uint_as_float(r[j + 1]), b0.x, b0.y);
+        v.y = conv_gelu_pair(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]), b0.z, b0.w);
+        v.z = conv_gelu_pair(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]), b1.x, b1.y);
+        v.w = conv_gelu_pair(__uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]), b1.z, b1.w);
         BHS_CHECK(lane * 64 + (((j >> 3) ^ wr_swz) << 4) + 16 <= EPI_STAGE_BYTES);
         *reinterpret_cast<uint4*>(staging + lane * 64 + (((j >> 3) ^ wr_swz) << 4)) = v;
       }
@@ -387,6 +518,8 @@ bhstem_conv_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   __shared__ __align__(8) unsigned long long bars[2 * STAGES + 4];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(128) uint8_t epi_staging[EPI_WARPS * EPI_STAGE_BYTES];
+  __shared__ __align__(16) float epi_bias[12 * BN];         // per epilogue warp: the bias of its share of the tile's columns
+
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -469,7 +602,7 @@ bhstem_conv_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     }
   } else {
     // ===================================== epilogue =========================================
-    epilogue_role<BN>(p, bias, out, tmem_base, tfull0, tempty0, warp, lane, epi_staging);
+    epilogue_role<BN>(p, bias, out, tmem_base, tfull0, tempty0, warp, lane, epi_staging, epi_bias);
   }
 
   tc_fence_before();
@@ -521,6 +654,8 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
   __shared__ __align__(8) unsigned long long bars[2 * A_STAGES + 2 * W_STAGES + 4];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(128) uint8_t epi_staging[EPI_WARPS * EPI_STAGE_BYTES];
+  __shared__ __align__(16) float epi_bias[12 * BN];         // per epilogue warp: the bias of its share of the tile's columns
+
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ring_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -568,7 +703,7 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
         const int b = tile / tiles_per_batch, mt = (tile % tiles_per_batch) / p.n_tiles;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           const int c0 = ks.first_channel(kb);
-          { PROF_T0(); mbar_wait(aempty0 + 8 * as, aph ^ 1); PROF_ADD(0); }
+          { PROF_T0(); mbar_wait_sleep(aempty0 + 8 * as, aph ^ 1); PROF_ADD(0); }
           const uint32_t sa = ring_a + as * ASTAGE_BYTES;
 #ifdef BHSTEM_PROFILE
           if (p.exp & 4) {
@@ -591,7 +726,7 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           const int c0 = ks.first_channel(kb);
           for (int tap = 0; tap < 3; ++tap) {
-            { PROF_T0(); mbar_wait(wempty0 + 8 * ws, wph ^ 1); PROF_ADD(1); }
+            { PROF_T0(); mbar_wait_sleep(wempty0 + 8 * ws, wph ^ 1); PROF_ADD(1); }
 #ifdef BHSTEM_PROFILE
             if (p.exp & 1) {
               mbar_arrive(wfull0 + 8 * ws);
@@ -628,7 +763,7 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
         const uint32_t b0_lo = sw128_desc_lo(ring_w);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
           const uint32_t acc = local & 1, accphase = (local >> 1) & 1;
-          { PROF_T0(); mbar_wait(tempty0 + 8 * acc, accphase ^ 1); PROF_ADD(4); }
+          { PROF_T0(); mbar_wait_sleep(tempty0 + 8 * acc, accphase ^ 1); PROF_ADD(4); }
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + acc * BN;
           uint32_t accumulate = 0;                           // only the tile's very first MMA overwrites
@@ -657,7 +792,7 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
       } else
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
         const uint32_t acc = local & 1, accphase = (local >> 1) & 1;
-        { PROF_T0(); mbar_wait(tempty0 + 8 * acc, accphase ^ 1); PROF_ADD(4); }
+        { PROF_T0(); mbar_wait_sleep(tempty0 + 8 * acc, accphase ^ 1); PROF_ADD(4); }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
@@ -684,7 +819,7 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
       }
     }
   } else {
-    epilogue_role<BN>(p, bias, out, tmem_base, tfull0, tempty0, warp, lane, epi_staging);
+    epilogue_role<BN>(p, bias, out, tmem_base, tfull0, tempty0, warp, lane, epi_staging, epi_bias);
   }
 
 #ifdef BHSTEM_PROFILE
@@ -721,9 +856,8 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
 // tcgen05.commit frees the stages / publishes the accumulators in BOTH CTAs (multicast), and both CTAs'
 // epilogue warps hand the accumulator stage back on the leader's TMEM-empty barrier.
 constexpr int PAIR_W_BYTES = 128 * BLOCK_K * 2;            // half of a 256-row weight tile
-constexpr int PAIR_W_STAGES = 8, PAIR_A_STAGES = 2;
+constexpr int PAIR_A_STAGES = 2;
 constexpr int PAIR_ASTAGE_BYTES = A0_BYTES + A1_BYTES;
-constexpr int PAIR_SMEM_BYTES = PAIR_A_STAGES * PAIR_ASTAGE_BYTES + PAIR_W_STAGES * PAIR_W_BYTES + 1024;
 constexpr int PAIR_BN = 256;
 
 __device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* map, uint32_t leader_bar_cluster, uint32_t dst,
@@ -755,14 +889,25 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {     // arrives 
                : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS_SHARED, 1)
+// EW epilogue warps (8: two per TMEM lane quarter; 16: four -- the split conv1, whose 15 MMA steps per tile leave
+// the epilogue's GELU as the bound) and WST weight-ring stages (the 16-warp form trades two stages for staging room).
+template <int EW, int WST>
+struct PairCfg {
+  static constexpr int THREADS = 32 * (3 + EW);             // weight producer, MMA issuer, EW epilogue warps, activation producer
+  static constexpr int A_WARP = 2 + EW;
+  static constexpr int SMEM_BYTES = PAIR_A_STAGES * PAIR_ASTAGE_BYTES + WST * PAIR_W_BYTES + 1024;
+};
+
+template <int EW, int WST>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<EW, WST>::THREADS, 1)
 bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                              const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias,
                              __nv_bfloat16* __restrict__ out, const StemProblem p, const SharedTaps st) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) unsigned long long bars[2 * PAIR_A_STAGES + 2 * PAIR_W_STAGES + 4];
+  __shared__ __align__(8) unsigned long long bars[2 * PAIR_A_STAGES + 2 * WST + 4];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ __align__(128) uint8_t epi_staging[EPI_WARPS * EPI_STAGE_BYTES];
+  __shared__ __align__(128) uint8_t epi_staging[EW * EPI_STAGE_BYTES];
+  __shared__ __align__(16) float epi_bias[12 * PAIR_BN];    // per epilogue warp: the bias of its share of the tile's columns
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_rank();
@@ -770,13 +915,13 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
   const uint32_t ring_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t ring_w = ring_a + PAIR_A_STAGES * PAIR_ASTAGE_BYTES;
   const uint32_t afull0 = smem_u32(&bars[0]), aempty0 = smem_u32(&bars[PAIR_A_STAGES]);
-  const uint32_t wfull0 = smem_u32(&bars[2 * PAIR_A_STAGES]), wempty0 = smem_u32(&bars[2 * PAIR_A_STAGES + PAIR_W_STAGES]);
-  const uint32_t tfull0 = smem_u32(&bars[2 * PAIR_A_STAGES + 2 * PAIR_W_STAGES]), tempty0 = tfull0 + 16;
+  const uint32_t wfull0 = smem_u32(&bars[2 * PAIR_A_STAGES]), wempty0 = smem_u32(&bars[2 * PAIR_A_STAGES + WST]);
+  const uint32_t tfull0 = smem_u32(&bars[2 * PAIR_A_STAGES + 2 * WST]), tempty0 = tfull0 + 16;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < PAIR_A_STAGES; ++s) { mbar_init(afull0 + 8 * s, 1); mbar_init(aempty0 + 8 * s, 1); }
-    for (int s = 0; s < PAIR_W_STAGES; ++s) { mbar_init(wfull0 + 8 * s, 1); mbar_init(wempty0 + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 2 * EPI_WARPS); }   // epilogue warps of both CTAs
+    for (int s = 0; s < WST; ++s) { mbar_init(wfull0 + 8 * s, 1); mbar_init(wempty0 + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 2 * EW); }   // epilogue warps of both CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {          // the same warp of BOTH CTAs allocates (cta_group::2), same destination slot
@@ -803,10 +948,10 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_ns0));
 #endif
 
-  if (warp == 0 || warp == A_PRODUCER_WARP) {
+  if (warp == 0 || warp == (PairCfg<EW, WST>::A_WARP)) {
     // ===================================== TMA producers (both CTAs) ========================
     // Independent single-thread producers for the activation ring (last warp) and the weight ring (warp 0).
-    if (warp == A_PRODUCER_WARP && elect_one()) {
+    if (warp == (PairCfg<EW, WST>::A_WARP) && elect_one()) {
       const uint32_t afull_leader = map_to_cta(afull0, 0);
       uint32_t as = 0, aph = 0;
       for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
@@ -814,7 +959,7 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
         const int my_row = mt * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           const int c0 = ks.first_channel(kb);
-          { PROF_T0(); mbar_wait(aempty0 + 8 * as, aph ^ 1); PROF_ADD(0); }
+          { PROF_T0(); mbar_wait_sleep(aempty0 + 8 * as, aph ^ 1); PROF_ADD(0); }
           const uint32_t sa = ring_a + as * PAIR_ASTAGE_BYTES;
           if (leader) mbar_expect_tx(afull0 + 8 * as, 2 * a_bytes);           // both CTAs' activation blocks
           tma_load_3d_pair(&map_a0, afull_leader + 8 * as, sa, st.a_col[0] + c0, my_row + st.a_row[0], b);
@@ -831,11 +976,11 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           const int c0 = ks.first_channel(kb);
           for (int tap = 0; tap < 3; ++tap) {
-            { PROF_T0(); mbar_wait(wempty0 + 8 * ws, wph ^ 1); PROF_ADD(1); }
+            { PROF_T0(); mbar_wait_sleep(wempty0 + 8 * ws, wph ^ 1); PROF_ADD(1); }
             if (leader) mbar_expect_tx(wfull0 + 8 * ws, 2 * PAIR_W_BYTES);    // both halves of the weight tile
             tma_load_3d_pair(&map_w, wfull_leader + 8 * ws, ring_w + ws * PAIR_W_BYTES, c0,
                              nt * PAIR_BN + static_cast<int>(rank) * 128, tap);
-            if (++ws == PAIR_W_STAGES) { ws = 0; wph ^= 1; }
+            if (++ws == WST) { ws = 0; wph ^= 1; }
           }
         }
       }
@@ -857,7 +1002,7 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
         const uint32_t b0_lo = sw128_desc_lo(ring_w);
         for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++local) {
           const uint32_t acc = local & 1, accphase = (local >> 1) & 1;
-          { PROF_T0(); mbar_wait(tempty0 + 8 * acc, accphase ^ 1); PROF_ADD(4); }
+          { PROF_T0(); mbar_wait_sleep(tempty0 + 8 * acc, accphase ^ 1); PROF_ADD(4); }
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + acc * PAIR_BN;
           uint32_t accumulate = 0;
@@ -876,7 +1021,7 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
               umma_bf16_pair_lo(tmem_d, al + 4, bl + 4, idesc, 1u);
               if (step4) umma_bf16_pair_lo(tmem_d, al + 6, bl + 6, idesc, 1u);
               umma_commit_pair(wempty0 + 8 * ws);
-              if (++ws == PAIR_W_STAGES) { ws = 0; wph ^= 1; }
+              if (++ws == WST) { ws = 0; wph ^= 1; }
             }
             umma_commit_pair(aempty0 + 8 * as);
             if (++as == PAIR_A_STAGES) { as = 0; aph ^= 1; }
@@ -886,7 +1031,7 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
       } else
       for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++local) {
         const uint32_t acc = local & 1, accphase = (local >> 1) & 1;
-        { PROF_T0(); mbar_wait(tempty0 + 8 * acc, accphase ^ 1); PROF_ADD(4); }
+        { PROF_T0(); mbar_wait_sleep(tempty0 + 8 * acc, accphase ^ 1); PROF_ADD(4); }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * PAIR_BN;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
@@ -901,7 +1046,7 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
             for (int k = 0; k < ksteps; ++k)
               umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | tap | k) != 0);
             umma_commit_pair(wempty0 + 8 * ws);
-            if (++ws == PAIR_W_STAGES) { ws = 0; wph ^= 1; }
+            if (++ws == WST) { ws = 0; wph ^= 1; }
           }
           umma_commit_pair(aempty0 + 8 * as);
           if (++as == PAIR_A_STAGES) { as = 0; aph ^= 1; }
@@ -910,12 +1055,12 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
       }
     }
   } else {
-    epilogue_role<PAIR_BN>(p, bias, out, tmem_base, tfull0, map_to_cta(tempty0, 0), warp, lane, epi_staging, pair_id,
+    epilogue_role<PAIR_BN, EW>(p, bias, out, tmem_base, tfull0, map_to_cta(tempty0, 0), warp, lane, epi_staging, epi_bias, pair_id,
                            num_pairs, 2 * BLOCK_M, static_cast<int>(rank) * BLOCK_M, true);
   }
 
 #ifdef BHSTEM_PROFILE
-  if (lane == 0 && warp == A_PRODUCER_WARP && leader) { PROF_FLUSH(0); }
+  if (lane == 0 && warp == (PairCfg<EW, WST>::A_WARP) && leader) { PROF_FLUSH(0); }
   if (lane == 0 && warp == 0 && leader) { PROF_FLUSH(1); }
   if (lane == 0 && warp == 1 && leader) {
     PROF_FLUSH(2); PROF_FLUSH(3); PROF_FLUSH(4);
@@ -952,43 +1097,78 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
 // which the conv1 epilogue adds to the accumulator of the n_var time-varying channels: 3 * n_var instead of
 // 3 * C products per output element (80 of 464 channels at the reference's dims: 5.8x fewer), and the
 // [B][T][C] encoder input is never materialised.
-// One warp per output channel, 8 channels per CTA, blockIdx.y strides over the windows; 16-byte loads.
-constexpr int BIAS_WARPS = 8;
+// One warp per output channel, 8 channels per CTA; blockIdx.y owns a contiguous share of the windows and walks
+// it BIAS_BCH windows at a time: their conditioning vectors are converted to fp32 once into shared memory, a
+// lane keeps the 3 x 8 weights of its 16-byte piece in registers (converted once per chunk) and multiplies
+// them with all BIAS_BCH vectors -- 24 FFMA per 2 LDS.128, no conversions in the inner loop.
+constexpr int BIAS_WARPS = 8, BIAS_BCH = 8;
 __global__ void __launch_bounds__(BIAS_WARPS * 32)
 bhstem_cond_bias_kernel(const __nv_bfloat16* __restrict__ w /* [3][D][C] */, const float* __restrict__ bias,
                         const __nv_bfloat16* __restrict__ cond /* [B][C - n_var] */, float* __restrict__ bias3,
-                        int batches, int d, int c, int n_var) {
+                        int batches, int d, int c, int n_var, int b_per_cta) {
+  extern __shared__ float xs[];                             // [BIAS_BCH][n_cond] fp32
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * BIAS_WARPS + warp;
-  if (n >= d) return;
-  const int n_cond = c - n_var, vecs = n_cond >> 3;       // n_var % 8 == 0 and C % 8 == 0: whole 16-byte pieces
-  const float bn = bias[n];
-  for (int b = blockIdx.y; b < batches; b += gridDim.y) {
-    float s[3] = {0.f, 0.f, 0.f};
-    const uint4* xrow = reinterpret_cast<const uint4*>(cond + static_cast<size_t>(b) * n_cond);
+  const bool active = n < d;
+  const int n_cond = c - n_var, vecs = n_cond >> 3;         // n_var % 8 == 0 and C % 8 == 0: whole 16-byte pieces
+  const int b_begin = blockIdx.y * b_per_cta, b_end = min(batches, b_begin + b_per_cta);
+  const float bn = active ? bias[n] : 0.f;
+  for (int b0 = b_begin; b0 < b_end; b0 += BIAS_BCH) {
+    const int nb = min(BIAS_BCH, b_end - b0);
+    __syncthreads();                                        // the previous chunk's vectors are no longer read
+    for (int i = threadIdx.x; i < BIAS_BCH * vecs; i += BIAS_WARPS * 32) {
+      const int bb = i / vecs, v = i - bb * vecs;
+      uint4 xv = make_uint4(0u, 0u, 0u, 0u);
+      if (bb < nb) xv = __ldg(reinterpret_cast<const uint4*>(cond + static_cast<size_t>(b0 + bb) * n_cond) + v);
+      float4* dst = reinterpret_cast<float4*>(xs + bb * n_cond + v * 8);
+      dst[0] = make_float4(__uint_as_float(xv.x << 16), __uint_as_float(xv.x & 0xffff0000u),
+                           __uint_as_float(xv.y << 16), __uint_as_float(xv.y & 0xffff0000u));
+      dst[1] = make_float4(__uint_as_float(xv.z << 16), __uint_as_float(xv.z & 0xffff0000u),
+                           __uint_as_float(xv.w << 16), __uint_as_float(xv.w & 0xffff0000u));
+    }
+    __syncthreads();
+    if (!active) continue;
+    float acc[BIAS_BCH][3];
+#pragma unroll
+    for (int bb = 0; bb < BIAS_BCH; ++bb) acc[bb][0] = acc[bb][1] = acc[bb][2] = 0.f;
     for (int v = lane; v < vecs; v += 32) {
-      const uint4 xv = __ldg(xrow + v);
-      const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+      float wf[3][8];
 #pragma unroll
       for (int tap = 0; tap < 3; ++tap) {
         const uint4 wv = __ldg(reinterpret_cast<const uint4*>(w + (static_cast<size_t>(tap) * d + n) * c + n_var) + v);
         const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {                      // bf16 -> fp32 is a shift; the products are exact in fp32
-          s[tap] = fmaf(__uint_as_float(ww[i] << 16), __uint_as_float(xw[i] << 16), s[tap]);
-          s[tap] = fmaf(__uint_as_float(ww[i] & 0xffff0000u), __uint_as_float(xw[i] & 0xffff0000u), s[tap]);
+        for (int i = 0; i < 4; ++i) {                        // bf16 -> fp32 is a shift; the products are exact in fp32
+          wf[tap][2 * i] = __uint_as_float(ww[i] << 16);
+          wf[tap][2 * i + 1] = __uint_as_float(ww[i] & 0xffff0000u);
         }
+      }
+#pragma unroll
+      for (int bb = 0; bb < BIAS_BCH; ++bb) {
+        const float4 x0 = *reinterpret_cast<const float4*>(xs + bb * n_cond + v * 8);
+        const float4 x1 = *reinterpret_cast<const float4*>(xs + bb * n_cond + v * 8 + 4);
+        const float xf[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+        for (int tap = 0; tap < 3; ++tap)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[bb][tap] = fmaf(wf[tap][i], xf[i], acc[bb][tap]);
       }
     }
 #pragma unroll
-    for (int tap = 0; tap < 3; ++tap)
+    for (int bb = 0; bb < BIAS_BCH; ++bb)
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) s[tap] += __shfl_xor_sync(0xffffffffu, s[tap], off);
-    if (lane == 0) {
-      float* o = bias3 + static_cast<size_t>(b) * 3 * d + n;
-      o[0] = bn + ((s[0] + s[1]) + s[2]);
-      o[d] = bn + (s[1] + s[2]);
-      o[2 * d] = bn + (s[0] + s[1]);
+      for (int tap = 0; tap < 3; ++tap)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc[bb][tap] += __shfl_xor_sync(0xffffffffu, acc[bb][tap], off);
+    if (lane < nb) {                                        // lane bb writes window b0 + bb (every lane holds every sum)
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int bb = 0; bb < BIAS_BCH; ++bb)
+        if (bb == lane) { s0 = acc[bb][0]; s1 = acc[bb][1]; s2 = acc[bb][2]; }
+      float* o = bias3 + static_cast<size_t>(b0 + lane) * 3 * d + n;
+      o[0] = bn + ((s0 + s1) + s2);
+      o[d] = bn + (s1 + s2);
+      o[2 * d] = bn + (s0 + s1);
     }
   }
 }
@@ -1048,6 +1228,7 @@ struct bhstem_handle {
   int variant = 1;      // 1: shared taps (row-shifted descriptors, default), 0: one TMA box per tap
   int pdl = 1;          // 1 (default): launch with programmatic stream serialisation (prologue overlaps the previous grid's tail)
   int pairs = 1;        // 1 (default): CTA-pair kernel (tcgen05 cta_group::2) when d_model % 256 == 0 and the SM count is even
+  int epi_warps[3] = {8, 8, 16};   // CTA-pair kernel, epilogue warps for conv1 / conv2 / the split conv1 (BHSTEM_OPT_EPILOGUE_WARPS)
   int exp = 0;          // -DBHSTEM_PROFILE builds only: BHSTEM_EXP timing experiments (wrong results)
 };
 
@@ -1087,6 +1268,7 @@ struct StageSel {
   const CUtensorMap *map_w, *map_w_half;
   const float* bias;
   int32_t bias_batch_stride, bias_edge_stride;
+  int epi_warps;           // CTA-pair kernel: 8 or 16 epilogue warps
 };
 
 template <int BN>
@@ -1147,9 +1329,14 @@ int launch_stage(bhstem_handle* h, int stage, const StageSel& sel, const void* i
       pp.m_tiles = (p.rows_out + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
       const long long pair_tiles = static_cast<long long>(pp.batches) * pp.m_tiles * pp.n_tiles;
       const int pgrid = 2 * static_cast<int>(pair_tiles < h->sms / 2 ? pair_tiles : h->sms / 2);
-      const cudaError_t e = launch_kernel(h->pdl != 0, bhstem_conv_gelu_pair_kernel, pgrid, THREADS_SHARED, PAIR_SMEM_BYTES,
-                                          stream, map_a0, map_a1, *sel.map_w_half, sel.bias,
-                                          static_cast<__nv_bfloat16*>(out), pp, st);
+      const bool wide = sel.epi_warps == 16;
+      const cudaError_t e =
+          wide ? launch_kernel(h->pdl != 0, bhstem_conv_gelu_pair_kernel<16, 6>, pgrid, PairCfg<16, 6>::THREADS,
+                               PairCfg<16, 6>::SMEM_BYTES, stream, map_a0, map_a1, *sel.map_w_half, sel.bias,
+                               static_cast<__nv_bfloat16*>(out), pp, st)
+               : launch_kernel(h->pdl != 0, bhstem_conv_gelu_pair_kernel<8, 8>, pgrid, PairCfg<8, 8>::THREADS,
+                               PairCfg<8, 8>::SMEM_BYTES, stream, map_a0, map_a1, *sel.map_w_half, sel.bias,
+                               static_cast<__nv_bfloat16*>(out), pp, st);
       if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
       ++h->launches;
       return BHSTEM_OK;
@@ -1266,7 +1453,8 @@ int bhstem_create(int32_t c_in, int32_t d_model, const float* conv1_weight, cons
     opt_in(reinterpret_cast<const void*>(bhstem_conv_gelu_kernel<128>), Cfg<128>::SMEM_BYTES);
     opt_in(reinterpret_cast<const void*>(bhstem_conv_gelu_shared_kernel<256>), CfgShared<256>::SMEM_BYTES);
     opt_in(reinterpret_cast<const void*>(bhstem_conv_gelu_shared_kernel<128>), CfgShared<128>::SMEM_BYTES);
-    opt_in(reinterpret_cast<const void*>(bhstem_conv_gelu_pair_kernel), PAIR_SMEM_BYTES);
+    opt_in(reinterpret_cast<const void*>(bhstem_conv_gelu_pair_kernel<8, 8>), PairCfg<8, 8>::SMEM_BYTES);
+    opt_in(reinterpret_cast<const void*>(bhstem_conv_gelu_pair_kernel<16, 6>), PairCfg<16, 6>::SMEM_BYTES);
     if (ea != cudaSuccess) { bhstem_destroy(h); return cuda_fail(ea, "cudaFuncSetAttribute"); }
   }
   if (rc != BHSTEM_OK) { bhstem_destroy(h); return rc; }
@@ -1291,6 +1479,14 @@ int bhstem_set_option(bhstem_handle* h, int32_t option, int64_t value) {
     h->pdl = static_cast<int>(value);
     return BHSTEM_OK;
   }
+  if (option == BHSTEM_OPT_EPILOGUE_WARPS) {
+    for (int i = 0; i < 3; ++i) {
+      const int v = static_cast<int>((value >> (8 * i)) & 0xff);
+      if (v != 8 && v != 16) return fail(BHSTEM_EINVAL, "BHSTEM_OPT_EPILOGUE_WARPS takes 8 or 16 per byte (conv1, conv2, split conv1)");
+    }
+    for (int i = 0; i < 3; ++i) h->epi_warps[i] = static_cast<int>((value >> (8 * i)) & 0xff);
+    return BHSTEM_OK;
+  }
   if (option != BHSTEM_OPT_VARIANT) return fail(BHSTEM_EINVAL, "unknown option");
   if (value != BHSTEM_VARIANT_TAP_BOXES && value != BHSTEM_VARIANT_SHARED_TAPS && value != BHSTEM_VARIANT_CTA_PAIRS)
     return fail(BHSTEM_EINVAL, "unknown kernel variant");
@@ -1304,8 +1500,8 @@ int bhstem_forward_stage(bhstem_handle* h, int32_t stage, const void* in, int64_
   if (rc != BHSTEM_OK) return rc;
   if (stage != 1 && stage != 2) return fail(BHSTEM_EINVAL, "stage must be 1 or 2");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const StageSel sel = stage == 1 ? StageSel{h->c_in, &h->map_w1, &h->map_w1_half, h->b1, 0, 0}
-                                  : StageSel{h->d, &h->map_w2, &h->map_w2_half, h->b2, 0, 0};
+  const StageSel sel = stage == 1 ? StageSel{h->c_in, &h->map_w1, &h->map_w1_half, h->b1, 0, 0, h->epi_warps[0]}
+                                  : StageSel{h->d, &h->map_w2, &h->map_w2_half, h->b2, 0, 0, h->epi_warps[1]};
   return h->bn == 256 ? launch_stage<256>(h, stage, sel, in, B, T, out, s) : launch_stage<128>(h, stage, sel, in, B, T, out, s);
 }
 
@@ -1325,6 +1521,13 @@ int bhstem_prepare_split(bhstem_handle* h, int32_t n_var) {
   if (dev != h->device) return fail(BHSTEM_EDEVICE, "handle was created on another device than the current one");
   if (h->n_var == n_var) return BHSTEM_OK;
   if (h->n_var != 0) return fail(BHSTEM_EINVAL, "this handle is already prepared for another n_var");
+  {
+    const size_t smem = static_cast<size_t>(BIAS_BCH) * (h->c_in - n_var) * sizeof(float);
+    if (smem > 200 * 1024) return fail(BHSTEM_EINVAL, "too many time-constant channels for the folded-bias kernel (c_in - n_var <= 6400)");
+    const cudaError_t ea = cudaFuncSetAttribute(reinterpret_cast<const void*>(bhstem_cond_bias_kernel),
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute");
+  }
   __nv_bfloat16* w = nullptr;
   const size_t rows = static_cast<size_t>(3) * h->d;
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&w), rows * n_var * 2);
@@ -1354,13 +1557,24 @@ int bhstem_forward_split(bhstem_handle* h, const void* x_var, const void* cond, 
       (reinterpret_cast<uintptr_t>(hidden) & 15))
     return fail(BHSTEM_EINVAL, "buffers must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int by = static_cast<int>(B < 16 ? B : 16);
-  bhstem_cond_bias_kernel<<<dim3((h->d + BIAS_WARPS - 1) / BIAS_WARPS, by), BIAS_WARPS * 32, 0, s>>>(
-      h->w1, h->b1, static_cast<const __nv_bfloat16*>(cond), bias3, static_cast<int>(B), h->d, h->c_in, h->n_var);
+  {
+    // about two CTAs per SM, each owning a multiple of BIAS_BCH windows
+    const int gx = (h->d + BIAS_WARPS - 1) / BIAS_WARPS;
+    const int chunks = static_cast<int>((B + BIAS_BCH - 1) / BIAS_BCH);
+    int by = (2 * h->sms + gx - 1) / gx;
+    if (by > chunks) by = chunks;
+    if (by < 1) by = 1;
+    const int b_per_cta = ((chunks + by - 1) / by) * BIAS_BCH;
+    by = static_cast<int>((B + b_per_cta - 1) / b_per_cta);
+    const size_t smem = static_cast<size_t>(BIAS_BCH) * (h->c_in - h->n_var) * sizeof(float);
+    bhstem_cond_bias_kernel<<<dim3(gx, by), BIAS_WARPS * 32, smem, s>>>(
+        h->w1, h->b1, static_cast<const __nv_bfloat16*>(cond), bias3, static_cast<int>(B), h->d, h->c_in, h->n_var,
+        b_per_cta);
+  }
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
   ++h->launches;
-  const StageSel sel{h->n_var, &h->map_w1v, &h->map_w1v_half, bias3, 3 * h->d, h->d};
+  const StageSel sel{h->n_var, &h->map_w1v, &h->map_w1v_half, bias3, 3 * h->d, h->d, h->epi_warps[2]};
   rc = h->bn == 256 ? launch_stage<256>(h, 1, sel, x_var, B, T, hidden, s) : launch_stage<128>(h, 1, sel, x_var, B, T, hidden, s);
   if (rc == BHSTEM_OK) rc = bhstem_forward_stage(h, 2, hidden, B, T, y, stream);
   return rc;

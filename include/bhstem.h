@@ -106,6 +106,11 @@ int bhstem_forward_split(bhstem_handle* h, const void* x_var, const void* cond, 
  * init, TMEM allocation) overlaps the tail of the previous kernel in the stream; every global access still
  * waits for that kernel to complete (griddepcontrol.wait).  0: plain stream order. */
 #define BHSTEM_OPT_PDL 2
+/* Epilogue warps of the CTA-pair kernel, one byte per stage: bits 0-7 conv1, 8-15 conv2, 16-23 the split conv1;
+ * each 8 (two warps per TMEM lane quarter, 8-stage weight ring) or 16 (four per quarter, 6-stage ring).  Default
+ * 8 / 8 / 16: the full convolutions are bound by the tensor pipe, the split conv1 (15 MMA steps per tile) by the
+ * epilogue's GELU.  Same results bit for bit. */
+#define BHSTEM_OPT_EPILOGUE_WARPS 3
 int bhstem_set_option(bhstem_handle* h, int32_t option, int64_t value);
 
 int bhstem_version(void);
