@@ -447,3 +447,46 @@ def test_split_errors(dev):
     with pytest.raises(RuntimeError):
         stem.forward_split(torch.zeros(1, 64, 88, dtype=torch.bfloat16, device=dev),
                            torch.zeros(1, 376, dtype=torch.bfloat16, device=dev))
+
+
+def test_cuda_graph_capture_of_the_split_serving_chain(dev):
+    """The split form of the serving chain -- frontend writing bf16 frames, folded bias, split conv1, conv2:
+    four launches -- captured once and replayed on new audio gives the eager bits, and stays within the bf16
+    tolerance of the chain over the materialised encoder input."""
+    from beatheritage_b200 import MelSpectrogram
+    from tests.golden import signals
+    mel = MelSpectrogram("torchaudio", True, 16000, 1024, 80, 128, 20, 8000, "reflect").to(dev)
+    stem = make_stem(464, 768, dev, seed=6)
+    torch.manual_seed(3)
+    cond = torch.randn(1, 384, device=dev)
+    cond16 = cond.to(torch.bfloat16)
+    x = torch.zeros(1, 524160, device=dev)
+    songs = [torch.from_numpy(signals.music(524160, seed=s).reshape(1, 524160)).to(dev) for s in (31, 32)]
+    frames = torch.empty(1, 4096, 80, dtype=torch.bfloat16, device=dev)
+    hidden = torch.empty(1, 4096, 768, dtype=torch.bfloat16, device=dev)
+    out = torch.empty(1, 2048, 768, dtype=torch.bfloat16, device=dev)
+
+    def chain():
+        return stem.forward_split(mel.forward_into(x, frames), cond16, hidden=hidden, out=out)
+
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        x.copy_(songs[0])
+        for _ in range(3):
+            chain()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        y = chain()
+    assert y.data_ptr() == out.data_ptr()
+    for song in songs:
+        x.copy_(song)
+        graph.replay()
+        replayed = out.clone()
+        eager = chain().clone()
+        full = stem(mel.forward_encoder_input(x, [cond], dtype=torch.bfloat16, channels_first=False)).clone()
+        torch.cuda.synchronize()
+        assert torch.equal(replayed, eager)
+        assert_close(replayed, full, "split chain vs chain over the encoder input", 0.10)

@@ -248,9 +248,37 @@ def run_c5(ctx):
                 def ours():
                     return stem(mel.forward_encoder_input(xd, [cvec], channels_first=False))
 
+                # split form: bf16 frames straight from the frontend, conditioning channels folded into a bias
+                frames16 = torch.empty(batch, 4096, 80, dtype=torch.bfloat16, device=dev)
+                hid16 = torch.empty(batch, 4096, enc.conv1.out_channels, dtype=torch.bfloat16, device=dev)
+                out16 = torch.empty(batch, 2048, enc.conv1.out_channels, dtype=torch.bfloat16, device=dev)
+                cvec16 = cvec.to(torch.bfloat16).contiguous()
+
+                def ours_split():
+                    return stem.forward_split(mel.forward_into(xd, frames16), cvec16, hidden=hid16, out=out16)
+
                 fr_btc = mel.forward_encoder_input(xd, [cvec], channels_first=False)
                 fr_bct = fr_btc.swapaxes(1, 2).contiguous()
                 a, b = ref_ops().float(), ours().float()
+                b_split = ours_split().float().clone()
+                split_graph_ms = None
+                try:
+                    side = torch.cuda.Stream(device=dev)
+                    side.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(side):
+                        for _ in range(3):
+                            ours_split()
+                    torch.cuda.current_stream(dev).wait_stream(side)
+                    torch.cuda.synchronize()
+                    sgraph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(sgraph):
+                        sg_out = ours_split()
+                    sgraph.replay()
+                    torch.cuda.synchronize()
+                    if torch.equal(sg_out.float(), b_split):
+                        split_graph_ms = timed(sgraph.replay, 50)
+                except Exception as e:  # noqa: BLE001
+                    split_graph_ms = f"unavailable: {type(e).__name__}: {e}"
                 # the same chain captured once in a CUDA graph (the serving loop: no host work per call)
                 graph_ms = None
                 try:
@@ -278,6 +306,9 @@ def run_c5(ctx):
                     "stem_only_ours_ms": timed(lambda: stem(fr_btc), 20),
                     "max_abs_diff": float((a - b).abs().max()),
                     "max_abs_value": float(a.abs().max()),
+                    "ours_split_frontend_to_stem_ms": timed(ours_split, 20),
+                    "ours_split_frontend_to_stem_cuda_graph_ms": split_graph_ms,
+                    "split_max_abs_diff_vs_reference_ops": float((a - b_split).abs().max()),
                 }
         c5["conv_stem_N3"] = stem_res
         return c5
