@@ -122,11 +122,8 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+[[maybe_unused]] __device__ __forceinline__ void mbar_arrive(uint32_t bar) {      // -DBHSTEM_PROFILE experiments only
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {     // barrier in any CTA of the cluster
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 // Hand-back of a TMEM accumulator stage: what has to be ordered before the arrival are this warp's tcgen05.ld
 // reads, and those are complete (tcgen05.wait::ld) and fenced (tcgen05.fence::before_thread_sync) already.  A
@@ -196,6 +193,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // waiting warp does not take issue slots from the epilogue warps on its scheduler (the tight poll loops were
 // 28 % of the split conv1's executed instructions).  The MMA issuer waits this way for a free accumulator
 // stage (a long wait exactly when the epilogue is the bound) and keeps the tight loop for its operands.
+// (A try_wait with a 20 us suspend-time hint instead of the nanosleep back-off measured the same: 136.3 against
+// 136.5 us for the split conv1, 225.6 against 224.5 us for conv2 at 46 windows.)
 __device__ __noinline__ void mbar_wait_sleep_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   unsigned ns = 32;
@@ -289,7 +288,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // 15 instructions + 2 MUFU against ~24 for erff (whose SASS spends 9 FSEL per element selecting
 // coefficients); after the bf16 rounding it equals torch's fp32 erf GELU everywhere except a handful of
 // inputs in the tail x <= -3.5 where 1 + erf cancels in both (|diff| <= 4e-6).  -DBHSTEM_ERFF restores erff.
-__device__ __forceinline__ float gelu_of_bf16(const float x) {
+[[maybe_unused]] __device__ __forceinline__ float gelu_of_bf16(const float x) {      // the scalar statement of the formula (-DBHSTEM_SCALAR_GELU)
 #ifdef BHSTEM_TIMING_NO_GELU      // timing experiments only: wrong results
   return x;
 #endif
@@ -1101,7 +1100,7 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
 // it BIAS_BCH windows at a time: their conditioning vectors are converted to fp32 once into shared memory, a
 // lane keeps the 3 x 8 weights of its 16-byte piece in registers (converted once per chunk) and multiplies
 // them with all BIAS_BCH vectors -- 24 FFMA per 2 LDS.128, no conversions in the inner loop.
-constexpr int BIAS_WARPS = 8, BIAS_BCH = 8;
+constexpr int BIAS_WARPS = 8, BIAS_BCH = 16;
 __global__ void __launch_bounds__(BIAS_WARPS * 32)
 bhstem_cond_bias_kernel(const __nv_bfloat16* __restrict__ w /* [3][D][C] */, const float* __restrict__ bias,
                         const __nv_bfloat16* __restrict__ cond /* [B][C - n_var] */, float* __restrict__ bias3,
