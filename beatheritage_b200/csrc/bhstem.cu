@@ -455,6 +455,8 @@ __device__ __forceinline__ void epilogue_role(const StemProblem& p, const float*
       __syncwarp();
     }
     const float* bl = bst + (is_edge ? edge * (CHUNKS * 32) : 0);
+    BHS_CHECK(bl >= bst && bl + CHUNKS * 32 <= bst + 3 * CHUNKS * 32 && bst + 3 * CHUNKS * 32 <= bias_stage_all + EW * 3 * CHUNKS * 32);
+    BHS_CHECK(p.bias_edge_stride == 0 || (b < p.batches && nt * BN + (half + 1) * CHUNKS * 32 <= p.n_out));
 #ifdef BHSTEM_PROFILE
     { const long long t0p = clock64(); mbar_wait_sleep(tfull0 + 8 * as, aphase); if (warp == 2 && lane == 0) atomicAdd(&g_prof[5], static_cast<unsigned long long>(clock64() - t0p)); }
 #else

@@ -110,4 +110,24 @@ for (B, T, c_in, d) in ((2, 256, 464, 768), (1, 200, 464, 768), (3, 64, 80, 384)
         diff = (y.float().cpu() - want).abs()
         assert bool((diff <= want.abs() * 2.0 ** -6 + 4e-3).all()), float(diff.max())
     n_cases += 1
+# ---- split conv stem (folded conditioning channels, 8 and 16 epilogue warps): the reference's dims, ragged rows,
+# every frame an edge, the 128-column kernel
+for (B, T, c_in, d, n_var) in ((2, 256, 464, 768, 80), (1, 200, 464, 768, 80), (1, 2, 16, 128, 8), (3, 64, 80, 384, 16),
+                               (17, 258, 464, 768, 80)):
+    stem = ConvStem(c_in, d)
+    with torch.no_grad():
+        for prm in stem.parameters():
+            prm.copy_(prm.to(torch.bfloat16).float())
+    stem = stem.to(dev)
+    x = (torch.randn(B, T, c_in) * 1.5).to(torch.bfloat16)
+    x[:, :, n_var:] = x[:, :1, n_var:]
+    for epi in (16, 8):
+        stem.set_epilogue_warps(8, 8, epi)
+        y = stem.forward_split(x[:, :, :n_var].contiguous().to(dev), x[:, 0, n_var:].contiguous().to(dev))
+        torch.cuda.synchronize()
+        if B * T <= 1024:
+            want = conv_stem_oracle.conv_stem(x, stem.conv1.weight.cpu(), stem.conv1.bias.cpu(), stem.conv2.weight.cpu(), stem.conv2.bias.cpu())
+            diff = (y.float().cpu() - want).abs()
+            assert bool((diff <= want.abs() * 2.0 ** -6 + 4e-3).all()), float(diff.max())
+        n_cases += 1
 print(f"bounds ok: {n_cases} cases through libbhmel_bounds.so / libbhstem_bounds.so, no assertion fired")
