@@ -490,3 +490,35 @@ def test_cuda_graph_capture_of_the_split_serving_chain(dev):
         torch.cuda.synchronize()
         assert torch.equal(replayed, eager)
         assert_close(replayed, full, "split chain vs chain over the encoder input", 0.10)
+
+
+def test_split_stem_is_reentrant_across_threads_and_streams(dev):
+    """One ConvStem (one handle) driven by two host threads on their own streams with different conditioning
+    vectors: the folded bias lives in a per-call scratch, the handle is read-only after bhstem_prepare_split."""
+    import threading
+    stem = make_stem(464, 768, dev, seed=51)
+    xs = [make_input(2, 512, 464, seed=s) for s in (52, 53)]
+    frames = [x[:, :, :80].contiguous().to(dev) for x in xs]
+    conds = [x[:, 0, 80:].contiguous().to(dev) for x in xs]
+    refs = [stem.forward_split(f, c).clone() for f, c in zip(frames, conds)]
+    torch.cuda.synchronize()
+    assert not torch.equal(refs[0], refs[1])
+    errors = []
+
+    def worker(f, c, ref):
+        try:
+            s = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(s):
+                for _ in range(40):
+                    if not torch.equal(stem.forward_split(f, c), ref):
+                        errors.append("mismatch")
+            s.synchronize()
+        except Exception as e:   # pragma: no cover
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=a) for a in zip(frames, conds, refs)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert errors == []
