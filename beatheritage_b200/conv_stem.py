@@ -82,6 +82,8 @@ class ConvStem(nn.Module):
                 _stem_lib.check(lib.bhstem_set_option(out.value, 1, self._variant))
             if getattr(self, "_epi", None) is not None:
                 _stem_lib.check(lib.bhstem_set_option(out.value, 3, self._epi))
+            if not getattr(self, "_small", True):
+                _stem_lib.check(lib.bhstem_set_option(out.value, 4, 0))
             if not getattr(self, "_pdl", True):
                 _stem_lib.check(lib.bhstem_set_option(out.value, 2, 0))
             self._handles[idx] = out.value
@@ -120,6 +122,14 @@ class ConvStem(nn.Module):
         lib = _stem_lib.lib()
         for h in self._handles.values():
             _stem_lib.check(lib.bhstem_set_option(h, 3, self._epi))
+
+    def set_small_batch_tiles(self, on: bool) -> None:
+        """128-column tiles for launches that would leave half the SMs idle (default on; same bits).
+        BHSTEM_OPT_SMALL_BATCH_TILES, include/bhstem.h."""
+        self._small = bool(on)
+        lib = _stem_lib.lib()
+        for h in self._handles.values():
+            _stem_lib.check(lib.bhstem_set_option(h, 4, int(self._small)))
 
     def set_pdl(self, on: bool) -> None:
         """Programmatic dependent launch (default on): a kernel's prologue overlaps the previous kernel's tail;

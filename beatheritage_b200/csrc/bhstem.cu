@@ -1113,7 +1113,18 @@ bhstem_cond_bias_kernel(const __nv_bfloat16* __restrict__ w /* [3][D][C] */, con
   const bool active = n < d;
   const int n_cond = c - n_var, vecs = n_cond >> 3;         // n_var % 8 == 0 and C % 8 == 0: whole 16-byte pieces
   const int b_begin = blockIdx.y * b_per_cta, b_end = min(batches, b_begin + b_per_cta);
+  // Launched as a programmatic dependent: the next kernel (the split conv1) may set up while this one runs, and
+  // everything that does not depend on the previous kernel in the stream -- the handle's weights and bias: the long
+  // DRAM latency of this kernel -- is fetched BEFORE waiting for it.  `cond` may be that kernel's output.
+  pdl_launch_dependents();
   const float bn = active ? bias[n] : 0.f;
+  uint4 w_first[3] = {};
+  if (active && lane < vecs) {
+#pragma unroll
+    for (int tap = 0; tap < 3; ++tap)
+      w_first[tap] = __ldg(reinterpret_cast<const uint4*>(w + (static_cast<size_t>(tap) * d + n) * c + n_var) + lane);
+  }
+  pdl_wait();
   for (int b0 = b_begin; b0 < b_end; b0 += BIAS_BCH) {
     const int nb = min(BIAS_BCH, b_end - b0);
     __syncthreads();                                        // the previous chunk's vectors are no longer read
@@ -1136,7 +1147,8 @@ bhstem_cond_bias_kernel(const __nv_bfloat16* __restrict__ w /* [3][D][C] */, con
       float wf[3][8];
 #pragma unroll
       for (int tap = 0; tap < 3; ++tap) {
-        const uint4 wv = __ldg(reinterpret_cast<const uint4*>(w + (static_cast<size_t>(tap) * d + n) * c + n_var) + v);
+        const uint4 wv = v == lane ? w_first[tap]
+                                   : __ldg(reinterpret_cast<const uint4*>(w + (static_cast<size_t>(tap) * d + n) * c + n_var) + v);
         const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {                        // bf16 -> fp32 is a shift; the products are exact in fp32
@@ -1229,6 +1241,7 @@ struct bhstem_handle {
   int variant = 1;      // 1: shared taps (row-shifted descriptors, default), 0: one TMA box per tap
   int pdl = 1;          // 1 (default): launch with programmatic stream serialisation (prologue overlaps the previous grid's tail)
   int pairs = 1;        // 1 (default): CTA-pair kernel (tcgen05 cta_group::2) when d_model % 256 == 0 and the SM count is even
+  int small_batch_tiles = 1;   // 1 (default): launches with few 256-column tiles run 128-column tiles (pick_bn)
   int epi_warps[3] = {8, 8, 16};   // CTA-pair kernel, epilogue warps for conv1 / conv2 / the split conv1 (BHSTEM_OPT_EPILOGUE_WARPS)
   int exp = 0;          // -DBHSTEM_PROFILE builds only: BHSTEM_EXP timing experiments (wrong results)
 };
@@ -1356,6 +1369,17 @@ int launch_stage(bhstem_handle* h, int stage, const StageSel& sel, const void* i
   if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
   ++h->launches;
   return BHSTEM_OK;
+}
+
+// Tile width of one launch.  d_model % 256 == 0 normally runs 256-column tiles (CTA pairs); when a launch has so
+// few of them that half the SMs would idle (one window of conv2: 16 x 3 tiles on 148 SMs) it runs the 128-column
+// one-CTA kernel instead -- twice the tiles at half the work each.  Same products in the same order per output
+// element, so the results are the same bits.
+int pick_bn(const bhstem_handle* h, int stage, int64_t B, int64_t T) {
+  if (h->bn == 128 || !h->small_batch_tiles) return h->bn;
+  const int64_t rows_out = stage == 1 ? T : T / 2;
+  const int64_t tiles256 = B * ((rows_out + BLOCK_M - 1) / BLOCK_M) * (h->d / 256);
+  return 2 * tiles256 <= h->sms ? 128 : 256;
 }
 
 int check_call(bhstem_handle* h, const void* in, int64_t B, int64_t T, void* out) {
@@ -1488,6 +1512,11 @@ int bhstem_set_option(bhstem_handle* h, int32_t option, int64_t value) {
     for (int i = 0; i < 3; ++i) h->epi_warps[i] = static_cast<int>((value >> (8 * i)) & 0xff);
     return BHSTEM_OK;
   }
+  if (option == BHSTEM_OPT_SMALL_BATCH_TILES) {
+    if (value != 0 && value != 1) return fail(BHSTEM_EINVAL, "BHSTEM_OPT_SMALL_BATCH_TILES takes 0 or 1");
+    h->small_batch_tiles = static_cast<int>(value);
+    return BHSTEM_OK;
+  }
   if (option != BHSTEM_OPT_VARIANT) return fail(BHSTEM_EINVAL, "unknown option");
   if (value != BHSTEM_VARIANT_TAP_BOXES && value != BHSTEM_VARIANT_SHARED_TAPS && value != BHSTEM_VARIANT_CTA_PAIRS)
     return fail(BHSTEM_EINVAL, "unknown kernel variant");
@@ -1503,7 +1532,10 @@ int bhstem_forward_stage(bhstem_handle* h, int32_t stage, const void* in, int64_
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const StageSel sel = stage == 1 ? StageSel{h->c_in, &h->map_w1, &h->map_w1_half, h->b1, 0, 0, h->epi_warps[0]}
                                   : StageSel{h->d, &h->map_w2, &h->map_w2_half, h->b2, 0, 0, h->epi_warps[1]};
-  return h->bn == 256 ? launch_stage<256>(h, stage, sel, in, B, T, out, s) : launch_stage<128>(h, stage, sel, in, B, T, out, s);
+  if (pick_bn(h, stage, B, T) == 256) return launch_stage<256>(h, stage, sel, in, B, T, out, s);
+  // 128-column tiles: the 128-row-box weight map is the one the CTA-pair kernel uses for its halves
+  const StageSel narrow{sel.c, h->bn == 256 ? sel.map_w_half : sel.map_w, sel.map_w_half, sel.bias, 0, 0, sel.epi_warps};
+  return launch_stage<128>(h, stage, narrow, in, B, T, out, s);
 }
 
 int bhstem_forward(bhstem_handle* h, const void* x, int64_t B, int64_t T, void* hidden, void* y, void* stream) {
@@ -1568,15 +1600,31 @@ int bhstem_forward_split(bhstem_handle* h, const void* x_var, const void* cond, 
     const int b_per_cta = ((chunks + by - 1) / by) * BIAS_BCH;
     by = static_cast<int>((B + b_per_cta - 1) / b_per_cta);
     const size_t smem = static_cast<size_t>(BIAS_BCH) * (h->c_in - h->n_var) * sizeof(float);
-    bhstem_cond_bias_kernel<<<dim3(gx, by), BIAS_WARPS * 32, smem, s>>>(
-        h->w1, h->b1, static_cast<const __nv_bfloat16*>(cond), bias3, static_cast<int>(B), h->d, h->c_in, h->n_var,
-        b_per_cta);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(gx), static_cast<unsigned>(by));
+    cfg.blockDim = dim3(BIAS_WARPS * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = h->pdl ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, bhstem_cond_bias_kernel, static_cast<const __nv_bfloat16*>(h->w1),
+                                             static_cast<const float*>(h->b1), static_cast<const __nv_bfloat16*>(cond), bias3,
+                                             static_cast<int>(B), static_cast<int>(h->d), static_cast<int>(h->c_in),
+                                             static_cast<int>(h->n_var), b_per_cta);
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
   }
-  const cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
   ++h->launches;
   const StageSel sel{h->n_var, &h->map_w1v, &h->map_w1v_half, bias3, 3 * h->d, h->d, h->epi_warps[2]};
-  rc = h->bn == 256 ? launch_stage<256>(h, 1, sel, x_var, B, T, hidden, s) : launch_stage<128>(h, 1, sel, x_var, B, T, hidden, s);
+  if (pick_bn(h, 1, B, T) == 256) {
+    rc = launch_stage<256>(h, 1, sel, x_var, B, T, hidden, s);
+  } else {
+    const StageSel narrow{sel.c, h->bn == 256 ? sel.map_w_half : sel.map_w, sel.map_w_half, sel.bias, sel.bias_batch_stride,
+                          sel.bias_edge_stride, sel.epi_warps};
+    rc = launch_stage<128>(h, 1, narrow, x_var, B, T, hidden, s);
+  }
   if (rc == BHSTEM_OK) rc = bhstem_forward_stage(h, 2, hidden, B, T, y, stream);
   return rc;
 }

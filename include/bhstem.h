@@ -111,6 +111,10 @@ int bhstem_forward_split(bhstem_handle* h, const void* x_var, const void* cond, 
  * 8 / 8 / 16: the full convolutions are bound by the tensor pipe, the split conv1 (15 MMA steps per tile) by the
  * epilogue's GELU.  Same results bit for bit. */
 #define BHSTEM_OPT_EPILOGUE_WARPS 3
+/* 1 (default): a launch with so few 256-column tiles that half the SMs would idle (one window of conv2: 48 tiles
+ * on 148 SMs) runs 128-column tiles on the one-CTA kernel instead -- twice the tiles, half the work each, same
+ * bits.  0: always the handle's tile width. */
+#define BHSTEM_OPT_SMALL_BATCH_TILES 4
 int bhstem_set_option(bhstem_handle* h, int32_t option, int64_t value);
 
 int bhstem_version(void);

@@ -522,3 +522,17 @@ def test_split_stem_is_reentrant_across_threads_and_streams(dev):
     for t in threads:
         t.join()
     assert errors == []
+
+
+def test_small_batch_tile_width_gives_the_same_bits(dev):
+    """One window leaves most SMs without a 256-column tile, so conv2 (and anything smaller) runs 128-column tiles
+    by default (BHSTEM_OPT_SMALL_BATCH_TILES): same products in the same order, identical results."""
+    stem = make_stem(464, 768, dev, seed=61)
+    x = make_input(1, 4096, 464, seed=62).to(dev)
+    frames, cond = x[:, :, :80].contiguous(), x[:, 0, 80:].contiguous()
+    got = (stem(x).clone(), stem.forward_split(frames, cond).clone(), stem(x[:, :200]).clone())
+    stem.set_small_batch_tiles(False)
+    want = (stem(x).clone(), stem.forward_split(frames, cond).clone(), stem(x[:, :200]).clone())
+    torch.cuda.synchronize()
+    for g, w in zip(got, want):
+        assert torch.equal(g, w)

@@ -14,6 +14,8 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
 stem = ConvStem(464, 768).to(dev)
+if "nosmall" in sys.argv:
+    stem.set_small_batch_tiles(False)
 x = (torch.randn(B, 4096, 464, device=dev) * 1.5).to(torch.bfloat16)
 ts = []
 for _ in range(reps):

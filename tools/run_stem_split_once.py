@@ -15,7 +15,9 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
 stem = ConvStem(464, 768).to(dev)
-if len(sys.argv) > 3:
+if "nosmall" in sys.argv:
+    stem.set_small_batch_tiles(False)
+if len(sys.argv) > 3 and sys.argv[3].isdigit():
     stem.set_epilogue_warps(8, 8, int(sys.argv[3]))
 frames = (torch.randn(B, 4096, 80, device=dev) * 1.5).to(torch.bfloat16)
 cond = (torch.randn(B, 384, device=dev) * 1.5).to(torch.bfloat16)
