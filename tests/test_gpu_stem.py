@@ -536,3 +536,23 @@ def test_small_batch_tile_width_gives_the_same_bits(dev):
     torch.cuda.synchronize()
     for g, w in zip(got, want):
         assert torch.equal(g, w)
+
+
+@pytest.mark.parametrize("B,T", [(2, 512), (1, 200), (3, 4096)])
+def test_kernel_variants_agree_on_the_split_stem(dev, B, T):
+    """Every schedule runs the split conv1 with the same per-window bias addressing: the CTA-pair kernel with 16 and
+    8 epilogue warps and the one-CTA shared-tap kernel give identical bits, the one-box-per-tap kernel (tap-major
+    summation) the stem's usual tolerance."""
+    stem = make_stem(464, 768, dev, seed=4)
+    x = make_input(B, T, 464, seed=B * 11 + T)
+    frames, cond = x[:, :, :80].contiguous().to(dev), x[:, 0, 80:].contiguous().to(dev)
+    outs = {}
+    for variant in ("cta_pairs", "shared_taps", "tap_boxes"):
+        stem.set_variant(variant)
+        outs[variant] = stem.forward_split(frames, cond).clone()
+    stem.set_variant("cta_pairs")
+    stem.set_epilogue_warps(8, 8, 8)
+    outs["cta_pairs_8"] = stem.forward_split(frames, cond).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(outs["cta_pairs"], outs["shared_taps"]) and torch.equal(outs["cta_pairs"], outs["cta_pairs_8"])
+    assert_close(outs["tap_boxes"], outs["shared_taps"], "tap_boxes vs shared_taps (split)", max_frac=0.10)
