@@ -186,7 +186,7 @@ class ConvStem(nn.Module):
 
     @torch.no_grad()
     def forward_split(self, frames: torch.Tensor, cond: torch.Tensor, hidden: torch.Tensor | None = None,
-                      out: torch.Tensor | None = None) -> torch.Tensor:
+                      out: torch.Tensor | None = None, bias_scratch: torch.Tensor | None = None) -> torch.Tensor:
         """The stem on the reference's encoder input WITHOUT building it: `frames` [B, T, n_mels] bf16 (what
         `MelSpectrogram.forward_into` writes into a dense bf16 buffer) and `cond` [B, C_in - n_mels] bf16, the
         concatenated conditioning embeddings of each window, which the reference repeats over the T frames
@@ -197,7 +197,8 @@ class ConvStem(nn.Module):
 
         up to the fp32 summation order inside conv1: the time-constant channels are folded into a per-window
         bias (three small sums per output channel), conv1 multiplies n_mels instead of C_in channels.
-        bhstem_forward_split, include/bhstem.h."""
+        `bias_scratch` [B, 3, D] float32 may be passed in like `hidden` / `out` (it receives the folded bias:
+        interior frames, frame 0, frame T - 1).  bhstem_forward_split, include/bhstem.h."""
         C, D = self.conv1.in_channels, self.conv1.out_channels
         if frames.dim() != 3 or cond.dim() != 2 or frames.shape[0] != cond.shape[0] or frames.shape[2] + cond.shape[1] != C:
             raise RuntimeError(f"expected frames [B, T, n] and cond [B, {C} - n], got {tuple(frames.shape)} and {tuple(cond.shape)}")
@@ -218,7 +219,10 @@ class ConvStem(nn.Module):
         if hidden is None:
             hidden = torch.empty((B, T, D), dtype=torch.bfloat16, device=frames.device)
         y = out if out is not None else torch.empty((B, T // 2, D), dtype=torch.bfloat16, device=frames.device)
-        bias3 = torch.empty((B, 3, D), dtype=torch.float32, device=frames.device)
+        if bias_scratch is not None and not (tuple(bias_scratch.shape) == (B, 3, D) and bias_scratch.dtype == torch.float32
+                                             and bias_scratch.is_contiguous() and bias_scratch.device == frames.device):
+            raise RuntimeError(f"bias_scratch must be a contiguous float32 tensor {(B, 3, D)} on {frames.device}")
+        bias3 = bias_scratch if bias_scratch is not None else torch.empty((B, 3, D), dtype=torch.float32, device=frames.device)
         h = self._split_handle_for(frames.device, n_var)
         with torch.cuda.device(frames.device):
             stream = torch.cuda.current_stream(frames.device).cuda_stream

@@ -48,3 +48,33 @@ def conv_stem(x_btc: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch
     y = conv_gelu(h, w2.detach().cpu(), b2.detach().cpu(), 2)
     y = y.permute(0, 2, 1).contiguous()
     return (y, h.permute(0, 2, 1).contiguous()) if return_hidden else y
+
+
+def folded_bias(cond_bc: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, n_var: int) -> torch.Tensor:
+    """The per-window bias of the split conv1 (include/bhstem.h, bhstem_forward_split), restated on the CPU in
+    float64: the reference repeats each window's conditioning vector over all T frames before conv1
+    (osuT5/osuT5/model/modeling_mapperatorinator.py:368-370), so those channels add, per tap,
+    S_tap[b][n] = sum_c w1[n][n_var + c][tap] * cond[b][c] -- all three taps inside the window, taps 1 and 2 at its
+    first frame (tap 0 reads conv1's zero padding, modeling_ropewhisper.py:1135 `padding=1`), taps 0 and 1 at its last.
+    cond_bc [B, C - n_var], w1 [D, C, 3], b1 [D] (values as the bf16 model holds them) -> [B, 3, D] float64:
+    rows = (interior frames, frame 0, frame T - 1)."""
+    w = _bf16_round(w1.detach().cpu().float()).double()[:, n_var:, :]
+    s = torch.einsum("nct,bc->btn", w, _bf16_round(cond_bc.detach().cpu().float()).double())      # [B, 3 taps, D]
+    b = _bf16_round(b1.detach().cpu().float()).double()
+    return torch.stack([b + s[:, 0] + s[:, 1] + s[:, 2], b + s[:, 1] + s[:, 2], b + s[:, 0] + s[:, 1]], dim=1)
+
+
+def split_conv1_preactivation(frames_btn: torch.Tensor, cond_bc: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor) -> torch.Tensor:
+    """conv1's pre-activation computed the split way in float64: the convolution over the n_var time-varying
+    channels plus folded_bias by (window, edge) -> [B, T, D].  tests/test_oracle.py checks that this equals conv1 over
+    the concatenated input [frames | cond repeated over T] exactly (up to float64 rounding)."""
+    n_var = frames_btn.shape[2]
+    x = _bf16_round(frames_btn.detach().cpu().float()).double().swapaxes(1, 2)
+    w = _bf16_round(w1.detach().cpu().float()).double()[:, :n_var, :]
+    y = F.conv1d(x, w, None, stride=1, padding=1).swapaxes(1, 2)                                   # [B, T, D]
+    fb = folded_bias(cond_bc, w1, b1, n_var)
+    T = y.shape[1]
+    y = y + fb[:, 0:1]
+    y[:, 0] += fb[:, 1] - fb[:, 0]
+    y[:, T - 1] += fb[:, 2] - fb[:, 0]
+    return y

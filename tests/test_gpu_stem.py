@@ -380,7 +380,11 @@ def test_split_conv1_edge_frames_drop_exactly_one_tap(dev):
     B, T, n_var = 2, 384, 80
     cond = make_input(B, 1, 464 - n_var, seed=22)[:, 0].contiguous()
     hidden = torch.empty(B, T, 768, dtype=torch.bfloat16, device=dev)
-    stem.forward_split(torch.zeros(B, T, n_var, dtype=torch.bfloat16, device=dev), cond.to(dev), hidden=hidden)
+    bias3 = torch.empty(B, 3, 768, device=dev)
+    stem.forward_split(torch.zeros(B, T, n_var, dtype=torch.bfloat16, device=dev), cond.to(dev), hidden=hidden,
+                       bias_scratch=bias3)
+    want3 = conv_stem_oracle.folded_bias(cond, stem.conv1.weight, stem.conv1.bias, n_var)
+    assert float((bias3.cpu().double() - want3).abs().max()) < 2e-5           # fp32 sums of 384 exact products per tap
     w = stem.conv1.weight.detach().cpu().double()[:, n_var:, :]               # [D, n_cond, 3]
     s = torch.einsum("nct,bc->btn", w, cond.double())                          # [B, 3, D]
     bias = stem.conv1.bias.detach().cpu().double()

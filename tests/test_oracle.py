@@ -216,3 +216,26 @@ def test_stem_gelu_formula_matches_torch_for_every_bf16_input():
     differs = model != want
     assert not bool((differs & (x > -3.5)).any())
     assert int(differs.sum()) <= 32 and float((model - want).abs().max()) <= 4e-6
+
+
+@pytest.mark.parametrize("B,T,c_in,d,n_var", [(2, 37, 464, 96, 80), (1, 2, 16, 8, 8), (3, 5, 24, 16, 16)])
+def test_split_conv1_algebra_equals_conv1_over_the_concatenated_input(B, T, c_in, d, n_var):
+    """N1 + N3 (bhstem_forward_split): folding the time-constant conditioning channels into a per-window bias --
+    with one tap dropped at each end of the window, where conv1 reads its zero padding -- is conv1 over the
+    reference's concatenated input (modeling_mapperatorinator.py:368-370), exactly.  float64, CPU only."""
+    from oracle import conv_stem_oracle as cso
+    g = torch.Generator().manual_seed(B * 100 + T)
+    w1 = torch.randn(d, c_in, 3, generator=g) * 0.05
+    b1 = torch.randn(d, generator=g) * 0.1
+    frames = (torch.randn(B, T, n_var, generator=g) * 1.5).to(torch.bfloat16)
+    cond = (torch.randn(B, c_in - n_var, generator=g) * 1.5).to(torch.bfloat16)
+    full = torch.cat([frames, cond.unsqueeze(1).expand(-1, T, -1)], dim=-1).double().swapaxes(1, 2)
+    w = w1.to(torch.bfloat16).double()
+    want = torch.nn.functional.conv1d(full, w, b1.to(torch.bfloat16).double(), padding=1).swapaxes(1, 2)
+    got = cso.split_conv1_preactivation(frames, cond, w1, b1)
+    assert got.shape == want.shape == (B, T, d)
+    assert float((got - want).abs().max()) < 1e-11
+    fb = cso.folded_bias(cond, w1, b1, n_var)
+    assert fb.shape == (B, 3, d)
+    if T > 2:      # interior frames really see all three taps, the edges one fewer
+        assert float((fb[:, 0] - fb[:, 1]).abs().max()) > 1e-3 and float((fb[:, 0] - fb[:, 2]).abs().max()) > 1e-3
