@@ -82,6 +82,8 @@ class ConvStem(nn.Module):
                 _stem_lib.check(lib.bhstem_set_option(out.value, 1, self._variant))
             if getattr(self, "_epi", None) is not None:
                 _stem_lib.check(lib.bhstem_set_option(out.value, 3, self._epi))
+            if getattr(self, "_deep", None) is not None:
+                _stem_lib.check(lib.bhstem_set_option(out.value, 5, self._deep))
             if not getattr(self, "_small", True):
                 _stem_lib.check(lib.bhstem_set_option(out.value, 4, 0))
             if not getattr(self, "_pdl", True):
@@ -122,6 +124,14 @@ class ConvStem(nn.Module):
         lib = _stem_lib.lib()
         for h in self._handles.values():
             _stem_lib.check(lib.bhstem_set_option(h, 3, self._epi))
+
+    def set_deep_a_ring(self, mask: int) -> None:
+        """3 activation + 6 weight stages (bit set, the default for conv1 / conv2) or 2 + 8 in the CTA-pair kernel, per
+        stage (bit 0 conv1, bit 1 conv2, bit 2 split conv1; A/B runs, same bits).  BHSTEM_OPT_DEEP_A_RING."""
+        self._deep = int(mask)
+        lib = _stem_lib.lib()
+        for h in self._handles.values():
+            _stem_lib.check(lib.bhstem_set_option(h, 5, self._deep))
 
     def set_small_batch_tiles(self, on: bool) -> None:
         """128-column tiles for launches that would leave half the SMs idle (default on; same bits).

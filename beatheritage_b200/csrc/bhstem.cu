@@ -857,7 +857,6 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
 // tcgen05.commit frees the stages / publishes the accumulators in BOTH CTAs (multicast), and both CTAs'
 // epilogue warps hand the accumulator stage back on the leader's TMEM-empty barrier.
 constexpr int PAIR_W_BYTES = 128 * BLOCK_K * 2;            // half of a 256-row weight tile
-constexpr int PAIR_A_STAGES = 2;
 constexpr int PAIR_ASTAGE_BYTES = A0_BYTES + A1_BYTES;
 constexpr int PAIR_BN = 256;
 
@@ -892,20 +891,21 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {     // arrives 
 
 // EW epilogue warps (8: two per TMEM lane quarter; 16: four -- the split conv1, whose 15 MMA steps per tile leave
 // the epilogue's GELU as the bound) and WST weight-ring stages (the 16-warp form trades two stages for staging room).
-template <int EW, int WST>
+template <int EW, int WST, int AST = 2>
 struct PairCfg {
   static constexpr int THREADS = 32 * (3 + EW);             // weight producer, MMA issuer, EW epilogue warps, activation producer
   static constexpr int A_WARP = 2 + EW;
-  static constexpr int SMEM_BYTES = PAIR_A_STAGES * PAIR_ASTAGE_BYTES + WST * PAIR_W_BYTES + 1024;
+  static constexpr int SMEM_BYTES = AST * PAIR_ASTAGE_BYTES + WST * PAIR_W_BYTES + 1024;
 };
 
-template <int EW, int WST>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<EW, WST>::THREADS, 1)
+template <int EW, int WST, int AST>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<EW, WST, AST>::THREADS, 1)
 bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                              const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias,
                              __nv_bfloat16* __restrict__ out, const StemProblem p, const SharedTaps st) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) unsigned long long bars[2 * PAIR_A_STAGES + 2 * WST + 4];
+  constexpr int MAXA = 2 * AST;                             // conv1 stages only the 17 KB block: up to twice the stages
+  __shared__ __align__(8) unsigned long long bars[2 * MAXA + 2 * WST + 4];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(128) uint8_t epi_staging[EW * EPI_STAGE_BYTES];
   __shared__ __align__(16) float epi_bias[12 * PAIR_BN];    // per epilogue warp: the bias of its share of the tile's columns
@@ -914,13 +914,18 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
   const uint32_t rank = cluster_rank();
   const bool leader = rank == 0;
   const uint32_t ring_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t ring_w = ring_a + PAIR_A_STAGES * PAIR_ASTAGE_BYTES;
-  const uint32_t afull0 = smem_u32(&bars[0]), aempty0 = smem_u32(&bars[PAIR_A_STAGES]);
-  const uint32_t wfull0 = smem_u32(&bars[2 * PAIR_A_STAGES]), wempty0 = smem_u32(&bars[2 * PAIR_A_STAGES + WST]);
-  const uint32_t tfull0 = smem_u32(&bars[2 * PAIR_A_STAGES + 2 * WST]), tempty0 = tfull0 + 16;
+  const uint32_t ring_w = ring_a + AST * PAIR_ASTAGE_BYTES;
+  const uint32_t afull0 = smem_u32(&bars[0]), aempty0 = smem_u32(&bars[MAXA]);
+  const uint32_t wfull0 = smem_u32(&bars[2 * MAXA]), wempty0 = smem_u32(&bars[2 * MAXA + WST]);
+  const uint32_t tfull0 = smem_u32(&bars[2 * MAXA + 2 * WST]), tempty0 = tfull0 + 16;
+  // An activation stage is the 136-row block (+ the 128-row block of even time steps for the stride-2 convolution);
+  // conv1 needs only the first, so the same shared memory holds (AST * 33 KB) / 17 KB stages of it.
+  const bool small_stage = st.n_aloads == 1;
+  const uint32_t astage_bytes = small_stage ? A0_BYTES : PAIR_ASTAGE_BYTES;
+  const uint32_t n_ast = small_stage ? (AST * PAIR_ASTAGE_BYTES) / A0_BYTES : AST;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < PAIR_A_STAGES; ++s) { mbar_init(afull0 + 8 * s, 1); mbar_init(aempty0 + 8 * s, 1); }
+    for (int s = 0; s < MAXA; ++s) { mbar_init(afull0 + 8 * s, 1); mbar_init(aempty0 + 8 * s, 1); }
     for (int s = 0; s < WST; ++s) { mbar_init(wfull0 + 8 * s, 1); mbar_init(wempty0 + 8 * s, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 2 * EW); }   // epilogue warps of both CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -949,10 +954,10 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_ns0));
 #endif
 
-  if (warp == 0 || warp == (PairCfg<EW, WST>::A_WARP)) {
+  if (warp == 0 || warp == (PairCfg<EW, WST, AST>::A_WARP)) {
     // ===================================== TMA producers (both CTAs) ========================
     // Independent single-thread producers for the activation ring (last warp) and the weight ring (warp 0).
-    if (warp == (PairCfg<EW, WST>::A_WARP) && elect_one()) {
+    if (warp == (PairCfg<EW, WST, AST>::A_WARP) && elect_one()) {
       const uint32_t afull_leader = map_to_cta(afull0, 0);
       uint32_t as = 0, aph = 0;
       for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
@@ -961,12 +966,12 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           const int c0 = ks.first_channel(kb);
           { PROF_T0(); mbar_wait_sleep(aempty0 + 8 * as, aph ^ 1); PROF_ADD(0); }
-          const uint32_t sa = ring_a + as * PAIR_ASTAGE_BYTES;
+          const uint32_t sa = ring_a + as * astage_bytes;
           if (leader) mbar_expect_tx(afull0 + 8 * as, 2 * a_bytes);           // both CTAs' activation blocks
           tma_load_3d_pair(&map_a0, afull_leader + 8 * as, sa, st.a_col[0] + c0, my_row + st.a_row[0], b);
           if (st.n_aloads == 2)
             tma_load_3d_pair(&map_a1, afull_leader + 8 * as, sa + A0_BYTES, st.a_col[1] + c0, my_row + st.a_row[1], b);
-          if (++as == PAIR_A_STAGES) { as = 0; aph ^= 1; }
+          if (++as == n_ast) { as = 0; aph ^= 1; }
         }
       }
     } else if (warp == 0 && elect_one()) {
@@ -1010,7 +1015,7 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             const bool step4 = ks.base == 4 || kb < ks.extra;
             { PROF_T0(); mbar_wait(afull0 + 8 * as, aph); PROF_ADD(2); }
-            const uint32_t a_off = as * (PAIR_ASTAGE_BYTES >> 4);
+            const uint32_t a_off = as * (astage_bytes >> 4);
 #pragma unroll
             for (int tap = 0; tap < 3; ++tap) {
               { PROF_T0(); mbar_wait(wfull0 + 8 * ws, wph); PROF_ADD(3); }
@@ -1025,7 +1030,7 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
               if (++ws == WST) { ws = 0; wph ^= 1; }
             }
             umma_commit_pair(aempty0 + 8 * as);
-            if (++as == PAIR_A_STAGES) { as = 0; aph ^= 1; }
+            if (++as == n_ast) { as = 0; aph ^= 1; }
           }
           umma_commit_pair(tfull0 + 8 * acc);
         }
@@ -1038,7 +1043,7 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           const int ksteps = ks.steps(kb);
           { PROF_T0(); mbar_wait(afull0 + 8 * as, aph); PROF_ADD(2); }
-          const uint32_t sa = ring_a + as * PAIR_ASTAGE_BYTES;
+          const uint32_t sa = ring_a + as * astage_bytes;
           for (int tap = 0; tap < 3; ++tap) {
             { PROF_T0(); mbar_wait(wfull0 + 8 * ws, wph); PROF_ADD(3); }
             tc_fence_after();
@@ -1050,7 +1055,7 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
             if (++ws == WST) { ws = 0; wph ^= 1; }
           }
           umma_commit_pair(aempty0 + 8 * as);
-          if (++as == PAIR_A_STAGES) { as = 0; aph ^= 1; }
+          if (++as == n_ast) { as = 0; aph ^= 1; }
         }
         umma_commit_pair(tfull0 + 8 * acc);
       }
@@ -1061,7 +1066,7 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
   }
 
 #ifdef BHSTEM_PROFILE
-  if (lane == 0 && warp == (PairCfg<EW, WST>::A_WARP) && leader) { PROF_FLUSH(0); }
+  if (lane == 0 && warp == (PairCfg<EW, WST, AST>::A_WARP) && leader) { PROF_FLUSH(0); }
   if (lane == 0 && warp == 0 && leader) { PROF_FLUSH(1); }
   if (lane == 0 && warp == 1 && leader) {
     PROF_FLUSH(2); PROF_FLUSH(3); PROF_FLUSH(4);
@@ -1241,6 +1246,7 @@ struct bhstem_handle {
   int variant = 1;      // 1: shared taps (row-shifted descriptors, default), 0: one TMA box per tap
   int pdl = 1;          // 1 (default): launch with programmatic stream serialisation (prologue overlaps the previous grid's tail)
   int pairs = 1;        // 1 (default): CTA-pair kernel (tcgen05 cta_group::2) when d_model % 256 == 0 and the SM count is even
+  int deep_a_ring = 3;         // bit 0 conv1, bit 1 conv2, bit 2 split conv1 (BHSTEM_OPT_DEEP_A_RING): default on for the full stages
   int small_batch_tiles = 1;   // 1 (default): launches with few 256-column tiles run 128-column tiles (pick_bn)
   int epi_warps[3] = {8, 8, 16};   // CTA-pair kernel, epilogue warps for conv1 / conv2 / the split conv1 (BHSTEM_OPT_EPILOGUE_WARPS)
   int exp = 0;          // -DBHSTEM_PROFILE builds only: BHSTEM_EXP timing experiments (wrong results)
@@ -1283,6 +1289,7 @@ struct StageSel {
   const float* bias;
   int32_t bias_batch_stride, bias_edge_stride;
   int epi_warps;           // CTA-pair kernel: 8 or 16 epilogue warps
+  int deep_a_ring = 0;     // CTA-pair kernel, 8 epilogue warps: 3 activation stages + 6 weight stages instead of 2 + 8
 };
 
 template <int BN>
@@ -1344,13 +1351,14 @@ int launch_stage(bhstem_handle* h, int stage, const StageSel& sel, const void* i
       const long long pair_tiles = static_cast<long long>(pp.batches) * pp.m_tiles * pp.n_tiles;
       const int pgrid = 2 * static_cast<int>(pair_tiles < h->sms / 2 ? pair_tiles : h->sms / 2);
       const bool wide = sel.epi_warps == 16;
+      auto go = [&](auto kernel, int threads, int smem) {
+        return launch_kernel(h->pdl != 0, kernel, pgrid, threads, smem, stream, map_a0, map_a1, *sel.map_w_half, sel.bias,
+                             static_cast<__nv_bfloat16*>(out), pp, st);
+      };
       const cudaError_t e =
-          wide ? launch_kernel(h->pdl != 0, bhstem_conv_gelu_pair_kernel<16, 6>, pgrid, PairCfg<16, 6>::THREADS,
-                               PairCfg<16, 6>::SMEM_BYTES, stream, map_a0, map_a1, *sel.map_w_half, sel.bias,
-                               static_cast<__nv_bfloat16*>(out), pp, st)
-               : launch_kernel(h->pdl != 0, bhstem_conv_gelu_pair_kernel<8, 8>, pgrid, PairCfg<8, 8>::THREADS,
-                               PairCfg<8, 8>::SMEM_BYTES, stream, map_a0, map_a1, *sel.map_w_half, sel.bias,
-                               static_cast<__nv_bfloat16*>(out), pp, st);
+          wide ? go(bhstem_conv_gelu_pair_kernel<16, 6, 2>, PairCfg<16, 6, 2>::THREADS, PairCfg<16, 6, 2>::SMEM_BYTES)
+          : sel.deep_a_ring ? go(bhstem_conv_gelu_pair_kernel<8, 6, 3>, PairCfg<8, 6, 3>::THREADS, PairCfg<8, 6, 3>::SMEM_BYTES)
+                            : go(bhstem_conv_gelu_pair_kernel<8, 8, 2>, PairCfg<8, 8, 2>::THREADS, PairCfg<8, 8, 2>::SMEM_BYTES);
       if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
       ++h->launches;
       return BHSTEM_OK;
@@ -1478,8 +1486,9 @@ int bhstem_create(int32_t c_in, int32_t d_model, const float* conv1_weight, cons
     opt_in(reinterpret_cast<const void*>(bhstem_conv_gelu_kernel<128>), Cfg<128>::SMEM_BYTES);
     opt_in(reinterpret_cast<const void*>(bhstem_conv_gelu_shared_kernel<256>), CfgShared<256>::SMEM_BYTES);
     opt_in(reinterpret_cast<const void*>(bhstem_conv_gelu_shared_kernel<128>), CfgShared<128>::SMEM_BYTES);
-    opt_in(reinterpret_cast<const void*>(bhstem_conv_gelu_pair_kernel<8, 8>), PairCfg<8, 8>::SMEM_BYTES);
-    opt_in(reinterpret_cast<const void*>(bhstem_conv_gelu_pair_kernel<16, 6>), PairCfg<16, 6>::SMEM_BYTES);
+    opt_in(reinterpret_cast<const void*>(bhstem_conv_gelu_pair_kernel<8, 8, 2>), PairCfg<8, 8>::SMEM_BYTES);
+    opt_in(reinterpret_cast<const void*>(bhstem_conv_gelu_pair_kernel<16, 6, 2>), PairCfg<16, 6>::SMEM_BYTES);
+    opt_in(reinterpret_cast<const void*>(bhstem_conv_gelu_pair_kernel<8, 6, 3>), PairCfg<8, 6, 3>::SMEM_BYTES);
     if (ea != cudaSuccess) { bhstem_destroy(h); return cuda_fail(ea, "cudaFuncSetAttribute"); }
   }
   if (rc != BHSTEM_OK) { bhstem_destroy(h); return rc; }
@@ -1512,6 +1521,11 @@ int bhstem_set_option(bhstem_handle* h, int32_t option, int64_t value) {
     for (int i = 0; i < 3; ++i) h->epi_warps[i] = static_cast<int>((value >> (8 * i)) & 0xff);
     return BHSTEM_OK;
   }
+  if (option == BHSTEM_OPT_DEEP_A_RING) {
+    if (value < 0 || value > 7) return fail(BHSTEM_EINVAL, "BHSTEM_OPT_DEEP_A_RING takes a 3-bit mask");
+    h->deep_a_ring = static_cast<int>(value);
+    return BHSTEM_OK;
+  }
   if (option == BHSTEM_OPT_SMALL_BATCH_TILES) {
     if (value != 0 && value != 1) return fail(BHSTEM_EINVAL, "BHSTEM_OPT_SMALL_BATCH_TILES takes 0 or 1");
     h->small_batch_tiles = static_cast<int>(value);
@@ -1532,7 +1546,11 @@ int bhstem_forward_stage(bhstem_handle* h, int32_t stage, const void* in, int64_
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const StageSel sel = stage == 1 ? StageSel{h->c_in, &h->map_w1, &h->map_w1_half, h->b1, 0, 0, h->epi_warps[0]}
                                   : StageSel{h->d, &h->map_w2, &h->map_w2_half, h->b2, 0, 0, h->epi_warps[1]};
-  if (pick_bn(h, stage, B, T) == 256) return launch_stage<256>(h, stage, sel, in, B, T, out, s);
+  if (pick_bn(h, stage, B, T) == 256) {
+    StageSel sel256 = sel;
+    sel256.deep_a_ring = (h->deep_a_ring >> (stage - 1)) & 1;
+    return launch_stage<256>(h, stage, sel256, in, B, T, out, s);
+  }
   // 128-column tiles: the 128-row-box weight map is the one the CTA-pair kernel uses for its halves
   const StageSel narrow{sel.c, h->bn == 256 ? sel.map_w_half : sel.map_w, sel.map_w_half, sel.bias, 0, 0, sel.epi_warps};
   return launch_stage<128>(h, stage, narrow, in, B, T, out, s);
@@ -1619,7 +1637,9 @@ int bhstem_forward_split(bhstem_handle* h, const void* x_var, const void* cond, 
   ++h->launches;
   const StageSel sel{h->n_var, &h->map_w1v, &h->map_w1v_half, bias3, 3 * h->d, h->d, h->epi_warps[2]};
   if (pick_bn(h, 1, B, T) == 256) {
-    rc = launch_stage<256>(h, 1, sel, x_var, B, T, hidden, s);
+    StageSel sel256 = sel;
+    sel256.deep_a_ring = (h->deep_a_ring >> 2) & 1;
+    rc = launch_stage<256>(h, 1, sel256, x_var, B, T, hidden, s);
   } else {
     const StageSel narrow{sel.c, h->bn == 256 ? sel.map_w_half : sel.map_w, sel.map_w_half, sel.bias, sel.bias_batch_stride,
                           sel.bias_edge_stride, sel.epi_warps};

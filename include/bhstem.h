@@ -115,6 +115,12 @@ int bhstem_forward_split(bhstem_handle* h, const void* x_var, const void* cond, 
  * on 148 SMs) runs 128-column tiles on the one-CTA kernel instead -- twice the tiles, half the work each, same
  * bits.  0: always the handle's tile width. */
 #define BHSTEM_OPT_SMALL_BATCH_TILES 4
+/* Ring depths of the CTA-pair kernel with 8 epilogue warps, a 3-bit mask (bit 0 conv1, bit 1 conv2, bit 2 split
+ * conv1 when it runs with 8 epilogue warps): 1 = 3 activation stages + 6 weight stages, 0 = 2 + 8 (same shared
+ * memory; conv1, which stages only the 136-row block, gets 5 / 3 activation stages out of the same space).  Default
+ * 3: the third activation stage covers the load latency of the streamed operand (conv2 -6 %, conv1 -4..8 %).  Same
+ * bits. */
+#define BHSTEM_OPT_DEEP_A_RING 5
 int bhstem_set_option(bhstem_handle* h, int32_t option, int64_t value);
 
 int bhstem_version(void);

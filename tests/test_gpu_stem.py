@@ -223,9 +223,12 @@ def test_kernel_variants_agree(dev, B, T):
     for variant in ("cta_pairs", "shared_taps", "tap_boxes"):
         stem.set_variant(variant)
         outs[variant] = stem(x).clone()
-    torch.cuda.synchronize()
     stem.set_variant("cta_pairs")
-    assert torch.equal(outs["cta_pairs"], outs["shared_taps"])
+    stem.set_deep_a_ring(0)                      # 2 activation + 8 weight stages instead of the default 3 + 6
+    outs["cta_pairs_2a8w"] = stem(x).clone()
+    stem.set_deep_a_ring(3)
+    torch.cuda.synchronize()
+    assert torch.equal(outs["cta_pairs"], outs["shared_taps"]) and torch.equal(outs["cta_pairs"], outs["cta_pairs_2a8w"])
     assert_close(outs["tap_boxes"], outs["shared_taps"], "tap_boxes vs shared_taps", max_frac=0.10)
     assert bool(torch.isfinite(outs["cta_pairs"].float()).all())
 
