@@ -626,13 +626,15 @@ bhstem_conv_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
 // block and tile the per-tap kernel above stages 3 x 48 KB, this one 17 (+16) KB + 3 x 32 KB.
 constexpr int A0_ROWS = 136, A0_BYTES = A0_ROWS * 128, A1_BYTES = BLOCK_M * 128;
 constexpr int ASTAGE_BYTES = A0_BYTES + A1_BYTES;          // 33 KB, a multiple of 1024
-constexpr int A_STAGES = 2, W_STAGES = 4;
+// Ring depths: 2 activation + 4 weight stages of 32 KB fill the shared memory for 256-column tiles; 128-column tiles
+// (16 KB weight stages) take 3 + 6 -- the activations are the streamed operand, see the CTA-pair kernel.
 constexpr int A_PRODUCER_WARP = 10;                        // shared-tap kernel: 11 warps
 constexpr int THREADS_SHARED = THREADS + 32;
 
 template <int BN>
 struct CfgShared {
   static constexpr int W_BYTES = BN * BLOCK_K * 2;
+  static constexpr int A_STAGES = BN == 128 ? 3 : 2, W_STAGES = BN == 128 ? 6 : 4;
   static constexpr int SMEM_BYTES = A_STAGES * ASTAGE_BYTES + W_STAGES * W_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN;
 };
@@ -651,6 +653,7 @@ bhstem_conv_gelu_shared_kernel(const __grid_constant__ CUtensorMap map_a0, const
                                const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias,
                                __nv_bfloat16* __restrict__ out, const StemProblem p, const SharedTaps st) {
   using C = CfgShared<BN>;
+  constexpr int A_STAGES = C::A_STAGES, W_STAGES = C::W_STAGES;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) unsigned long long bars[2 * A_STAGES + 2 * W_STAGES + 4];
   __shared__ uint32_t tmem_base_slot;
