@@ -16,23 +16,30 @@
 //   bhstem_conv_gelu_pair_kernel    DEFAULT for d_model % 256 == 0 (BHSTEM_VARIANT_CTA_PAIRS): CTA pairs,
 //                                   tcgen05.mma.cta_group::2, each CTA stages its 128 activation rows and HALF
 //                                   of the 256-row weight tile, which halves the per-SM weight ingest that
-//                                   bounds the one-CTA kernels (conv1: 0.31 ms against 0.34 for 46 windows).
-//   bhstem_conv_gelu_shared_kernel  BHSTEM_VARIANT_SHARED_TAPS, and d_model % 256 != 0.  One staged block of rows
-//                                   per 64-channel step feeds all taps through row-shifted descriptors;
-//                                   separate weight / activation rings.
+//                                   bounds the one-CTA kernels.  Instantiations <epilogue warps, weight stages,
+//                                   activation stages>: <8, 6, 3> (default: the activations are the streamed
+//                                   operand, a third stage of look-ahead took the tensor pipe from 83 to 94 %
+//                                   active), <8, 8, 2> (A/B), <16, 6, 2> (the split conv1, epilogue-bound).
+//   bhstem_conv_gelu_shared_kernel  BHSTEM_VARIANT_SHARED_TAPS, d_model % 256 != 0, and launches with too few
+//                                   256-column tiles to fill the SMs (128-column instantiation).  One staged
+//                                   block of rows per 64-channel step feeds all taps through row-shifted
+//                                   descriptors; separate weight / activation rings.
 //   bhstem_conv_gelu_kernel         BHSTEM_VARIANT_TAP_BOXES: one TMA box per (tap, channel step); the first
 //                                   working version, kept as the A/B baseline.
 // One persistent CTA per SM, warp-specialised (default kernel: 352 threads):
 //   warp 0      weight producer       one thread: TMA box BN rows x 64 ch per (channel step, tap), 128-byte
-//                                      swizzle, 4-stage mbarrier ring
-//   warp 10     activation producer   one thread: the staged block(s) of rows per channel step, 2-stage ring
+//                                      swizzle, mbarrier ring
+//   warp 10     activation producer   one thread: the staged block(s) of rows per channel step, its own ring
 //   warp 1      MMA issuer            one thread issues tcgen05.mma.kind::f16 (128 x BN x 16, bf16 -> fp32)
 //                                      into one of two TMEM accumulator stages; tcgen05.commit frees the
 //                                      shared-memory stages / publishes the accumulator
 //   warps 2-9   epilogue              two per TMEM lane quarter, half the columns each: tcgen05.ld 32 lanes x
-//                                      32 columns -> + bias -> round to bf16 (the conv output) -> erf GELU in
-//                                      fp32 -> bf16 -> staged -> 64-byte row segments to HBM; overlaps the
-//                                      next tile's MMAs through the second accumulator stage
+//                                      32 columns -> + bias (staged per tile in shared memory) -> round to bf16
+//                                      (the conv output) -> erf GELU in fp32 on packed pairs (FFMA2) -> bf16 ->
+//                                      staged -> 64-byte row segments to HBM; overlaps the next tile's MMAs
+//                                      through the second accumulator stage
+// bhstem_forward_split adds bhstem_cond_bias_kernel in front of conv1: the reference's time-constant conditioning
+// channels folded into a per-window bias, conv1 over the time-varying channels only (see that kernel).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
