@@ -1113,18 +1113,22 @@ bhstem_conv_gelu_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const _
 // which the conv1 epilogue adds to the accumulator of the n_var time-varying channels: 3 * n_var instead of
 // 3 * C products per output element (80 of 464 channels at the reference's dims: 5.8x fewer), and the
 // [B][T][C] encoder input is never materialised.
-// One warp per output channel, 8 channels per CTA; blockIdx.y owns a contiguous share of the windows and walks
-// it BIAS_BCH windows at a time: their conditioning vectors are converted to fp32 once into shared memory, a
-// lane keeps the 3 x 8 weights of its 16-byte piece in registers (converted once per chunk) and multiplies
-// them with all BIAS_BCH vectors -- 24 FFMA per 2 LDS.128, no conversions in the inner loop.
+// A group of G lanes per output channel (G = 32, 16 or 8: the one that leaves the fewest lanes idle for the
+// channel count -- 384 channels are 48 sixteen-byte pieces: three full rounds of 16 lanes), 8 warps per CTA;
+// blockIdx.y owns a contiguous share of the windows and walks it BIAS_BCH windows at a time: their conditioning
+// vectors are converted to fp32 once into shared memory, a lane keeps the 3 x 8 weights of its 16-byte piece in
+// registers (converted once) and multiplies them with all BIAS_BCH vectors -- 24 FFMA per 2 LDS.128, no
+// conversions in the inner loop -- and the sums are reduced over the group with log2(G) shuffle rounds.
 constexpr int BIAS_WARPS = 8, BIAS_BCH = 16;
+template <int G>
 __global__ void __launch_bounds__(BIAS_WARPS * 32)
 bhstem_cond_bias_kernel(const __nv_bfloat16* __restrict__ w /* [3][D][C] */, const float* __restrict__ bias,
                         const __nv_bfloat16* __restrict__ cond /* [B][C - n_var] */, float* __restrict__ bias3,
                         int batches, int d, int c, int n_var, int b_per_cta) {
   extern __shared__ float xs[];                             // [BIAS_BCH][n_cond] fp32
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = blockIdx.x * BIAS_WARPS + warp;
+  const int sub = lane % G;                                 // my place in the group
+  const int n = (blockIdx.x * BIAS_WARPS + warp) * (32 / G) + lane / G;
   const bool active = n < d;
   const int n_cond = c - n_var, vecs = n_cond >> 3;         // n_var % 8 == 0 and C % 8 == 0: whole 16-byte pieces
   const int b_begin = blockIdx.y * b_per_cta, b_end = min(batches, b_begin + b_per_cta);
@@ -1134,10 +1138,10 @@ bhstem_cond_bias_kernel(const __nv_bfloat16* __restrict__ w /* [3][D][C] */, con
   pdl_launch_dependents();
   const float bn = active ? bias[n] : 0.f;
   uint4 w_first[3] = {};
-  if (active && lane < vecs) {
+  if (active && sub < vecs) {
 #pragma unroll
     for (int tap = 0; tap < 3; ++tap)
-      w_first[tap] = __ldg(reinterpret_cast<const uint4*>(w + (static_cast<size_t>(tap) * d + n) * c + n_var) + lane);
+      w_first[tap] = __ldg(reinterpret_cast<const uint4*>(w + (static_cast<size_t>(tap) * d + n) * c + n_var) + sub);
   }
   pdl_wait();
   for (int b0 = b_begin; b0 < b_end; b0 += BIAS_BCH) {
@@ -1154,51 +1158,64 @@ bhstem_cond_bias_kernel(const __nv_bfloat16* __restrict__ w /* [3][D][C] */, con
                            __uint_as_float(xv.w << 16), __uint_as_float(xv.w & 0xffff0000u));
     }
     __syncthreads();
-    if (!active) continue;
     float acc[BIAS_BCH][3];
 #pragma unroll
     for (int bb = 0; bb < BIAS_BCH; ++bb) acc[bb][0] = acc[bb][1] = acc[bb][2] = 0.f;
-    for (int v = lane; v < vecs; v += 32) {
-      float wf[3][8];
+    if (active) {
+      for (int v = sub; v < vecs; v += G) {
+        float wf[3][8];
 #pragma unroll
-      for (int tap = 0; tap < 3; ++tap) {
-        const uint4 wv = v == lane ? w_first[tap]
-                                   : __ldg(reinterpret_cast<const uint4*>(w + (static_cast<size_t>(tap) * d + n) * c + n_var) + v);
-        const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+        for (int tap = 0; tap < 3; ++tap) {
+          const uint4 wv = v == sub ? w_first[tap]
+                                    : __ldg(reinterpret_cast<const uint4*>(w + (static_cast<size_t>(tap) * d + n) * c + n_var) + v);
+          const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {                        // bf16 -> fp32 is a shift; the products are exact in fp32
-          wf[tap][2 * i] = __uint_as_float(ww[i] << 16);
-          wf[tap][2 * i + 1] = __uint_as_float(ww[i] & 0xffff0000u);
+          for (int i = 0; i < 4; ++i) {                      // bf16 -> fp32 is a shift; the products are exact in fp32
+            wf[tap][2 * i] = __uint_as_float(ww[i] << 16);
+            wf[tap][2 * i + 1] = __uint_as_float(ww[i] & 0xffff0000u);
+          }
+        }
+#pragma unroll
+        for (int bb = 0; bb < BIAS_BCH; ++bb) {
+          const float4 x0 = *reinterpret_cast<const float4*>(xs + bb * n_cond + v * 8);
+          const float4 x1 = *reinterpret_cast<const float4*>(xs + bb * n_cond + v * 8 + 4);
+          const float xf[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+          for (int tap = 0; tap < 3; ++tap)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[bb][tap] = fmaf(wf[tap][i], xf[i], acc[bb][tap]);
         }
       }
-#pragma unroll
-      for (int bb = 0; bb < BIAS_BCH; ++bb) {
-        const float4 x0 = *reinterpret_cast<const float4*>(xs + bb * n_cond + v * 8);
-        const float4 x1 = *reinterpret_cast<const float4*>(xs + bb * n_cond + v * 8 + 4);
-        const float xf[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-        for (int tap = 0; tap < 3; ++tap)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[bb][tap] = fmaf(wf[tap][i], xf[i], acc[bb][tap]);
-      }
     }
+    // every lane takes part in the shuffles (a warp may hold active and inactive groups)
 #pragma unroll
     for (int bb = 0; bb < BIAS_BCH; ++bb)
 #pragma unroll
       for (int tap = 0; tap < 3; ++tap)
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) acc[bb][tap] += __shfl_xor_sync(0xffffffffu, acc[bb][tap], off);
-    if (lane < nb) {                                        // lane bb writes window b0 + bb (every lane holds every sum)
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        for (int off = G / 2; off > 0; off >>= 1) acc[bb][tap] += __shfl_xor_sync(0xffffffffu, acc[bb][tap], off);
+    if (active) {
 #pragma unroll
-      for (int bb = 0; bb < BIAS_BCH; ++bb)
-        if (bb == lane) { s0 = acc[bb][0]; s1 = acc[bb][1]; s2 = acc[bb][2]; }
-      float* o = bias3 + static_cast<size_t>(b0 + lane) * 3 * d + n;
-      o[0] = bn + ((s0 + s1) + s2);
-      o[d] = bn + (s1 + s2);
-      o[2 * d] = bn + (s0 + s1);
+      for (int bb = 0; bb < BIAS_BCH; ++bb) {               // lane `bb % G` of the group writes window b0 + bb
+        if (bb % G == sub && bb < nb) {
+          float* o = bias3 + static_cast<size_t>(b0 + bb) * 3 * d + n;
+          o[0] = bn + ((acc[bb][0] + acc[bb][1]) + acc[bb][2]);
+          o[d] = bn + (acc[bb][1] + acc[bb][2]);
+          o[2 * d] = bn + (acc[bb][0] + acc[bb][1]);
+        }
+      }
     }
   }
+}
+
+// lanes per output channel: the group size that wastes the fewest lane-rounds, the larger one on a tie
+int bias_group(int vecs) {
+  int best = 32, waste = ((vecs + 31) / 32) * 32;
+  for (int g : {16, 8}) {
+    const int wst = ((vecs + g - 1) / g) * g;
+    if (wst < waste) { best = g; waste = wst; }
+  }
+  return best;
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -1585,8 +1602,11 @@ int bhstem_prepare_split(bhstem_handle* h, int32_t n_var) {
   {
     const size_t smem = static_cast<size_t>(BIAS_BCH) * (h->c_in - n_var) * sizeof(float);
     if (smem > 200 * 1024) return fail(BHSTEM_EINVAL, "too many time-constant channels for the folded-bias kernel (c_in - n_var <= 6400)");
-    const cudaError_t ea = cudaFuncSetAttribute(reinterpret_cast<const void*>(bhstem_cond_bias_kernel),
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t ea = cudaSuccess;
+    for (const void* fn : {reinterpret_cast<const void*>(bhstem_cond_bias_kernel<32>),
+                           reinterpret_cast<const void*>(bhstem_cond_bias_kernel<16>),
+                           reinterpret_cast<const void*>(bhstem_cond_bias_kernel<8>)})
+      if (ea == cudaSuccess) ea = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute");
   }
   __nv_bfloat16* w = nullptr;
@@ -1620,7 +1640,11 @@ int bhstem_forward_split(bhstem_handle* h, const void* x_var, const void* cond, 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   {
     // about two CTAs per SM, each owning a multiple of BIAS_BCH windows
-    const int gx = (h->d + BIAS_WARPS - 1) / BIAS_WARPS;
+    // few windows: the launch is latency-bound, so the widest groups (most CTAs) win (one window: 7.4 us with
+    // 32-lane groups against 9.6 with 16); many windows: the fewest idle lane-rounds (46 windows: 11.3 against 15.0 us)
+    const int g = B <= BIAS_BCH ? 32 : bias_group((h->c_in - h->n_var) / 8);
+    const int per_cta = BIAS_WARPS * (32 / g);
+    const int gx = (h->d + per_cta - 1) / per_cta;
     const int chunks = static_cast<int>((B + BIAS_BCH - 1) / BIAS_BCH);
     int by = (2 * h->sms + gx - 1) / gx;
     if (by > chunks) by = chunks;
@@ -1638,7 +1662,8 @@ int bhstem_forward_split(bhstem_handle* h, const void* x_var, const void* cond, 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = h->pdl ? 1 : 0;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, bhstem_cond_bias_kernel, static_cast<const __nv_bfloat16*>(h->w1),
+    auto kernel = g == 32 ? bhstem_cond_bias_kernel<32> : g == 16 ? bhstem_cond_bias_kernel<16> : bhstem_cond_bias_kernel<8>;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<const __nv_bfloat16*>(h->w1),
                                              static_cast<const float*>(h->b1), static_cast<const __nv_bfloat16*>(cond), bias3,
                                              static_cast<int>(B), static_cast<int>(h->d), static_cast<int>(h->c_in),
                                              static_cast<int>(h->n_var), b_per_cta);
