@@ -153,3 +153,13 @@ def test_stem_sass_uses_tcgen05_tmem_and_tma():
     for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UTCBAR"):
         assert mnemonic in sass, mnemonic
     assert "HMMA.16816" not in sass            # no legacy mma.sync path
+    # the epilogue's GELU runs on packed fp32 pairs, and the TMEM hand-back is a relaxed arrival: the only
+    # MEMBARs left in the CTA-pair kernels belong to the two cluster barriers (start / end of the kernel)
+    for mnemonic in ("FFMA2", "FMUL2", "FADD2"):
+        assert mnemonic in sass, mnemonic
+    kernels = sass.split("Function : ")[1:]
+    pair = [k for k in kernels if "pair_kernel" in k.split("\n", 1)[0]]
+    assert len(pair) >= 3                      # <8, 6, 3>, <8, 8, 2>, <16, 6, 2>
+    for k in pair:
+        assert k.count("MEMBAR.ALL.CTA") <= 2, k.split("\n", 1)[0]
+    assert any("cond_bias_kernel" in k.split("\n", 1)[0] for k in kernels)
