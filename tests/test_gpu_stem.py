@@ -563,3 +563,25 @@ def test_kernel_variants_agree_on_the_split_stem(dev, B, T):
     torch.cuda.synchronize()
     assert torch.equal(outs["cta_pairs"], outs["shared_taps"]) and torch.equal(outs["cta_pairs"], outs["cta_pairs_8"])
     assert_close(outs["tap_boxes"], outs["shared_taps"], "tap_boxes vs shared_taps (split)", max_frac=0.10)
+
+
+def test_plain_c_host_program_drives_the_split_serving_chain(dev, tmp_path):
+    """examples/c_abi_stem_demo.c: a C program (no Python, no torch) runs frontend -> stem through both C ABIs in
+    the full and the split form and checks that they agree within the stem's tolerance."""
+    import os
+    import shutil
+    import subprocess
+    from tests.conftest import ROOT
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available on this box")
+    from beatheritage_b200 import build as _build
+    _build.build()
+    exe = str(tmp_path / "c_abi_stem_demo")
+    libdir = os.path.join(ROOT, "beatheritage_b200")
+    subprocess.run([nvcc, "-x", "cu", os.path.join(ROOT, "examples", "c_abi_stem_demo.c"), "-I", os.path.join(ROOT, "include"),
+                    "-L", libdir, "-lbhmel", "-lbhstem", "-Xlinker", f"-rpath={libdir}", "-o", exe], check=True,
+                   capture_output=True)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "frames per window: 512" in res.stdout and "split vs full" in res.stdout
