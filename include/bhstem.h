@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define BHSTEM_VERSION 1
+#define BHSTEM_VERSION 2   /* 2: bhstem_prepare_split / bhstem_forward_split, options 3-5 */
 
 #define BHSTEM_OK 0
 #define BHSTEM_EINVAL 1

@@ -126,7 +126,7 @@ def test_stem_header_binding_and_exports_agree(stem_lib):
     assert stem_declared_functions() == sorted(_stem_lib.SIGNATURES)
     for name in stem_declared_functions():
         assert hasattr(stem_lib, name), f"libbhstem.so does not export {name}"
-    assert stem_lib.bhstem_version() == 1
+    assert stem_lib.bhstem_version() == 2
 
 
 def test_stem_create_rejects_bad_parameters_before_touching_cuda(stem_lib):
